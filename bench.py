@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""
+bench.py -- SSHG yield points/s on the "synthetic scale" sweep of BASELINE.json
+(20k energies x 181 theta x 721 phi x 4 polarisations, random 27-component chi2; configs[4]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one evaluation of the whole cube by the fused yield kernel (K2), the spectra already
+resident in HBM; with N ranks the theta axis is cut into N contiguous shards (no data-path
+collective, strong scaling: the cube is fixed).  Rank 0 prints ONE JSON line.
+
+  value      whole-job points/s, device-resident (CUDA events, max over ranks)
+  e2e        the same metric through the host-buffer C-ABI call (H2D of the spectra, kernel, D2H of the
+             yields into pinned host memory inside the timed region) on a theta sub-sample of each shard
+  roofline   HBM bound: algorithmic bytes (8 B per point, written once) / average K2 launch time
+  cpu_baseline  the NumPy oracle port (oracle/shg_oracle.py) on the box's host cores, bounded sample
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the reference is pure
+Python and /root/reference does not exist on the GPU box) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+N_ENERGY, N_THETA, N_PHI = 20000, 181, 721
+WORKLOAD = "synthetic scale (BASELINE.json configs[4]): 20000 E x 181 theta x 721 phi x 4 pol, d = 10 nm, seed 20250"
+METRIC = "SSHG yield points/sec (E x theta x phi x pol)"
+E2E_THETAS = 8            # thetas of each rank's shard that the end-to-end leg evaluates per step
+CPU_PHI_CHUNK = 8         # phi values per CPU task (keeps NumPy temporaries ~100 MB)
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU leg: the oracle port fanned over the host cores
+# ------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init():
+    from shgyield_b200.synthetic import config5
+    from oracle import shg_oracle as orc
+    cfg = config5(N_ENERGY, N_THETA, N_PHI)
+    _CPU["cfg"] = cfg
+    _CPU["orc"] = orc
+    _CPU["e1"] = {"M%d" % (m + 1): cfg["eps1w"][m] for m in range(3)}
+    _CPU["e2"] = {"M%d" % (m + 1): cfg["eps2w"][m] for m in range(3)}
+    _CPU["chi"] = {k: cfg["chi2"][i] for i, k in enumerate(orc.CHI2_KEYS)}
+
+
+def _cpu_task(task):
+    """One theta x CPU_PHI_CHUNK phi x all energies x 4 polarisations; returns the point count."""
+    if not _CPU:
+        _cpu_init()
+    it, ip = task
+    cfg, orc = _CPU["cfg"], _CPU["orc"]
+    phi = cfg["phi"][ip:ip + CPU_PHI_CHUNK]
+    y = orc.yield_points(cfg["energy"], _CPU["e1"], _CPU["e2"], _CPU["chi"], cfg["theta"][it], phi[:, None], 10.0,
+                         True, orc.SCIPY_1_18_CONSTANTS)
+    return sum(int(np.asarray(y[p]).size) for p in ("pp", "ps", "sp", "ss"))
+
+
+def _cpu_tasks(n, offset=0):
+    tasks = []
+    for k in range(n):
+        j = offset + k
+        tasks.append(((7 * j) % (N_THETA - 1), (CPU_PHI_CHUNK * j) % (N_PHI - CPU_PHI_CHUNK)))
+    return tasks
+
+
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+class CpuPool:
+    """Process pool over the host cores (fork; created before CUDA is initialised)."""
+
+    def __init__(self, workers):
+        import multiprocessing as mp
+        self.workers = workers
+        self.pool = mp.get_context("fork").Pool(workers, initializer=_cpu_init) if workers > 1 else None
+        if self.pool is None:
+            _cpu_init()
+
+    def run(self, tasks):
+        t0 = time.perf_counter()
+        if self.pool is None:
+            pts = sum(_cpu_task(t) for t in tasks)
+        else:
+            pts = sum(self.pool.map(_cpu_task, tasks, chunksize=1))
+        return pts, time.perf_counter() - t0
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+
+
+def cpu_baseline(target_s=12.0):
+    """Bounded sample on all cores: calibrate with one task per worker, then ~target_s of work."""
+    cores = cpu_cores()
+    pool = CpuPool(cores)
+    try:
+        pool.run(_cpu_tasks(cores))                                  # warm-up (imports, page faults)
+        pts, dt = pool.run(_cpu_tasks(cores, cores))
+        rounds = max(1, min(40, int(target_s / max(dt, 1e-3))))
+        pts, dt = pool.run(_cpu_tasks(cores * rounds, 2 * cores))
+    finally:
+        pool.close()
+    return {"value": pts / dt, "unit": "points/s", "cores": cores, "kind": "port",
+            "sample": "%d tasks of 1 theta x %d phi x %d E x 4 pol (%.3g points) of the same workload, "
+                      "NumPy oracle port of shg.py, one process per core" % (cores * rounds, CPU_PHI_CHUNK, N_ENERGY, pts),
+            "seconds": dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = cpu_cores()
+    pool = CpuPool(cores)
+    tasks_per_step = cores
+    try:
+        for w in range(args.warmup):
+            pool.run(_cpu_tasks(tasks_per_step, w * tasks_per_step))
+        t0 = time.perf_counter()
+        pts = 0
+        for s in range(args.steps):
+            p, _ = pool.run(_cpu_tasks(tasks_per_step, (args.warmup + s) * tasks_per_step))
+            pts += p
+        dt = time.perf_counter() - t0
+    finally:
+        pool.close()
+    value = pts / dt
+    sample = "each step = %d tasks of 1 theta x %d phi x %d E x 4 pol (%.3g points) of the workload" % (
+        tasks_per_step, CPU_PHI_CHUNK, N_ENERGY, pts / max(args.steps, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "host": "NumPy oracle port of the reference's shg.py (pure Python "
+                       "reference; /root/reference is not on the GPU box)"},
+            "cpu_baseline": {"value": value, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU leg
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                smax.append(float(c[2]))
+                power.append(float(c[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": float(max(power))}
+
+
+def measured_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (copy, read+write, burst)"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json absent)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+        raise SystemExit("WORLD_SIZE %d != --gpus %d" % (world, args.gpus))
+
+    # CPU baseline first: the fork pool must exist before CUDA is initialised in this process
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.cpu_seconds)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from shgyield_b200 import _lib, grid
+    from shgyield_b200.shg import physical_constants
+    from shgyield_b200.synthetic import config5
+
+    cfg = config5(N_ENERGY, N_THETA, N_PHI)
+    consts = physical_constants()
+    ctx = _lib.context(local)
+    t_lo, t_hi = grid.shard_bounds(N_THETA, world, rank)
+    put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = {k: put(v) for k, v in cfg.items()}
+    out = torch.empty((t_hi - t_lo, 1, 4, N_PHI, N_ENERGY), dtype=torch.float64, device=dev)
+    my_pts = out.numel()
+    total_pts = N_THETA * 4 * N_PHI * N_ENERGY
+
+    def step():
+        grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                               out=out, consts=consts, t_range=(t_lo, t_hi))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # roofline denominators measured in the same run (rank 0 only; before the timed region)
+    peaks = {}
+    if rank == 0:
+        import ctypes as C
+        v = C.c_double()
+        _lib.check(ctx.lib.sshg_peak_store(ctx.handle, 8 << 30, 5, C.byref(v)), ctx.lib)
+        peaks["store_gbs"] = v.value
+        _lib.check(ctx.lib.sshg_peak_dfma(ctx.handle, 5, C.byref(v)), ctx.lib)
+        peaks["fp64_tflops"] = v.value
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_start.record()
+    for a, b in ev:
+        a.record()
+        step()
+        b.record()
+    t_end.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launches - launches0
+    total_ms = t_start.elapsed_time(t_end)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+
+    # ---- end to end: host buffers through the C ABI (H2D spectra + kernel + D2H yields), per step ----
+    n_e2e = min(E2E_THETAS, t_hi - t_lo)
+    e2e_range = (t_lo, t_lo + n_e2e)
+    host_out = _lib.pinned_empty((n_e2e, 1, 4, N_PHI, N_ENERGY))
+    host_in = {k: np.ascontiguousarray(v) for k, v in cfg.items()}
+
+    def e2e_step():
+        grid.yield_grid_host(host_in["energy"], host_in["theta"], host_in["phi"], host_in["thick"], host_in["eps1w"],
+                             host_in["eps2w"], host_in["chi2"], consts=consts, t_range=e2e_range, out=host_out)
+
+    ctx.set_stream(None)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_check = float(host_out[0, 0, :, 0, :].sum())
+    h2d = sum(int(v.nbytes) for v in host_in.values())
+    d2h = int(host_out.nbytes)
+    e2e_pts = n_e2e * 4 * N_PHI * N_ENERGY
+
+    # ---- reduce over ranks (max time; sums of points) ----------------------------------------------
+    stats = torch.tensor([total_ms, e2e_s, float(np.mean(step_ms))], dtype=torch.float64, device=dev)
+    counts = torch.tensor([float(my_pts), float(e2e_pts), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    total_ms, e2e_s, mean_step_ms = (float(x) for x in stats.cpu())
+    sum_pts, sum_e2e_pts, sum_launches = (float(x) for x in counts.cpu())
+    assert int(sum_pts) == total_pts
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        value = total_pts * args.steps / (total_ms * 1e-3)
+        k2_ms = float(np.mean(step_ms))                      # this rank's K2 launch (+ the 1-CTA phi-table kernel)
+        achieved = 8.0 * my_pts / (k2_ms * 1e-3) / 1e9
+        flops = 28.0 * my_pts + 1000.0 * (t_hi - t_lo) * N_ENERGY
+        line = {
+            "metric": METRIC, "value": value, "unit": "points/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": "theta shards x%d, no data-path collective" % world,
+                       "l2": "each step writes %.1f GB per GPU (>> 126 MB L2); inputs 7.7 MB" % (8e-9 * my_pts),
+                       "layout": "[theta][d][pol][phi][E] f64"},
+            "e2e": {"value": sum_e2e_pts * e2e_steps / e2e_s, "unit": "points/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "sample": "sshg_yield with host buffers on the first %d thetas of each rank's shard "
+                              "(%.3g points/step/GPU), pinned result buffer, %d steps" % (n_e2e, e2e_pts, e2e_steps),
+                    "checksum": e2e_check},
+            "gpu_launches": int(sum_launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "kernel": "yield_grid_kernel (K2); algorithmic bytes = 8 B x %.4g points per launch; "
+                                   "duration = mean CUDA-event time of the %d timed launches on rank 0 (%.3f ms)"
+                                   % (my_pts, args.steps, k2_ms),
+                         "store_peak_gbs_measured": peaks.get("store_gbs"),
+                         "fp64_peak_tflops_measured": peaks.get("fp64_tflops"),
+                         "alg_fp64_tflops": flops / (k2_ms * 1e-3) / 1e12},
+            "cpu_baseline": cpu,
+            "ms_per_step_device_max": mean_step_ms,
+        }
+        print(json.dumps(line), flush=True)
+    _lib.pinned_free(host_out)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.steps < 1:
+        raise SystemExit("--steps must be >= 1")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

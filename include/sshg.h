@@ -1,0 +1,158 @@
+/*
+ * sshg.h -- C ABI of libsshg.so: SSHG yield evaluation on NVIDIA B200 (sm_100a), FP64.
+ *
+ * Drop-in boundary for ONE path of roguephysicist/SHGYield: `shgyield/shg.py::shgyield`
+ * (reference shg.py:381-437) and the helpers it calls.  The reference has no FFI of its own
+ * (it is 437 lines of NumPy/SciPy); each entry point below names the reference lines it
+ * replaces.  A maintainer binds these with ctypes -- the stub is shown in INTEGRATION.md and
+ * shipped as shgyield_b200/_lib.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; complex128 arrays are interleaved (re, im) doubles, i.e.
+ *     the memory of a C-contiguous NumPy complex128 array;
+ *   - every function returns 0 (SSHG_OK) or a negative sshg_status; the message of the last
+ *     failure on the calling thread is sshg_last_error();
+ *   - `where` says which pointers live on the device: SSHG_HOST (0): all host;
+ *     SSHG_IN_DEVICE: inputs are device pointers; SSHG_OUT_DEVICE: `out` is a device pointer;
+ *     SSHG_DEVICE = both.  Host calls are synchronous; when `out` is a device pointer the call
+ *     is asynchronous and ordered on the context's stream (sshg_ctx_stream / sshg_ctx_sync);
+ *   - the caller owns every buffer; the library never keeps a caller pointer after returning;
+ *   - a context is bound to one device and is not thread-safe; use one per thread / rank.
+ *   - there is NO CPU fallback: without a CUDA device sshg_ctx_create fails with SSHG_ECUDA.
+ */
+#ifndef SSHG_H_
+#define SSHG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SSHG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SSHG_API __attribute__((visibility("default")))
+#else
+#define SSHG_API
+#endif
+
+typedef enum {
+    SSHG_OK = 0,
+    SSHG_EINVAL = -1,   /* bad argument (Python shim raises ValueError)  */
+    SSHG_ECUDA = -2,    /* CUDA runtime / launch failure (RuntimeError)    */
+    SSHG_ENOMEM = -3    /* host or device allocation failed (MemoryError)  */
+} sshg_status;
+
+enum { SSHG_HOST = 0, SSHG_IN_DEVICE = 1, SSHG_OUT_DEVICE = 2, SSHG_DEVICE = 3 };
+
+/* polarisation order of every output: index 0..3 = pp, ps, sp, ss
+ * (first letter = incoming 1w field, second = outgoing 2w field; reference shg.py:433-436) */
+enum { SSHG_PP = 0, SSHG_PS = 1, SSHG_SP = 2, SSHG_SS = 3 };
+
+/* canonical order of the 18 chi2 rows (reference shg.py:66-133):
+ * xxx xyy xzz xyz xxz xxy  yxx yyy yzz yyz yxz yxy  zxx zyy zzz zyz zxz zxy */
+#define SSHG_NCHI 18
+
+typedef struct sshg_ctx sshg_ctx;
+
+/* Physical constants and bug-compatibility switches shared by the yield entry points.
+ * The reference reads the constants from scipy.constants at run time (shg.py:181,194,429-430);
+ * the caller passes the same values so results do not drift with the CODATA edition. */
+typedef struct {
+    double h_eVs;            /* "Planck constant in eV s"            (shg.py:181,194) */
+    double hbar_eVs;         /* "Planck constant over 2 pi in eV s"  (shg.py:429)     */
+    double eps0;             /* vacuum permittivity, F/m             (shg.py:430)     */
+    double c;                /* speed of light, m/s                  (shg.py:181,430) */
+    int32_t mref;            /* 1: multiple reflections on (shg.py:179,192); 0: R^M = r^{lb} */
+    int32_t sinc_normalized; /* 1: np.sinc = sin(pi x)/(pi x) as shipped (shg.py:183); 0: sin(x)/x */
+    int32_t zzz_phi_quirk;   /* 1: chi_zzz term of r_pP times sin(phi)^3 as shipped (shg.py:269);
+                                0: sin(theta)^3 (Eq. 50 of PRB 94, 115314)          */
+    int32_t reserved;
+} sshg_physics;
+
+/* A rectangular sweep: energy x theta x phi x thickness (x 4 polarisations).
+ * Replaces the reference's NumPy broadcast over rad_pp/ps/sp/ss + prefactor
+ * (shg.py:201-378, 428-436 with sigma_out = 0).
+ * Output layout: out[t - t0][d - d0][pol][p][e], double, e contiguous;
+ * only the shard t in [t0,t1), d in [d0,d1) is computed and stored. */
+typedef struct {
+    int64_t nE, nT, nP, nD;
+    const double* energy_eV;  /* [nE]                                                   */
+    const double* theta_deg;  /* [nT]  angle of incidence                               */
+    const double* phi_deg;    /* [nP]  azimuth                                          */
+    const double* thick_nm;   /* [nD]  thin-layer thickness                             */
+    const double* eps1w;      /* [3][nE][2]  eps(w)  of M1 (vacuum), M2 (layer), M3 (bulk) */
+    const double* eps2w;      /* [3][nE][2]  eps(2w)                                    */
+    const double* chi2;       /* [18][nE][2] chi2 rows in canonical order, ALREADY rotated */
+    sshg_physics phys;
+    int64_t t0, t1, d0, d1;   /* shard (t1 = d1 = 0 means the full range)              */
+} sshg_problem;
+
+/* A list of independent points (the general NumPy-broadcast shape of shgyield()):
+ * point i uses spectra column eidx[i].  Output layout out[pol][i]. */
+typedef struct {
+    int64_t n;                /* number of points                                        */
+    int64_t nE;               /* number of spectra columns                               */
+    const double* energy_eV;  /* [nE]                                                   */
+    const int64_t* eidx;      /* [n]   column of each point, 0 <= eidx < nE             */
+    const double* theta_deg;  /* [n]                                                    */
+    const double* phi_deg;    /* [n]                                                    */
+    const double* thick_nm;   /* [n]                                                    */
+    const double* eps1w;      /* [3][nE][2]                                             */
+    const double* eps2w;      /* [3][nE][2]                                             */
+    const double* chi2;       /* [18][nE][2], already rotated                           */
+    sshg_physics phys;
+} sshg_points;
+
+/* ---- library / context ------------------------------------------------------------------- */
+SSHG_API int sshg_abi_version(void);
+SSHG_API const char* sshg_last_error(void);               /* thread-local, valid until the next call */
+SSHG_API int sshg_device_count(int* count);
+SSHG_API int sshg_ctx_create(int device, sshg_ctx** out); /* owns one stream + scratch               */
+SSHG_API void sshg_ctx_destroy(sshg_ctx* ctx);
+/* adopt a caller's cudaStream_t (e.g. torch's current stream); NULL selects the context's own
+ * stream again; pass cudaStreamLegacy ((void*)1) to target the legacy default stream */
+SSHG_API int sshg_ctx_set_stream(sshg_ctx* ctx, void* cuda_stream);
+SSHG_API void* sshg_ctx_stream(sshg_ctx* ctx);
+SSHG_API int sshg_ctx_sync(sshg_ctx* ctx);
+SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by this context so far */
+SSHG_API int sshg_host_alloc(void** ptr, int64_t bytes);  /* page-locked host memory for fast D2H    */
+SSHG_API int sshg_host_free(void* ptr);
+
+/* ---- Gaussian broadening: replaces broad / broadC (shg.py:26-35), i.e.
+ * scipy.ndimage.gaussian_filter along one axis: taps exp(-k^2/(2 sigma^2))/sum,
+ * radius int(4 sigma + 0.5), 'reflect' boundary; sigma <= 1e-15 copies.
+ * `rows` signals of `n` samples; sample j of row r is at in[r*row_stride + j*elem_stride]
+ * (same addressing for out; in != out).  sigma is in SAMPLES (shg.py:13). */
+SSHG_API int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_t rows, int64_t n,
+                 int64_t row_stride, int64_t elem_stride, double sigma, int where);
+
+/* ---- in-plane rotation of chi2: replaces rotate (shg.py:63-134).
+ * chi_in / chi_out: [18][nE][2]; gamma_deg as passed to shgyield().  xxy_quirk = 1 keeps the
+ * reference's sign on the chi_yyy contribution to chi_xxy (shg.py:92). */
+SSHG_API int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, int64_t nE,
+                double gamma_deg, int xxy_quirk, int where);
+
+/* ---- cubic interpolating (not-a-knot) spline resampling: replaces spline / splineC /
+ * splineEPS (shg.py:38-55, 423-424), i.e. InterpolatedUnivariateSpline(x, y, ext=2)(xq).
+ * y: [rows][n] sampled on the common axis x[n]; out: [rows][nq].  Queries outside
+ * [x[0], x[n-1]] fail with SSHG_EINVAL (ext=2 raises ValueError). */
+SSHG_API int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
+                         const double* xq, int64_t nq, double* out, int where);
+
+/* ---- the fused yield kernel: Fresnel factors + three-layer multiple reflection + chi2
+ * contraction + |Gamma r|^2 (shg.py:137-378, 428-436).  */
+SSHG_API int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where);
+SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
+
+/* ---- measurement helpers used by bench.py for the roofline denominators ---------------- */
+/* streaming 128-bit stores over `bytes` of device memory; returns achieved GB/s (best of iters) */
+SSHG_API int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs);
+/* register-resident DFMA loop on all SMs; returns achieved FP64 TFLOP/s (best of iters) */
+SSHG_API int sshg_peak_dfma(sshg_ctx* ctx, int iters, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSHG_H_ */

@@ -1,0 +1,185 @@
+// Context management, error reporting and host/device staging for libsshg.so.
+#include "sshg_internal.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void sshg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sshg_cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    const char* base = strrchr(file, '/');
+    sshg_set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), base ? base + 1 : file, line, what);
+    return e == cudaErrorMemoryAllocation ? SSHG_ENOMEM : SSHG_ECUDA;
+}
+
+int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (slot < 0 || slot >= SSHG_NSCRATCH) {
+        sshg_set_error("internal: scratch slot %d", slot);
+        return SSHG_EINVAL;
+    }
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            // the old buffer may still be in use by work queued on the streams
+            SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+            SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+            SSHG_CUDA(cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t cap = bytes + bytes / 4;
+        cap = (cap + 255) & ~(size_t)255;
+        cudaError_t e = cudaMalloc(&ctx->scratch[slot], cap);
+        if (e != cudaSuccess) {
+            cap = (bytes + 255) & ~(size_t)255;
+            e = cudaMalloc(&ctx->scratch[slot], cap);
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            sshg_set_error("device allocation of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+            return SSHG_ENOMEM;
+        }
+        ctx->scratch_bytes[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return SSHG_OK;
+}
+
+int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device, const void** dev) {
+    if (on_device) {
+        *dev = src;
+        return SSHG_OK;
+    }
+    void* d;
+    if (int rc = sshg_scratch(ctx, slot, bytes, &d)) return rc;
+    // pageable source: the runtime stages the copy before returning, so the caller's buffer is
+    // free to change as soon as the API call returns.
+    SSHG_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    *dev = d;
+    return SSHG_OK;
+}
+
+extern "C" {
+
+int sshg_abi_version(void) { return SSHG_ABI_VERSION; }
+
+const char* sshg_last_error(void) { return g_err; }
+
+int sshg_device_count(int* count) {
+    SSHG_REQUIRE(count, "sshg_device_count: null argument");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *count = 0;
+        return sshg_cuda_fail(e, "cudaGetDeviceCount", __FILE__, __LINE__);
+    }
+    *count = n;
+    return SSHG_OK;
+}
+
+int sshg_ctx_create(int device, sshg_ctx** out) {
+    SSHG_REQUIRE(out, "sshg_ctx_create: null argument");
+    *out = nullptr;
+    int n = 0;
+    if (int rc = sshg_device_count(&n)) return rc;
+    if (n == 0) {
+        sshg_set_error("no CUDA device: libsshg has no CPU fallback");
+        return SSHG_ECUDA;
+    }
+    SSHG_REQUIRE(device >= 0 && device < n, "sshg_ctx_create: device %d of %d", device, n);
+    SSHG_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    SSHG_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        sshg_set_error("device %d is sm_%d%d; libsshg is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return SSHG_ECUDA;
+    }
+    sshg_ctx* ctx = (sshg_ctx*)calloc(1, sizeof(sshg_ctx));
+    if (!ctx) {
+        sshg_set_error("out of host memory");
+        return SSHG_ENOMEM;
+    }
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+        e = cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        sshg_ctx_destroy(ctx);
+        return sshg_cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return SSHG_OK;
+}
+
+void sshg_ctx_destroy(sshg_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    for (int i = 0; i < SSHG_NSCRATCH; ++i)
+        if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
+    for (int k = 0; k < 2; ++k) {
+        if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
+        if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
+    }
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    free(ctx);
+}
+
+int sshg_ctx_set_stream(sshg_ctx* ctx, void* cuda_stream) {
+    SSHG_REQUIRE(ctx, "sshg_ctx_set_stream: null context");
+    cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    if (next == ctx->stream) return SSHG_OK;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));   // scratch buffers are ordered on the old stream
+    ctx->stream = next;
+    return SSHG_OK;
+}
+
+void* sshg_ctx_stream(sshg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int sshg_ctx_sync(sshg_ctx* ctx) {
+    SSHG_REQUIRE(ctx, "sshg_ctx_sync: null context");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    return SSHG_OK;
+}
+
+int64_t sshg_ctx_launches(sshg_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sshg_host_alloc(void** ptr, int64_t bytes) {
+    SSHG_REQUIRE(ptr && bytes > 0, "sshg_host_alloc: bad argument");
+    cudaError_t e = cudaMallocHost(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        *ptr = nullptr;
+        sshg_set_error("pinned host allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return SSHG_ENOMEM;
+    }
+    return SSHG_OK;
+}
+
+int sshg_host_free(void* ptr) {
+    if (!ptr) return SSHG_OK;
+    SSHG_CUDA(cudaFreeHost(ptr));
+    return SSHG_OK;
+}
+
+}  // extern "C"

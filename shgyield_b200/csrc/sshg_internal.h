@@ -1,0 +1,44 @@
+// Internal declarations shared by the translation units of libsshg.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/sshg.h"
+
+#define SSHG_NSCRATCH 16
+
+struct sshg_ctx {
+    int device;
+    cudaStream_t own_stream;
+    cudaStream_t stream;        // own_stream or an adopted caller stream
+    cudaStream_t copy_stream;   // D2H of finished slabs while the next slab is computed
+    cudaEvent_t ev_done[2];     // slab k computed
+    cudaEvent_t ev_copied[2];   // slab k copied to the host
+    int num_sms;
+    int64_t launches;
+    // growable device scratch buffers (inputs copied from the host, staged outputs)
+    void* scratch[SSHG_NSCRATCH];
+    size_t scratch_bytes[SSHG_NSCRATCH];
+};
+
+void sshg_set_error(const char* fmt, ...);
+int sshg_cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out);   // grows if needed
+
+#define SSHG_CUDA(call)                                                                   \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) return sshg_cuda_fail(e_, #call, __FILE__, __LINE__);      \
+    } while (0)
+
+#define SSHG_REQUIRE(cond, ...)                                                           \
+    do {                                                                                  \
+        if (!(cond)) {                                                                    \
+            sshg_set_error(__VA_ARGS__);                                                  \
+            return SSHG_EINVAL;                                                           \
+        }                                                                                 \
+    } while (0)
+
+// Copies a host array to a scratch slot (or passes a device pointer through).
+int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device,
+                  const void** dev);

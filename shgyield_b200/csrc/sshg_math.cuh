@@ -1,0 +1,256 @@
+// FP64 complex arithmetic and the per-column physics of the SSHG yield
+// (wave vectors, Fresnel factors, three-layer multiple reflection, chi2 contraction).
+//
+// Follows the formulas of the reference shgyield/shg.py (PRB 94, 115314):
+//   wvec 137-141, frefs/frefp 144-156, ftrans/ftranp 159-171, mrc2w 174-185, mrc1w 188-198,
+//   rad_pp 201-270, rad_ps 273-314, rad_sp 317-352, rad_ss 355-378, prefactor 428-436.
+// The evaluation is re-organised for the GPU: everything that does not depend on the azimuth
+// phi is done once per (energy, theta, thickness) column ("column setup"), each r(phi) is then
+// a 7-term (sS: 4-term) real-basis expansion with complex coefficients.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+// The physics is plain FP64 arithmetic, so it is declared __host__ __device__: the product only
+// ever calls it from kernels; tests/hostmath_harness.cu runs the same functions on the CPU to
+// check the formulas against the golden vectors without a GPU.
+#define SSHG_HD __host__ __device__ __forceinline__
+
+namespace sshg {
+
+struct cplx {
+    double re, im;
+};
+
+SSHG_HD cplx mk(double r, double i) { return cplx{r, i}; }
+SSHG_HD cplx operator+(cplx a, cplx b) { return mk(a.re + b.re, a.im + b.im); }
+SSHG_HD cplx operator-(cplx a, cplx b) { return mk(a.re - b.re, a.im - b.im); }
+SSHG_HD cplx operator-(cplx a) { return mk(-a.re, -a.im); }
+SSHG_HD cplx operator*(cplx a, cplx b) {
+    return mk(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+SSHG_HD cplx operator*(double s, cplx a) { return mk(s * a.re, s * a.im); }
+SSHG_HD cplx operator+(double s, cplx a) { return mk(s + a.re, a.im); }
+SSHG_HD cplx operator-(double s, cplx a) { return mk(s - a.re, -a.im); }
+SSHG_HD cplx csq(cplx a) { return mk(a.re * a.re - a.im * a.im, 2.0 * a.re * a.im); }
+
+// 1/b with one real division.
+SSHG_HD cplx crecip(cplx b) {
+    double n = 1.0 / (b.re * b.re + b.im * b.im);
+    return mk(b.re * n, -b.im * n);
+}
+SSHG_HD cplx operator/(cplx a, cplx b) { return a * crecip(b); }
+
+// Principal square root with the C99 / NumPy branch-cut convention: for negative real parts the
+// sign of the imaginary part (including a signed zero) selects the half plane.
+SSHG_HD cplx csqrt_(cplx z) {
+    double a = z.re, b = z.im;
+    if (a == 0.0 && b == 0.0) return mk(0.0, b);
+    double t = sqrt(0.5 * (fabs(a) + sqrt(a * a + b * b)));
+    if (a >= 0.0) return mk(t, b / (2.0 * t));
+    return mk(fabs(b) / (2.0 * t), copysign(t, b));
+}
+
+// exp(i z)
+SSHG_HD cplx cexp_i(cplx z) {
+    double s, c;
+    sincos(z.re, &s, &c);
+    double m = exp(-z.im);
+    return mk(m * c, m * s);
+}
+
+// sin(z) for complex z
+SSHG_HD cplx csin_(cplx z) {
+    double s, c;
+    sincos(z.re, &s, &c);
+    return mk(s * cosh(z.im), c * sinh(z.im));
+}
+
+struct Physics {
+    double kd;            // 1e-9 / (h c):  E[eV] * d[nm] * kd = d / lambda_vacuum
+    double pref;          // 100 / (hbar * sqrt(2 eps0 c^3)):  sqrt(prefactor) = pref * E / |cos(theta)|
+    int mref;
+    int sinc_normalized;
+    int zzz_phi_quirk;
+};
+
+// Everything of one (energy, theta, thickness) column that the four polarisations share.
+struct Column {
+    cplx Gpp, Gps, Gsp, Gss;   // sqrt(prefactor) * Gamma / n_l for each polarisation
+    cplx A;                    // (1 - R^M_p) W_l          x/y part of the outgoing P field
+    cplx Bz;                   // (1 + R^M_p) sin(theta)   z part of the outgoing P field
+    cplx Q;                    // (1 + R^M_p) (1 + r^M_p)^2          (chi_zzz quirk term)
+    cplx a2, ab, b2;           // (1-r^M_p)^2 w_l^2, (1+r^M_p)(1-r^M_p) w_l sin(theta), (1+r^M_p)^2 sin^2(theta)
+};
+
+struct Fresnel {
+    cplx r_p_vl, r_p_lb, r_s_vl, r_s_lb;   // reflection, vacuum|layer and layer|bulk
+    cplx t_p, t_s;                         // transmission vacuum -> layer
+    cplx w_l;                              // wave vector in the layer
+};
+
+// shg.py:137-171 for one frequency.  Shares the denominators between r and t.
+SSHG_HD Fresnel fresnel_set(cplx ev, cplx el, cplx eb, double s2) {
+    Fresnel f;
+    cplx wv = csqrt_(mk(ev.re - s2, ev.im));
+    cplx wl = csqrt_(mk(el.re - s2, el.im));
+    cplx wb = csqrt_(mk(eb.re - s2, eb.im));
+    f.w_l = wl;
+    // s polarisation
+    cplx isvl = crecip(wv + wl);
+    f.r_s_vl = (wv - wl) * isvl;
+    f.t_s = (2.0 * wv) * isvl;
+    f.r_s_lb = (wl - wb) / (wl + wb);
+    // p polarisation
+    cplx wvel = wv * el, wlev = wl * ev;
+    cplx ipvl = crecip(wvel + wlev);
+    f.r_p_vl = (wvel - wlev) * ipvl;
+    f.t_p = ((2.0 * wv) * csqrt_(ev * el)) * ipvl;      // sqrt of the PRODUCT (shg.py:170)
+    cplx wleb = wl * eb, wbel = wb * el;
+    f.r_p_lb = (wleb - wbel) / (wleb + wbel);
+    return f;
+}
+
+// Column setup: shg.py:174-216, 277-288, 321-332, 359-370 and the prefactor 428-430.
+SSHG_HD Column column_setup(const cplx e1[3], const cplx e2[3], double energy,
+                                               double sin_t, double cos_t, double thick,
+                                               const Physics& ph) {
+    const double s2 = sin_t * sin_t;
+    Fresnel f1 = fresnel_set(e1[0], e1[1], e1[2], s2);   // fundamental
+    Fresnel f2 = fresnel_set(e2[0], e2[1], e2[2], s2);   // second harmonic
+
+    cplx Rp = f2.r_p_lb, Rs = f2.r_s_lb, rp = f1.r_p_lb, rs = f1.r_s_lb;
+    if (ph.mref) {
+        const double x = energy * thick * ph.kd;         // d / lambda
+        const double PI = 3.141592653589793;
+        // 2w: delta = 8 pi x W_l;  R^M = R_lb e^{i delta/2} / (1 + R_vl R_lb e^{i delta}) * sinc(delta/2)
+        cplx hd = (4.0 * PI * x) * f2.w_l;               // delta / 2
+        cplx eh = cexp_i(hd);
+        cplx ed = csq(eh);
+        cplx arg = hd;
+        if (arg.re == 0.0 && arg.im == 0.0) arg = mk(1.0e-20, 0.0);   // np.sinc: 0 -> 1e-20
+        if (ph.sinc_normalized) arg = PI * arg;
+        cplx snc = csin_(arg) / arg;
+        Rp = ((f2.r_p_lb * eh) / (1.0 + f2.r_p_vl * f2.r_p_lb * ed)) * snc;
+        Rs = ((f2.r_s_lb * eh) / (1.0 + f2.r_s_vl * f2.r_s_lb * ed)) * snc;
+        // 1w: varphi = 4 pi x w_l;  r^M = r_lb e^{i varphi} / (1 + r_vl r_lb e^{i varphi})
+        cplx ev = cexp_i((4.0 * PI * x) * f1.w_l);
+        rp = (f1.r_p_lb * ev) / (1.0 + f1.r_p_vl * f1.r_p_lb * ev);
+        rs = (f1.r_s_lb * ev) / (1.0 + f1.r_s_vl * f1.r_s_lb * ev);
+    }
+
+    const cplx inl = crecip(csqrt_(e1[1]));              // 1 / n_l(w)
+    const cplx iNl = crecip(csqrt_(e2[1]));              // 1 / N_l(2w)
+    const cplx q = (ph.pref * energy / fabs(cos_t)) * inl;   // sqrt(prefactor) / n_l
+    const cplx out_p = f2.t_p * iNl;                     // T_p / N_l
+    const cplx out_s = f2.t_s * (1.0 + Rs);              // T_s (1 + R^M_s)
+    const cplx in_p = csq(f1.t_p * inl);                 // (t_p / n_l)^2
+    const cplx in_s = csq(f1.t_s * (1.0 + rs));          // (t_s (1 + r^M_s))^2
+
+    Column c;
+    c.Gpp = q * (out_p * in_p);
+    c.Gps = q * (out_s * in_p);
+    c.Gsp = q * (out_p * in_s);
+    c.Gss = q * (out_s * in_s);
+    const cplx onepR = 1.0 + Rp, onepr = 1.0 + rp, onemr = 1.0 - rp;
+    c.A = (1.0 - Rp) * f2.w_l;
+    c.Bz = sin_t * onepR;
+    c.Q = ph.zzz_phi_quirk ? onepR * csq(onepr) : sin_t * s2 * (onepR * csq(onepr));
+    const cplx a = onemr * f1.w_l;
+    const cplx b = sin_t * onepr;
+    c.a2 = csq(a);
+    c.ab = a * b;
+    c.b2 = csq(b);
+    return c;
+}
+
+// chi2 rows in canonical order (include/sshg.h)
+enum { XXX = 0, XYY, XZZ, XYZ, XXZ, XXY, YXX, YYY, YZZ, YYZ, YXZ, YXY, ZXX, ZYY, ZZZ, ZYZ, ZXZ, ZXY };
+
+// phi basis: F = {1, c^2, s c, c^3, s c^2, s^2 c, s^3} with c = cos(phi), s = sin(phi).
+// The first three span the even harmonics (0, 2), the last four the odd ones (1, 3):
+// F_even(phi + pi) = F_even(phi), F_odd(phi + pi) = -F_odd(phi).
+//
+// `fold` maps the monomial coefficients of the reference's sums onto F using
+// s^2 = 1 - c^2, c = c^3 + s^2 c, s = s c^2 + s^3, and scales by G.
+SSHG_HD void fold(cplx G, cplx m1, cplx mc2, cplx msc, cplx ms2, cplx mc3,
+                                     cplx msc2, cplx ms2c, cplx ms3, cplx mc, cplx ms, cplx k[7]) {
+    k[0] = G * (m1 + ms2);
+    k[1] = G * (mc2 - ms2);
+    k[2] = G * msc;
+    k[3] = G * (mc3 + mc);
+    k[4] = G * (msc2 + ms);
+    k[5] = G * (ms2c + mc);
+    k[6] = G * (ms3 + ms);
+}
+
+template <typename ChiFn>   // chi(i) returns row i of the rotated chi2 at this energy
+SSHG_HD void coeffs_pp(const Column& c, ChiFn chi, const Physics& ph, cplx k[7]) {
+    const cplx Aa2 = c.A * c.a2, Aab = c.A * c.ab, Ab2 = c.A * c.b2;
+    const cplx Ba2 = c.Bz * c.a2, Bab = c.Bz * c.ab;
+    const cplx zero = mk(0.0, 0.0);
+    cplx mc3 = -(Aa2 * chi(XXX));
+    cplx msc2 = -(Aa2 * (2.0 * chi(XXY) + chi(YXX)));
+    cplx ms2c = -(Aa2 * (chi(XYY) + 2.0 * chi(YXY)));
+    cplx ms3 = -(Aa2 * chi(YYY));
+    cplx m1 = zero;
+    if (ph.zzz_phi_quirk) ms3 = ms3 + c.Q * chi(ZZZ);    // shg.py:269
+    else m1 = c.Q * chi(ZZZ);
+    cplx mc2 = Ba2 * chi(ZXX) - 2.0 * (Aab * chi(XXZ));
+    cplx msc = 2.0 * (Ba2 * chi(ZXY)) - 2.0 * (Aab * (chi(XYZ) + chi(YXZ)));
+    cplx ms2 = Ba2 * chi(ZYY) - 2.0 * (Aab * chi(YYZ));
+    cplx mc = 2.0 * (Bab * chi(ZXZ)) - Ab2 * chi(XZZ);
+    cplx ms = 2.0 * (Bab * chi(ZYZ)) - Ab2 * chi(YZZ);
+    fold(c.Gpp, m1, mc2, msc, ms2, mc3, msc2, ms2c, ms3, mc, ms, k);
+}
+
+template <typename ChiFn>
+SSHG_HD void coeffs_ps(const Column& c, ChiFn chi, cplx k[7]) {
+    const cplx zero = mk(0.0, 0.0);
+    cplx mc3 = c.a2 * chi(YXX);
+    cplx msc2 = c.a2 * (2.0 * chi(YXY) - chi(XXX));
+    cplx ms2c = c.a2 * (chi(YYY) - 2.0 * chi(XXY));
+    cplx ms3 = -(c.a2 * chi(XYY));
+    cplx mc2 = 2.0 * (c.ab * chi(YXZ));
+    cplx msc = 2.0 * (c.ab * (chi(YYZ) - chi(XXZ)));
+    cplx ms2 = -2.0 * (c.ab * chi(XYZ));
+    cplx mc = c.b2 * chi(YZZ);
+    cplx ms = -(c.b2 * chi(XZZ));
+    fold(c.Gps, zero, mc2, msc, ms2, mc3, msc2, ms2c, ms3, mc, ms, k);
+}
+
+template <typename ChiFn>
+SSHG_HD void coeffs_sp(const Column& c, ChiFn chi, cplx k[7]) {
+    const cplx zero = mk(0.0, 0.0);
+    cplx mc3 = -(c.A * chi(XYY));
+    cplx msc2 = c.A * (2.0 * chi(XXY) - chi(YYY));
+    cplx ms2c = c.A * (2.0 * chi(YXY) - chi(XXX));
+    cplx ms3 = -(c.A * chi(YXX));
+    cplx mc2 = c.Bz * chi(ZYY);
+    cplx msc = -2.0 * (c.Bz * chi(ZXY));
+    cplx ms2 = c.Bz * chi(ZXX);
+    fold(c.Gsp, zero, mc2, msc, ms2, mc3, msc2, ms2c, ms3, zero, zero, k);
+}
+
+// sS has no even part: k[0..3] multiply {c^3, s c^2, s^2 c, s^3}.
+template <typename ChiFn>
+SSHG_HD void coeffs_ss(const Column& c, ChiFn chi, cplx k[4]) {
+    k[0] = c.Gss * chi(YYY);
+    k[1] = -(c.Gss * (chi(XYY) + 2.0 * chi(YXY)));
+    k[2] = c.Gss * (2.0 * chi(XXY) + chi(YXX));
+    k[3] = -(c.Gss * chi(XXX));
+}
+
+// basis row for one azimuth: b[0..5] = {c^2, s c, c^3, s c^2, s^2 c, s^3}
+SSHG_HD void phi_basis(double phi_deg, double b[6]) {
+    double s, c;
+    sincos(phi_deg * (3.141592653589793 / 180.0), &s, &c);
+    b[0] = c * c;
+    b[1] = s * c;
+    b[2] = b[0] * c;
+    b[3] = b[1] * c;
+    b[4] = b[1] * s;
+    b[5] = s * s * s;
+}
+
+}  // namespace sshg

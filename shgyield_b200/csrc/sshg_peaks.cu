@@ -1,0 +1,96 @@
+// Roofline denominators measured in the same run as the bench:
+// a pure streaming-store kernel (the yield cube is write-only traffic, while
+// MEASURED_PEAKS.json's figure is a read+write copy) and a register-resident DFMA loop.
+#include "sshg_internal.h"
+
+namespace {
+
+__global__ void __launch_bounds__(256) store_kernel(double2* __restrict__ p, long long n2, double v) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
+        __stcs(p + i, make_double2(v, v + (double)(i & 7)));
+}
+
+constexpr int DFMA_ILP = 8;
+constexpr int DFMA_ITERS = 4096;
+
+__global__ void __launch_bounds__(256) dfma_kernel(double* __restrict__ sink, double a, double b) {
+    double x[DFMA_ILP];
+#pragma unroll
+    for (int k = 0; k < DFMA_ILP; ++k) x[k] = a + (double)(threadIdx.x + k);
+#pragma unroll 4
+    for (int it = 0; it < DFMA_ITERS; ++it) {
+#pragma unroll
+        for (int k = 0; k < DFMA_ILP; ++k) x[k] = fma(x[k], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < DFMA_ILP; ++k) s += x[k];
+    if (s == 12345.678) sink[0] = s;           // never true; keeps the loop alive
+}
+
+}  // namespace
+
+extern "C" int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs) {
+    SSHG_REQUIRE(ctx && gbs && bytes >= 1024 && iters > 0, "sshg_peak_store: bad argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    void* buf = nullptr;
+    cudaError_t e = cudaMalloc(&buf, (size_t)bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        sshg_set_error("sshg_peak_store: device allocation of %lld bytes failed", (long long)bytes);
+        return SSHG_ENOMEM;
+    }
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const long long n2 = bytes / 16;
+    const int grid = ctx->num_sms * 8;
+    float best = 1e30f;
+    for (int it = 0; it < iters + 2; ++it) {
+        cudaEventRecord(t0, ctx->stream);
+        store_kernel<<<grid, 256, 0, ctx->stream>>>((double2*)buf, n2, 1.0 + it);
+        cudaEventRecord(t1, ctx->stream);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (it >= 2 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    e = cudaGetLastError();
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(buf);
+    if (e != cudaSuccess) return sshg_cuda_fail(e, "store_kernel", __FILE__, __LINE__);
+    *gbs = (double)(n2 * 16) / (best * 1e-3) / 1e9;
+    return SSHG_OK;
+}
+
+extern "C" int sshg_peak_dfma(sshg_ctx* ctx, int iters, double* tflops) {
+    SSHG_REQUIRE(ctx && tflops && iters > 0, "sshg_peak_dfma: bad argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    void* sink;
+    if (int rc = sshg_scratch(ctx, 15, 16, &sink)) return rc;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int grid = ctx->num_sms * 16, block = 256;
+    float best = 1e30f;
+    for (int it = 0; it < iters + 2; ++it) {
+        cudaEventRecord(t0, ctx->stream);
+        dfma_kernel<<<grid, block, 0, ctx->stream>>>((double*)sink, 1.0000001, 1e-9);
+        cudaEventRecord(t1, ctx->stream);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (it >= 2 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    if (e != cudaSuccess) return sshg_cuda_fail(e, "dfma_kernel", __FILE__, __LINE__);
+    const double flops = 2.0 * DFMA_ILP * DFMA_ITERS * (double)grid * block;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    return SSHG_OK;
+}

@@ -1,0 +1,217 @@
+// Per-energy preparation kernels: in-plane rotation of chi2 and cubic-spline resampling.
+//
+//  * sshg_rotate replaces rotate() of the reference (shgyield/shg.py:63-134).  The reference's
+//    18 formulas are the rank-3 tensor rotation chi'_abc = R_ai R_bj R_ck chi_ijk about z by the
+//    internal angle g = pi/2 - gamma (shg.py:65) written out on the 18 components with
+//    chi_abc = chi_acb folded -- except for one sign (the chi_yyy contribution to chi_xxy,
+//    shg.py:92).  Here the 18x18 real matrix is built from R on the host and applied per energy
+//    on the device; `xxy_quirk` flips that one entry to reproduce the shipped behaviour.
+//
+//  * sshg_spline_resample replaces spline/splineC/splineEPS (shg.py:38-55, 423-424):
+//    InterpolatedUnivariateSpline(x, y, ext=2) is FITPACK's interpolating cubic spline with
+//    knots x[2:-2], i.e. the unique not-a-knot cubic interpolant.  It is computed here from its
+//    second derivatives (tridiagonal system, Thomas algorithm, one thread per signal) and
+//    evaluated piecewise.
+#include "sshg_internal.h"
+
+#include <math.h>
+#include <string.h>
+
+namespace {
+
+struct RotMatrix {
+    double m[SSHG_NCHI][SSHG_NCHI];
+};
+
+// canonical rows: xxx xyy xzz xyz xxz xxy  yxx yyy yzz yyz yxz yxy  zxx zyy zzz zyz zxz zxy
+const int kRowAxes[SSHG_NCHI][3] = {
+    {0, 0, 0}, {0, 1, 1}, {0, 2, 2}, {0, 1, 2}, {0, 0, 2}, {0, 0, 1},
+    {1, 0, 0}, {1, 1, 1}, {1, 2, 2}, {1, 1, 2}, {1, 0, 2}, {1, 0, 1},
+    {2, 0, 0}, {2, 1, 1}, {2, 2, 2}, {2, 1, 2}, {2, 0, 2}, {2, 0, 1}};
+
+int row_of(int a, int b, int c) {
+    if (b > c) {
+        int t = b;
+        b = c;
+        c = t;
+    }
+    for (int r = 0; r < SSHG_NCHI; ++r)
+        if (kRowAxes[r][0] == a && kRowAxes[r][1] == b && kRowAxes[r][2] == c) return r;
+    return -1;
+}
+
+__global__ void rotate_kernel(const double2* __restrict__ in, double2* __restrict__ out, long long nE,
+                              const RotMatrix M) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    double2 v[SSHG_NCHI];
+#pragma unroll
+    for (int j = 0; j < SSHG_NCHI; ++j) v[j] = in[j * nE + e];
+#pragma unroll 1
+    for (int k = 0; k < SSHG_NCHI; ++k) {
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int j = 0; j < SSHG_NCHI; ++j) {
+            const double m = M.m[k][j];
+            if (m != 0.0) {                    // uniform branch: absent terms must not see Inf/NaN
+                re = fma(m, v[j].x, re);
+                im = fma(m, v[j].y, im);
+            }
+        }
+        out[k * nE + e] = make_double2(re, im);
+    }
+}
+
+// ---- spline -------------------------------------------------------------------------------
+// Second derivatives of the not-a-knot cubic spline, one thread per signal.
+// cp/dp: scratch [n][rows] (thread-contiguous).  y, M: [rows][n].
+__global__ void spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                    double* __restrict__ M, double* __restrict__ cp, double* __restrict__ dp,
+                                    long long rows, long long n) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const double* yr = y + r * n;
+    double* Mr = M + r * n;
+    const long long m = n - 2;
+    const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
+    const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
+    double cprev = 0.0, dprev = 0.0;
+    for (long long i = 0; i < m; ++i) {
+        const double hl = x[i + 1] - x[i], hr = x[i + 2] - x[i + 1];
+        double lower = hl, diag = 2.0 * (hl + hr), upper = hr;
+        const double rhs = 6.0 * ((yr[i + 2] - yr[i + 1]) / hr - (yr[i + 1] - yr[i]) / hl);
+        if (i == 0) {
+            diag += hl * (1.0 + q0);
+            upper -= hl * q0;
+        }
+        if (i == m - 1) {
+            diag += hr * (1.0 + q1);
+            lower -= hr * q1;
+        }
+        const double den = (i == 0) ? diag : diag - lower * cprev;
+        cprev = upper / den;
+        dprev = (i == 0) ? rhs / den : (rhs - lower * dprev) / den;
+        cp[i * rows + r] = cprev;
+        dp[i * rows + r] = dprev;
+    }
+    double next = dprev;                        // M_{n-2}
+    Mr[m] = next;
+    for (long long i = m - 2; i >= 0; --i) {
+        next = dp[i * rows + r] - cp[i * rows + r] * next;
+        Mr[i + 1] = next;
+    }
+    Mr[0] = (1.0 + q0) * Mr[1] - q0 * Mr[2];
+    Mr[n - 1] = (1.0 + q1) * Mr[n - 2] - q1 * Mr[n - 3];
+}
+
+__global__ void spline_eval_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                   const double* __restrict__ M, long long rows, long long n,
+                                   const double* __restrict__ xq, long long nq, double* __restrict__ out,
+                                   int* __restrict__ flag) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= rows * nq) return;
+    const long long r = g / nq, k = g % nq;
+    const double q = xq[k];
+    if (!(q >= x[0] && q <= x[n - 1])) {        // also catches NaN
+        if (r == 0) atomicOr(flag, 1);
+        out[g] = nan("");
+        return;
+    }
+    long long lo = 0, hi = n - 1;               // x[lo] <= q <= x[hi]
+    while (hi - lo > 1) {
+        const long long mid = (lo + hi) >> 1;
+        if (x[mid] <= q) lo = mid;
+        else hi = mid;
+    }
+    const double h = x[lo + 1] - x[lo];
+    const double a = x[lo + 1] - q, b = q - x[lo];
+    const double M0 = M[r * n + lo], M1 = M[r * n + lo + 1];
+    const double y0 = y[r * n + lo], y1 = y[r * n + lo + 1];
+    out[g] = (M0 * a * a * a + M1 * b * b * b) / (6.0 * h) + (y0 / h - M0 * h / 6.0) * a + (y1 / h - M1 * h / 6.0) * b;
+}
+
+}  // namespace
+
+extern "C" int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, int64_t nE, double gamma_deg,
+                           int xxy_quirk, int where) {
+    SSHG_REQUIRE(ctx && chi_in && chi_out, "sshg_rotate: null argument");
+    SSHG_REQUIRE(nE > 0, "sshg_rotate: nE must be positive");
+    SSHG_REQUIRE(chi_in != chi_out, "sshg_rotate: in-place rotation is not supported");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const double deg = 3.141592653589793 / 180.0;
+    const double g = 90.0 * deg - gamma_deg * deg;        // shg.py:65 with rotang = radians(gamma)
+    const double s = sin(g), c = cos(g);
+    const double R[3][3] = {{s, -c, 0.0}, {c, s, 0.0}, {0.0, 0.0, 1.0}};
+    RotMatrix M;
+    memset(&M, 0, sizeof(M));
+    for (int k = 0; k < SSHG_NCHI; ++k) {
+        const int a = kRowAxes[k][0], b = kRowAxes[k][1], cc = kRowAxes[k][2];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+                for (int l = 0; l < 3; ++l) {
+                    const double w = R[a][i] * R[b][j] * R[cc][l];
+                    if (w != 0.0) M.m[k][row_of(i, j, l)] += w;
+                }
+    }
+    if (xxy_quirk) M.m[5][7] = -M.m[5][7];                // chi_xxy <- chi_yyy, shg.py:92
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    const size_t bytes = (size_t)SSHG_NCHI * nE * 16;
+    const void* din;
+    if (int rc = sshg_stage_in(ctx, 10, chi_in, bytes, in_dev, &din)) return rc;
+    void* dout = chi_out;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
+    }
+    SSHG_REQUIRE(((uintptr_t)din | (uintptr_t)dout) % 16 == 0, "sshg_rotate: device arrays must be 16-byte aligned");
+    rotate_kernel<<<(unsigned)((nE + 127) / 128), 128, 0, ctx->stream>>>((const double2*)din, (double2*)dout, nE, M);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (!out_dev) {
+        SSHG_CUDA(cudaMemcpyAsync(chi_out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SSHG_OK;
+}
+
+extern "C" int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
+                                    const double* xq, int64_t nq, double* out, int where) {
+    SSHG_REQUIRE(ctx && x && y && xq && out, "sshg_spline_resample: null argument");
+    SSHG_REQUIRE(rows > 0 && nq > 0, "sshg_spline_resample: rows and nq must be positive");
+    SSHG_REQUIRE(n >= 4, "sshg_spline_resample: a cubic interpolating spline needs at least 4 samples (got %lld)",
+                 (long long)n);
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    if (!in_dev) {
+        for (int64_t i = 1; i < n; ++i)
+            SSHG_REQUIRE(x[i] > x[i - 1], "sshg_spline_resample: x must be strictly increasing (x[%lld])", (long long)i);
+    }
+    const void *dx, *dy, *dq;
+    if (int rc = sshg_stage_in(ctx, 10, x, (size_t)n * 8, in_dev, &dx)) return rc;
+    if (int rc = sshg_stage_in(ctx, 11, y, (size_t)rows * n * 8, in_dev, &dy)) return rc;
+    if (int rc = sshg_stage_in(ctx, 12, xq, (size_t)nq * 8, in_dev, &dq)) return rc;
+    void *dM, *dcp, *ddp, *dflag;
+    if (int rc = sshg_scratch(ctx, 13, (size_t)rows * n * 8, &dM)) return rc;
+    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 16, &dcp)) return rc;
+    ddp = (char*)dcp + (size_t)rows * n * 8;
+    if (int rc = sshg_scratch(ctx, 15, 16, &dflag)) return rc;
+    void* dout = out;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 9, (size_t)rows * nq * 8, &dout)) return rc;
+    }
+    SSHG_CUDA(cudaMemsetAsync(dflag, 0, 4, ctx->stream));
+    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(
+        (const double*)dx, (const double*)dy, (double*)dM, (double*)dcp, (double*)ddp, rows, n);
+    SSHG_CUDA(cudaGetLastError());
+    const long long total = (long long)rows * nq;
+    spline_eval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+        (const double*)dx, (const double*)dy, (const double*)dM, rows, n, (const double*)dq, nq, (double*)dout,
+        (int*)dflag);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    int flag = 0;
+    SSHG_CUDA(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!out_dev) SSHG_CUDA(cudaMemcpyAsync(out, dout, (size_t)rows * nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    SSHG_REQUIRE(flag == 0, "sshg_spline_resample: a query lies outside the sampled range [x[0], x[n-1]] (ext=2)");
+    return SSHG_OK;
+}

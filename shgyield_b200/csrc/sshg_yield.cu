@@ -1,0 +1,496 @@
+// K2: the fused SSHG yield kernel (sm_100a, FP64).
+//
+// One thread owns two adjacent energies of one (theta, thickness) column.  It
+//   (A) evaluates the column setup once (Fresnel factors, multiple reflection, Gamma's:
+//       reference shg.py:137-216) and parks the ten shared complex factors in shared memory,
+//   (B) per polarisation contracts the rotated chi2 with them into 7 (sS: 4) complex
+//       coefficients held in registers (shg.py:218-269, 290-313, 334-351, 372-377), and
+//   (C) sweeps the azimuth: r(phi) = sum_k coef_k F_k(phi), yield = |r|^2 (shg.py:433-436),
+//       written with streaming 128-bit stores, energy fastest.
+// The phi basis F is a small table in shared memory, read as warp broadcasts.  When the phi
+// grid contains phi and phi + 180 deg the even/odd split of F gives both rows from one
+// evaluation (20 instead of 28 FP64 instructions per energy and row pair; sS: 10).
+//
+// HBM traffic: 8 B per yield point written once; inputs are 384 B per energy, L2 resident.
+#include "sshg_internal.h"
+#include "sshg_math.cuh"
+
+using namespace sshg;
+
+namespace {
+
+constexpr int NT = 256;        // threads per CTA
+constexpr int EPT = 2;         // energies per thread
+constexpr int CHUNK = 384;     // phi items per shared-memory table chunk
+constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
+
+struct YieldArgs {
+    const double2* eps1w;      // [3][nE]
+    const double2* eps2w;      // [3][nE]
+    const double2* chi;        // [18][nE]
+    const double* energy;      // [nE]
+    const double* theta_deg;   // [nT]
+    const double* thick_nm;    // [nD]
+    const double* tab;         // [1 + ...]: header (H as double) then items x 6 doubles
+    double* out;
+    long long nE, nP;
+    long long col0;            // first local column of this launch (out points at it)
+    int nTs, nDs, t0, d0;      // shard extents / offsets
+    int n_tiles;
+    int vec_ok;                // 128-bit stores allowed (nE even, out 16-B aligned)
+    Physics ph;
+};
+
+__device__ __forceinline__ void store2(double* p, double y0, double y1, bool vec, bool valid1) {
+    if (vec) {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(y0, y1));
+    } else {
+        __stcs(p, y0);
+        if (valid1) __stcs(p + 1, y1);
+    }
+}
+
+// phi table: tab[0] = H (number of (phi, phi+180) pairs), then item rows of 6 doubles.
+// item i < H      -> rows i and i + H of the cube, basis of phi[i]
+// item i >= H     -> row i + H (the un-paired tail), basis of phi[i + H]
+__global__ void phi_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
+                                 int allow_pairs) {
+    __shared__ int bad;
+    const long long H = nP / 2;
+    if (threadIdx.x == 0) bad = (allow_pairs && H > 0) ? 0 : 1;
+    __syncthreads();
+    if (allow_pairs && H > 0) {
+        int mybad = 0;
+        for (long long j = threadIdx.x; j < H; j += blockDim.x)
+            if (phi[j + H] != phi[j] + 180.0) mybad = 1;
+        if (mybad) bad = 1;
+    }
+    __syncthreads();
+    const long long h = bad ? 0 : H;
+    if (threadIdx.x == 0) tab[0] = (double)h;
+    const long long items = nP - h;
+    for (long long i = threadIdx.x; i < items; i += blockDim.x) {
+        double b[6];
+        phi_basis(phi[i < h ? i : i + h], b);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) tab[1 + i * 6 + k] = b[k];
+    }
+}
+
+struct Coef7 {
+    double r[7], i[7];
+};
+
+// (C) for a 7-term polarisation, two energies per thread.
+__device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const double* __restrict__ tb,
+                                       int n_pair, int n_single, double* plo, double* phi_, double* psg,
+                                       long long stride, bool vec, bool valid1) {
+#pragma unroll 2
+    for (int i = 0; i < n_pair; ++i) {
+        const double b0 = tb[0], b1 = tb[1], b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
+        tb += 6;
+        double er0 = fma(k0.r[2], b1, fma(k0.r[1], b0, k0.r[0]));
+        double ei0 = fma(k0.i[2], b1, fma(k0.i[1], b0, k0.i[0]));
+        double or0 = fma(k0.r[6], b5, fma(k0.r[5], b4, fma(k0.r[4], b3, k0.r[3] * b2)));
+        double oi0 = fma(k0.i[6], b5, fma(k0.i[5], b4, fma(k0.i[4], b3, k0.i[3] * b2)));
+        double er1 = fma(k1.r[2], b1, fma(k1.r[1], b0, k1.r[0]));
+        double ei1 = fma(k1.i[2], b1, fma(k1.i[1], b0, k1.i[0]));
+        double or1 = fma(k1.r[6], b5, fma(k1.r[5], b4, fma(k1.r[4], b3, k1.r[3] * b2)));
+        double oi1 = fma(k1.i[6], b5, fma(k1.i[5], b4, fma(k1.i[4], b3, k1.i[3] * b2)));
+        double ar0 = er0 + or0, ai0 = ei0 + oi0, sr0 = er0 - or0, si0 = ei0 - oi0;
+        double ar1 = er1 + or1, ai1 = ei1 + oi1, sr1 = er1 - or1, si1 = ei1 - oi1;
+        store2(plo, fma(ar0, ar0, ai0 * ai0), fma(ar1, ar1, ai1 * ai1), vec, valid1);
+        store2(phi_, fma(sr0, sr0, si0 * si0), fma(sr1, sr1, si1 * si1), vec, valid1);
+        plo += stride;
+        phi_ += stride;
+    }
+#pragma unroll 2
+    for (int i = 0; i < n_single; ++i) {
+        const double b0 = tb[0], b1 = tb[1], b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
+        tb += 6;
+        double r0 = fma(k0.r[6], b5, fma(k0.r[5], b4, fma(k0.r[4], b3, fma(k0.r[3], b2,
+                    fma(k0.r[2], b1, fma(k0.r[1], b0, k0.r[0]))))));
+        double i0 = fma(k0.i[6], b5, fma(k0.i[5], b4, fma(k0.i[4], b3, fma(k0.i[3], b2,
+                    fma(k0.i[2], b1, fma(k0.i[1], b0, k0.i[0]))))));
+        double r1 = fma(k1.r[6], b5, fma(k1.r[5], b4, fma(k1.r[4], b3, fma(k1.r[3], b2,
+                    fma(k1.r[2], b1, fma(k1.r[1], b0, k1.r[0]))))));
+        double i1 = fma(k1.i[6], b5, fma(k1.i[5], b4, fma(k1.i[4], b3, fma(k1.i[3], b2,
+                    fma(k1.i[2], b1, fma(k1.i[1], b0, k1.i[0]))))));
+        store2(psg, fma(r0, r0, i0 * i0), fma(r1, r1, i1 * i1), vec, valid1);
+        psg += stride;
+    }
+}
+
+struct Coef4 {
+    double r[4], i[4];
+};
+
+// (C) for sS: odd part only, so the row at phi + 180 deg equals the row at phi.
+__device__ __forceinline__ void sweep4(const Coef4& k0, const Coef4& k1, const double* __restrict__ tb,
+                                       int n_pair, int n_single, double* plo, double* phi_, double* psg,
+                                       long long stride, bool vec, bool valid1) {
+#pragma unroll 2
+    for (int i = 0; i < n_pair + n_single; ++i) {
+        const double b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
+        tb += 6;
+        double r0 = fma(k0.r[3], b5, fma(k0.r[2], b4, fma(k0.r[1], b3, k0.r[0] * b2)));
+        double i0 = fma(k0.i[3], b5, fma(k0.i[2], b4, fma(k0.i[1], b3, k0.i[0] * b2)));
+        double r1 = fma(k1.r[3], b5, fma(k1.r[2], b4, fma(k1.r[1], b3, k1.r[0] * b2)));
+        double i1 = fma(k1.i[3], b5, fma(k1.i[2], b4, fma(k1.i[1], b3, k1.i[0] * b2)));
+        const double y0 = fma(r0, r0, i0 * i0), y1 = fma(r1, r1, i1 * i1);
+        if (i < n_pair) {
+            store2(plo, y0, y1, vec, valid1);
+            store2(phi_, y0, y1, vec, valid1);
+            plo += stride;
+            phi_ += stride;
+        } else {
+            store2(psg, y0, y1, vec, valid1);
+            psg += stride;
+        }
+    }
+}
+
+__device__ __forceinline__ cplx ldc(const double2* p) {
+    double2 v = __ldg(p);
+    return mk(v.x, v.y);
+}
+
+__global__ void __launch_bounds__(NT, 2) yield_grid_kernel(const YieldArgs a) {
+    extern __shared__ double smem[];
+    double* tabs = smem;                        // [CHUNK][6]
+    double* cols = smem + CHUNK * 6;            // [EPT][NCOL][NT]
+
+    const long long blk = blockIdx.x;
+    const int tile = (int)(blk % a.n_tiles);
+    const long long lcol = blk / a.n_tiles;     // column within this launch
+    const long long col = a.col0 + lcol;        // local column of the shard = tl * nDs + dl
+    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+    const int tid = threadIdx.x;
+    const long long e0 = ((long long)tile * NT + tid) * EPT;
+    const bool active = e0 < a.nE;
+    const bool valid1 = e0 + 1 < a.nE;
+    const long long nE = a.nE;
+    const long long ee[2] = {active ? e0 : nE - 1, valid1 ? e0 + 1 : nE - 1};
+
+    // ---- (A) column setup, one energy at a time to keep register pressure down -------------
+    {
+        double st, ct;
+        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
+        const double thick = a.thick_nm[a.d0 + dl];
+#pragma unroll 1
+        for (int k = 0; k < EPT; ++k) {
+            const long long e = ee[k];
+            cplx e1[3], e2[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                e1[m] = ldc(a.eps1w + m * nE + e);
+                e2[m] = ldc(a.eps2w + m * nE + e);
+            }
+            Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
+            double* d = cols + (k * NCOL) * NT + tid;
+            const cplx v[10] = {c.Gpp, c.Gps, c.Gsp, c.Gss, c.A, c.Bz, c.Q, c.a2, c.ab, c.b2};
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                d[(2 * j) * NT] = v[j].re;
+                d[(2 * j + 1) * NT] = v[j].im;
+            }
+        }
+    }
+
+    const long long H = (long long)a.tab[0];
+    const long long items = a.nP - H;
+    const bool vec = a.vec_ok != 0;
+    const long long rows_per_pol = a.nP * nE;
+    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+
+    auto col_field = [&](int k, int j) -> cplx {
+        const double* d = cols + (k * NCOL) * NT + tid;
+        return mk(d[(2 * j) * NT], d[(2 * j + 1) * NT]);
+    };
+    auto load_column = [&](int k) -> Column {
+        Column c;
+        c.Gpp = col_field(k, 0); c.Gps = col_field(k, 1); c.Gsp = col_field(k, 2); c.Gss = col_field(k, 3);
+        c.A = col_field(k, 4); c.Bz = col_field(k, 5); c.Q = col_field(k, 6);
+        c.a2 = col_field(k, 7); c.ab = col_field(k, 8); c.b2 = col_field(k, 9);
+        return c;
+    };
+
+    for (long long base = 0; base < items; base += CHUNK) {
+        const int n_items = (int)min((long long)CHUNK, items - base);
+        __syncthreads();                        // previous chunk fully consumed; columns parked
+        for (int i = tid; i < n_items * 6; i += NT) tabs[i] = a.tab[1 + base * 6 + i];
+        __syncthreads();
+        if (!active) continue;
+        // items [base, base + n_items): pairs are the items below H
+        const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
+        const int n_single = n_items - n_pair;
+        const long long first_single_item = base + n_pair;       // >= H when n_single > 0
+
+#pragma unroll 1
+        for (int pol = 0; pol < 4; ++pol) {
+            double* prow = out_col + pol * rows_per_pol;
+            double* plo = prow + base * nE;                      // row = item           (item < H)
+            double* phi_ = prow + (base + H) * nE;               // row = item + H
+            double* psg = prow + (first_single_item + H) * nE;   // row = item + H       (item >= H)
+            if (pol == 3) {
+                Coef4 k[2];
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) {
+                    const long long e = ee[q];
+                    Column c = load_column(q);
+                    cplx kk[4];
+                    coeffs_ss(c, [&](int r) { return ldc(a.chi + r * nE + e); }, kk);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
+                }
+                sweep4(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+            } else {
+                Coef7 k[2];
+#pragma unroll
+                for (int q = 0; q < EPT; ++q) {
+                    const long long e = ee[q];
+                    Column c = load_column(q);
+                    auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+                    cplx kk[7];
+                    if (pol == 0) coeffs_pp(c, chi, a.ph, kk);
+                    else if (pol == 1) coeffs_ps(c, chi, kk);
+                    else coeffs_sp(c, chi, kk);
+#pragma unroll
+                    for (int j = 0; j < 7; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
+                }
+                sweep7(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+            }
+        }
+    }
+}
+
+// General NumPy-broadcast shape: one thread per point, all four polarisations.
+struct PointArgs {
+    const double2* eps1w;
+    const double2* eps2w;
+    const double2* chi;
+    const double* energy;
+    const long long* eidx;
+    const double* theta_deg;
+    const double* phi_deg;
+    const double* thick_nm;
+    double* out;               // [4][n]
+    long long n, nE;
+    Physics ph;
+};
+
+__global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const long long e = a.eidx[i], nE = a.nE;
+    double st, ct;
+    sincos(a.theta_deg[i] * (3.141592653589793 / 180.0), &st, &ct);
+    cplx e1[3], e2[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        e1[m] = ldc(a.eps1w + m * nE + e);
+        e2[m] = ldc(a.eps2w + m * nE + e);
+    }
+    const Column c = column_setup(e1, e2, a.energy[e], st, ct, a.thick_nm[i], a.ph);
+    double b[6];
+    phi_basis(a.phi_deg[i], b);
+    auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+#pragma unroll 1
+    for (int pol = 0; pol < 3; ++pol) {
+        cplx k[7];
+        if (pol == 0) coeffs_pp(c, chi, a.ph, k);
+        else if (pol == 1) coeffs_ps(c, chi, k);
+        else coeffs_sp(c, chi, k);
+        double re = k[0].re, im = k[0].im;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            re = fma(k[j + 1].re, b[j], re);
+            im = fma(k[j + 1].im, b[j], im);
+        }
+        a.out[pol * a.n + i] = fma(re, re, im * im);
+    }
+    {
+        cplx k[4];
+        coeffs_ss(c, chi, k);
+        double re = k[0].re * b[2], im = k[0].im * b[2];
+#pragma unroll
+        for (int j = 1; j < 4; ++j) {
+            re = fma(k[j].re, b[j + 2], re);
+            im = fma(k[j].im, b[j + 2], im);
+        }
+        a.out[3 * a.n + i] = fma(re, re, im * im);
+    }
+}
+
+Physics make_physics(const sshg_physics& p) {
+    Physics ph;
+    ph.kd = 1e-9 / (p.h_eVs * p.c);
+    ph.pref = 100.0 / (p.hbar_eVs * sqrt(2.0 * p.eps0 * p.c * p.c * p.c));
+    ph.mref = p.mref;
+    ph.sinc_normalized = p.sinc_normalized;
+    ph.zzz_phi_quirk = p.zzz_phi_quirk;
+    return ph;
+}
+
+int check_physics(const sshg_physics& p) {
+    SSHG_REQUIRE(p.h_eVs > 0 && p.hbar_eVs > 0 && p.eps0 > 0 && p.c > 0,
+                 "sshg_physics: h_eVs, hbar_eVs, eps0 and c must be positive");
+    return SSHG_OK;
+}
+
+constexpr size_t GRID_SMEM = (size_t)(CHUNK * 6 + EPT * NCOL * NT) * sizeof(double);
+
+}  // namespace
+
+extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where) {
+    SSHG_REQUIRE(ctx && p && out, "sshg_yield: null argument");
+    SSHG_REQUIRE(p->nE > 0 && p->nT > 0 && p->nP > 0 && p->nD > 0,
+                 "sshg_yield: nE, nT, nP, nD must be positive (got %lld %lld %lld %lld)",
+                 (long long)p->nE, (long long)p->nT, (long long)p->nP, (long long)p->nD);
+    SSHG_REQUIRE(p->energy_eV && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
+                 "sshg_yield: null input array");
+    if (int rc = check_physics(p->phys)) return rc;
+    const int64_t t0 = p->t0, t1 = p->t1 ? p->t1 : p->nT, d0 = p->d0, d1 = p->d1 ? p->d1 : p->nD;
+    SSHG_REQUIRE(0 <= t0 && t0 < t1 && t1 <= p->nT, "sshg_yield: bad theta shard [%lld,%lld) of %lld",
+                 (long long)t0, (long long)t1, (long long)p->nT);
+    SSHG_REQUIRE(0 <= d0 && d0 < d1 && d1 <= p->nD, "sshg_yield: bad thickness shard [%lld,%lld) of %lld",
+                 (long long)d0, (long long)d1, (long long)p->nD);
+    SSHG_REQUIRE(p->nP < (1LL << 31) && p->nE < (1LL << 40), "sshg_yield: axis too long");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    const size_t nE = (size_t)p->nE;
+    YieldArgs a{};
+    const void* d;
+    if (int rc = sshg_stage_in(ctx, 0, p->eps1w, 3 * nE * 16, in_dev, &d)) return rc;
+    a.eps1w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 1, p->eps2w, 3 * nE * 16, in_dev, &d)) return rc;
+    a.eps2w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 2, p->chi2, SSHG_NCHI * nE * 16, in_dev, &d)) return rc;
+    a.chi = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 3, p->energy_eV, nE * 8, in_dev, &d)) return rc;
+    a.energy = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 4, p->theta_deg, (size_t)p->nT * 8, in_dev, &d)) return rc;
+    a.theta_deg = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 5, p->thick_nm, (size_t)p->nD * 8, in_dev, &d)) return rc;
+    a.thick_nm = (const double*)d;
+    const void* dphi;
+    if (int rc = sshg_stage_in(ctx, 6, p->phi_deg, (size_t)p->nP * 8, in_dev, &dphi)) return rc;
+    SSHG_REQUIRE(((uintptr_t)a.eps1w | (uintptr_t)a.eps2w | (uintptr_t)a.chi) % 16 == 0,
+                 "sshg_yield: complex device arrays must be 16-byte aligned");
+
+    void* tab;
+    if (int rc = sshg_scratch(ctx, 7, (size_t)(1 + 6 * p->nP) * 8, &tab)) return rc;
+    a.tab = (const double*)tab;
+    phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches++;
+
+    a.nE = p->nE;
+    a.nP = p->nP;
+    a.nTs = (int)(t1 - t0);
+    a.nDs = (int)(d1 - d0);
+    a.t0 = (int)t0;
+    a.d0 = (int)d0;
+    a.n_tiles = (int)((p->nE + NT * EPT - 1) / (NT * EPT));
+    a.ph = make_physics(p->phys);
+
+    const int64_t cols = (int64_t)a.nTs * a.nDs;
+    const int64_t per_col = 4 * p->nP * p->nE;            // doubles per column
+    SSHG_REQUIRE(cols * a.n_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM));
+
+    auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
+        YieldArgs b = a;
+        b.col0 = c0;
+        b.out = dst;
+        b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
+        yield_grid_kernel<<<(unsigned)(nc * a.n_tiles), NT, GRID_SMEM, st>>>(b);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SSHG_OK;
+    };
+
+    if (out_dev) return launch(0, cols, out, ctx->stream);
+
+    // Host output: compute slabs of columns into two device buffers and copy slab k back on the
+    // copy stream while slab k+1 is computed.
+    const size_t slab_target = (size_t)256 << 20;
+    int64_t cols_per_slab = (int64_t)(slab_target / ((size_t)per_col * 8));
+    if (cols_per_slab < 1) cols_per_slab = 1;
+    if (cols_per_slab > cols) cols_per_slab = cols;
+    const size_t slab_bytes = (size_t)cols_per_slab * per_col * 8;
+    void* buf[2];
+    if (int rc = sshg_scratch(ctx, 8, slab_bytes, &buf[0])) return rc;
+    if (cols_per_slab < cols) {
+        if (int rc = sshg_scratch(ctx, 9, slab_bytes, &buf[1])) return rc;
+    } else {
+        buf[1] = buf[0];
+    }
+    int k = 0;
+    bool used[2] = {false, false};
+    for (int64_t c0 = 0; c0 < cols; c0 += cols_per_slab, k ^= 1) {
+        const int64_t nc = (cols - c0 < cols_per_slab) ? cols - c0 : cols_per_slab;
+        if (used[k]) SSHG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));   // buffer drained
+        if (int rc = launch(c0, nc, (double*)buf[k], ctx->stream)) return rc;
+        SSHG_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
+        SSHG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
+        SSHG_CUDA(cudaMemcpyAsync(out + c0 * per_col, buf[k], (size_t)nc * per_col * 8, cudaMemcpyDeviceToHost,
+                                  ctx->copy_stream));
+        SSHG_CUDA(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
+        used[k] = true;
+    }
+    SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SSHG_OK;
+}
+
+extern "C" int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where) {
+    SSHG_REQUIRE(ctx && p && out, "sshg_yield_points: null argument");
+    SSHG_REQUIRE(p->n > 0 && p->nE > 0, "sshg_yield_points: n and nE must be positive");
+    SSHG_REQUIRE(p->energy_eV && p->eidx && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
+                 "sshg_yield_points: null input array");
+    if (int rc = check_physics(p->phys)) return rc;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    const size_t nE = (size_t)p->nE, n = (size_t)p->n;
+    if (!in_dev) {
+        for (size_t i = 0; i < n; ++i)
+            SSHG_REQUIRE(p->eidx[i] >= 0 && p->eidx[i] < p->nE, "sshg_yield_points: eidx[%zu] = %lld out of range", i,
+                         (long long)p->eidx[i]);
+    }
+    PointArgs a{};
+    const void* d;
+    if (int rc = sshg_stage_in(ctx, 0, p->eps1w, 3 * nE * 16, in_dev, &d)) return rc;
+    a.eps1w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 1, p->eps2w, 3 * nE * 16, in_dev, &d)) return rc;
+    a.eps2w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 2, p->chi2, SSHG_NCHI * nE * 16, in_dev, &d)) return rc;
+    a.chi = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 3, p->energy_eV, nE * 8, in_dev, &d)) return rc;
+    a.energy = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 4, p->theta_deg, n * 8, in_dev, &d)) return rc;
+    a.theta_deg = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 5, p->thick_nm, n * 8, in_dev, &d)) return rc;
+    a.thick_nm = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 6, p->phi_deg, n * 8, in_dev, &d)) return rc;
+    a.phi_deg = (const double*)d;
+    if (int rc = sshg_stage_in(ctx, 7, p->eidx, n * 8, in_dev, &d)) return rc;
+    a.eidx = (const long long*)d;
+    a.n = p->n;
+    a.nE = p->nE;
+    a.ph = make_physics(p->phys);
+    void* dout = out;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 8, 4 * n * 8, &dout)) return rc;
+    }
+    a.out = (double*)dout;
+    yield_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    if (!out_dev) {
+        SSHG_CUDA(cudaMemcpyAsync(out, dout, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SSHG_OK;
+}

@@ -1,0 +1,204 @@
+"""
+Rectangular sweeps (energy x theta x phi x thickness x 4 polarisations) on one or several B200s.
+
+The reference can only express a sweep by broadcasting NumPy arrays through `shg.shgyield`
+(reference shg.py:381-437; e.g. energy (E,), theta (T,1), phi (P,1,1)).  `shgyield_grid` is the
+additive entry point for the large cases of BASELINE.json (configs 3-5): it takes the four axes
+explicitly and returns the yield cube in the kernel's layout [T, D, 4, P, E] (pol = pp, ps, sp, ss;
+energy contiguous).
+
+Multi-GPU: every point is independent, so theta (or thickness) is cut into contiguous shards, one
+per rank (one process per GPU, torch.distributed).  Each rank's slab is a contiguous block of the
+cube; the only collective is the optional gather of the slabs (NCCL over NVLink).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .shg import _physics, _prepare, physical_constants
+
+POLS = ("pp", "ps", "sp", "ss")
+
+
+def shard_bounds(n: int, world: int, rank: int) -> tuple:
+    """Contiguous shard [lo, hi) of range(n) for `rank` of `world`: the first n % world ranks get
+    one extra element (181 thetas over 8 ranks -> 23 x 5 + 22 x 3)."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError("bad rank %d of %d" % (rank, world))
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def choose_shard_axis(nT: int, nD: int, world: int) -> str:
+    """Shard theta when there are enough thetas for every rank, else thickness if that has."""
+    if nT >= world or nD < world:
+        return "theta"
+    return "thick"
+
+
+def _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, phys, t_range=None, d_range=None, keep=None):
+    """Builds the sshg_problem struct; `keep` collects the arrays whose memory it points to."""
+    def host(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return a
+
+    def addr(a, dt):
+        if isinstance(a, np.ndarray) or not hasattr(a, "data_ptr"):
+            return host(a, dt).ctypes.data
+        keep.append(a)
+        return a.data_ptr()
+
+    def size(a):
+        return int(a.numel()) if hasattr(a, "numel") else int(np.asarray(a).size)
+
+    nE, nT, nP, nD = size(energy), size(theta), size(phi), size(thick)
+    t0, t1 = t_range if t_range is not None else (0, nT)
+    d0, d1 = d_range if d_range is not None else (0, nD)
+    return _lib.Problem(nE=nE, nT=nT, nP=nP, nD=nD,
+                        energy_eV=addr(energy, np.float64), theta_deg=addr(theta, np.float64),
+                        phi_deg=addr(phi, np.float64), thick_nm=addr(thick, np.float64),
+                        eps1w=addr(eps1w, np.complex128), eps2w=addr(eps2w, np.complex128),
+                        chi2=addr(chi2, np.complex128), phys=phys, t0=t0, t1=t1, d0=d0, d1=d1)
+
+
+def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, consts=None, sinc_normalized=True,
+                    zzz_phi_quirk=True, t_range=None, d_range=None, out=None, pinned=False):
+    """Host arrays in, host cube out: float64 [T_shard, D_shard, 4, P, E].  The library computes
+    slabs on the device and copies slab k back while slab k+1 is computed."""
+    ctx = _lib.context()
+    keep = []
+    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, _physics(consts, mref, sinc_normalized, zzz_phi_quirk),
+                 t_range, d_range, keep)
+    shape = (p.t1 - p.t0, p.d1 - p.d0, 4, p.nP, p.nE)
+    if keep[4].shape != (3, p.nE) or keep[5].shape != (3, p.nE) or keep[6].shape != (18, p.nE):
+        raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
+    if out is None:
+        out = _lib.pinned_empty(shape) if pinned else np.empty(shape)
+    elif out.shape != shape or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
+    _lib.check(ctx.lib.sshg_yield(ctx.handle, C.byref(p), out.ctypes.data, _lib.HOST), ctx.lib)
+    return out
+
+
+def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, mref=True, consts=None,
+                      sinc_normalized=True, zzz_phi_quirk=True, t_range=None, d_range=None, stream=None):
+    """Device-resident sweep: every array is a CUDA torch tensor (float64 / complex128), `out` a
+    float64 CUDA tensor [T_shard, D_shard, 4, P, E] (allocated if None).  Asynchronous: the kernels
+    are queued on torch's current stream (or `stream`)."""
+    import torch
+    ctx = _lib.context(energy.device.index)
+    s = stream if stream is not None else torch.cuda.current_stream(energy.device)
+    ctx.set_stream(s.cuda_stream)
+    keep = []
+    for t, dt in ((energy, torch.float64), (theta, torch.float64), (phi, torch.float64), (thick, torch.float64),
+                  (eps1w, torch.complex128), (eps2w, torch.complex128), (chi2, torch.complex128)):
+        if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
+            raise ValueError("device sweep needs contiguous CUDA tensors of float64 / complex128")
+    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, _physics(consts, mref, sinc_normalized, zzz_phi_quirk),
+                 t_range, d_range, keep)
+    shape = (p.t1 - p.t0, p.d1 - p.d0, 4, p.nP, p.nE)
+    if tuple(eps1w.shape) != (3, p.nE) or tuple(eps2w.shape) != (3, p.nE) or tuple(chi2.shape) != (18, p.nE):
+        raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
+    if out is None:
+        out = torch.empty(shape, dtype=torch.float64, device=energy.device)
+    elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
+        raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
+    _lib.check(ctx.lib.sshg_yield(ctx.handle, C.byref(p), out.data_ptr(), _lib.DEVICE), ctx.lib)
+    return out
+
+
+def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0, sigma_chi=0.0,
+                  sigma_out=0.0, mode="3-layer", mref=True, device=True, shard=None, gather=False):
+    """
+    Sweep with the reference's material arguments (same meaning as shg.shgyield) over explicit 1-D
+    axes energy[E], theta[T], phi[P], thick[D].  Returns {'energy','theta','phi','thick',
+    'cube': [T, D, 4, P, E], 'pp','ps','sp','ss': views [T, D, P, E]} -- torch CUDA tensors when
+    `device` (default), else NumPy arrays.
+
+    shard=(rank, world[, 'theta'|'thick']) computes only that rank's slab; with gather=True and an
+    initialised torch.distributed process group the slabs are gathered on every rank (all_gather).
+    sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles).
+    """
+    energy = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
+    theta = np.atleast_1d(np.asarray(theta, dtype=np.float64)).ravel()
+    phi = np.atleast_1d(np.asarray(phi, dtype=np.float64)).ravel()
+    thick = np.atleast_1d(np.asarray(thick, dtype=np.float64)).ravel()
+    consts = physical_constants()
+    eps1w, eps2w, chi_rot, thick_eff = _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
+                                                sigma_chi, mode)
+    thick = np.atleast_1d(np.asarray(thick_eff, dtype=np.float64)).ravel()
+    t_range = d_range = None
+    if shard is not None:
+        rank, world = int(shard[0]), int(shard[1])
+        axis = shard[2] if len(shard) > 2 else choose_shard_axis(theta.size, thick.size, world)
+        if axis == "theta":
+            t_range = shard_bounds(theta.size, world, rank)
+        else:
+            d_range = shard_bounds(thick.size, world, rank)
+    if device:
+        import torch
+        dev = torch.device("cuda", _lib.context().device)
+        put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+        cube = yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
+                                 mref=mref, consts=consts, t_range=t_range, d_range=d_range)
+        if sigma_out > 1e-15:
+            cube = broaden_energy_device(cube, sigma_out)
+        if gather and shard is not None:
+            cube = gather_slabs(cube, theta.size, thick.size, shard)
+    else:
+        cube = yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi_rot, mref=mref, consts=consts,
+                               t_range=t_range, d_range=d_range)
+        if sigma_out > 1e-15:
+            from .shg import _gauss_axis
+            cube = _gauss_axis(_lib.context(), cube, sigma_out, cube.ndim - 1)
+    res = {"energy": energy, "theta": theta, "phi": phi, "thick": thick, "cube": cube}
+    for k, pol in enumerate(POLS):
+        res[pol] = cube[:, :, k]
+    return res
+
+
+def broaden_energy_device(cube, sigma):
+    """K1 along the energy (last, contiguous) axis of a device cube; returns a new tensor."""
+    import torch
+    ctx = _lib.context(cube.device.index)
+    ctx.set_stream(torch.cuda.current_stream(cube.device).cuda_stream)
+    out = torch.empty_like(cube)
+    n = cube.shape[-1]
+    rows = cube.numel() // n
+    _lib.check(ctx.lib.sshg_gauss1d(ctx.handle, cube.data_ptr(), out.data_ptr(), rows, n, n, 1, float(sigma),
+                                    _lib.DEVICE), ctx.lib)
+    return out
+
+
+def gather_slabs(slab, nT: int, nD: int, shard):
+    """all_gather of the per-rank slabs into the full cube [T, D, 4, P, E] (every rank gets it).
+    Works on CUDA tensors (NCCL) and CPU tensors (gloo; used by the CPU tests of the host logic).
+    Theta shards are contiguous blocks of the cube; uneven shards are padded to the largest."""
+    import torch
+    import torch.distributed as dist
+    rank, world = int(shard[0]), int(shard[1])
+    axis = shard[2] if len(shard) > 2 else choose_shard_axis(nT, nD, world)
+    n_axis = nT if axis == "theta" else nD
+    dim = 0 if axis == "theta" else 1
+    bounds = [shard_bounds(n_axis, world, r) for r in range(world)]
+    widest = max(hi - lo for lo, hi in bounds)
+    pad_shape = list(slab.shape)
+    pad_shape[dim] = widest
+    if slab.shape[dim] == widest:
+        mine = slab.contiguous()
+    else:
+        mine = torch.zeros(pad_shape, dtype=slab.dtype, device=slab.device)
+        mine.narrow(dim, 0, slab.shape[dim]).copy_(slab)
+    parts = [torch.empty(pad_shape, dtype=slab.dtype, device=slab.device) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    full_shape = list(slab.shape)
+    full_shape[dim] = n_axis
+    full = torch.empty(full_shape, dtype=slab.dtype, device=slab.device)
+    for (lo, hi), part in zip(bounds, parts):
+        full.narrow(dim, lo, hi - lo).copy_(part.narrow(dim, 0, hi - lo))
+    return full

@@ -1,0 +1,317 @@
+"""
+Host-side mirror of the reference's `shgyield/shg.py` for the SSHG yield path.
+
+Same entry point, argument meaning, return dict and error behaviour as the reference
+(`shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0,
+sigma_chi=0.0, sigma_out=5.0, mode='3-layer', mref=True)`, reference shg.py:381), but every
+numerical stage runs in hand-written sm_100a CUDA kernels behind the C ABI of libsshg.so
+(include/sshg.h):
+
+    broad / broadC            -> sshg_gauss1d          (K1, shared-memory tiled FIR)
+    spline / splineC / EPS    -> sshg_spline_resample  (not-a-knot cubic spline)
+    rotate                    -> sshg_rotate
+    wvec .. rad_ss, |.|^2     -> sshg_yield / sshg_yield_points (K2, fused)
+
+The host only splits dicts, averages the (at most three) tensor components of a medium,
+validates, and maps NumPy broadcast shapes onto the kernels' layouts.  There is no CPU
+fallback: without libsshg.so and a B200 every compute call raises RuntimeError.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import warnings
+
+import numpy as np
+
+from . import _lib
+
+CHI2_KEYS = ("xxx", "xyy", "xzz", "xyz", "xxz", "xxy",
+             "yxx", "yyy", "yzz", "yyz", "yxz", "yxy",
+             "zxx", "zyy", "zzz", "zyz", "zxz", "zxy")          # reference shg.py:66-133
+POLS = ("pp", "ps", "sp", "ss")
+
+# grids with at least this many points go through the tiled grid kernel; smaller broadcasts
+# use the one-thread-per-point kernel (launch-latency bound either way)
+GRID_MIN_POINTS = 4096
+
+
+def physical_constants() -> dict:
+    """The four constants the reference reads from scipy.constants at run time
+    (reference shg.py:181,194,429-430); read from the same SciPy so results do not drift."""
+    from scipy import constants
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return {"h_eVs": constants.value("Planck constant in eV s"),
+                "hbar_eVs": constants.value("Planck constant over 2 pi in eV s"),
+                "eps0": constants.epsilon_0, "c": constants.c}
+
+
+def _physics(consts, mref=True, sinc_normalized=True, zzz_phi_quirk=True) -> _lib.Physics:
+    c = consts or physical_constants()
+    return _lib.Physics(c["h_eVs"], c["hbar_eVs"], c["eps0"], c["c"], int(bool(mref)), int(bool(sinc_normalized)),
+                        int(bool(zzz_phi_quirk)), 0)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: Gaussian broadening  (reference shg.py:26-35)
+# ---------------------------------------------------------------------------------------------
+def _gauss_axis(ctx, arr: np.ndarray, sigma: float, axis: int) -> np.ndarray:
+    """One axis of scipy.ndimage.gaussian_filter on a C-contiguous float64 array."""
+    out = np.empty_like(arr)
+    n = arr.shape[axis]
+    inner = int(np.prod(arr.shape[axis + 1:], dtype=np.int64))
+    outer = int(np.prod(arr.shape[:axis], dtype=np.int64))
+    lib = ctx.lib
+    if inner == 1:
+        _lib.check(lib.sshg_gauss1d(ctx.handle, arr.ctypes.data, out.ctypes.data, outer, n, n, 1, float(sigma),
+                                    _lib.HOST), lib)
+    else:
+        blk = n * inner * arr.itemsize
+        for o in range(outer):
+            _lib.check(lib.sshg_gauss1d(ctx.handle, arr.ctypes.data + o * blk, out.ctypes.data + o * blk, inner, n,
+                                        1, inner, float(sigma), _lib.HOST), lib)
+    return out
+
+
+def broad(data, sigma):
+    """Gaussian broadening of a real array (sigma in samples, every axis, like the reference's
+    scipy.ndimage.gaussian_filter call, shg.py:26-28)."""
+    arr = np.ascontiguousarray(data, dtype=np.float64)
+    sigma = float(sigma)
+    if arr.ndim == 0 or arr.size == 0 or not sigma > 1e-15:
+        return arr.copy()
+    ctx = _lib.context()
+    for ax in range(arr.ndim):
+        arr = _gauss_axis(ctx, arr, sigma, ax)
+    return arr
+
+
+def broadC(data, sigma):
+    """Gaussian broadening of a complex array, real and imaginary parts separately (shg.py:31-35)."""
+    data = np.asarray(data)
+    return broad(data.real, sigma) + 1j * broad(data.imag, sigma)
+
+
+# ---------------------------------------------------------------------------------------------
+# spline resampling  (reference shg.py:38-55)
+# ---------------------------------------------------------------------------------------------
+class _DeviceSpline:
+    """Callable stand-in for InterpolatedUnivariateSpline(energy, data, ext=2)."""
+
+    def __init__(self, data, energy):
+        self.x = np.ascontiguousarray(energy, dtype=np.float64)
+        self.y = np.ascontiguousarray(data, dtype=np.float64)
+        if self.x.ndim != 1 or self.x.shape != self.y.shape:
+            raise ValueError("x and y should have a same length")
+
+    def __call__(self, xq):
+        q = np.asarray(xq, dtype=np.float64)
+        return _resample_rows(self.x, self.y[None, :], q.ravel())[0].reshape(q.shape)
+
+
+def _resample_rows(x, rows, xq):
+    """rows [R, n] sampled on x[n] -> [R, nq] at xq; ValueError outside the range (ext=2)."""
+    ctx = _lib.context()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    rows = np.ascontiguousarray(rows, dtype=np.float64)
+    xq = np.ascontiguousarray(xq, dtype=np.float64)
+    out = np.empty((rows.shape[0], xq.size))
+    if xq.size == 0:
+        return out
+    _lib.check(ctx.lib.sshg_spline_resample(ctx.handle, x.ctypes.data, rows.ctypes.data, rows.shape[0], x.size,
+                                            xq.ctypes.data, xq.size, out.ctypes.data, _lib.HOST), ctx.lib)
+    return out
+
+
+def spline(data, energy):
+    return _DeviceSpline(data, energy)
+
+
+def splineC(data, energy):
+    data = np.asarray(data)
+    return (_DeviceSpline(data.real, energy), _DeviceSpline(data.imag, energy))
+
+
+def _resample_group(specs: dict, queries):
+    """{key: {'energy', 'data'}} -> {key: [complex array per query vector]}; spectra that share
+    an energy axis go through one kernel call."""
+    out = {k: [None] * len(queries) for k in specs}
+    groups = {}
+    for k, v in specs.items():
+        x = np.ascontiguousarray(v["energy"], dtype=np.float64)
+        groups.setdefault((x.size, x.tobytes()), (x, []))[1].append(k)
+    sizes = [np.asarray(q).size for q in queries]
+    allq = np.concatenate([np.asarray(q, dtype=np.float64).ravel() for q in queries]) if queries else np.empty(0)
+    for x, keys in groups.values():
+        rows = np.empty((2 * len(keys), x.size))
+        for i, k in enumerate(keys):
+            d = np.asarray(specs[k]["data"])
+            if d.shape != x.shape:
+                raise ValueError("x and y should have a same length")
+            rows[2 * i], rows[2 * i + 1] = d.real, d.imag
+        res = _resample_rows(x, rows, allq)
+        off = 0
+        for j, (q, sz) in enumerate(zip(queries, sizes)):
+            for i, k in enumerate(keys):
+                out[k][j] = (res[2 * i, off:off + sz] + 1j * res[2 * i + 1, off:off + sz]).reshape(np.shape(q))
+            off += sz
+    return out
+
+
+def splineEPS(data, energy):
+    """Every epsilon component at E and at 2E (reference shg.py:50-55)."""
+    energy = np.asarray(energy, dtype=np.float64)
+    r = _resample_group(data, [energy, 2 * energy])
+    return ({k: v[0] for k, v in r.items()}, {k: v[1] for k, v in r.items()})
+
+
+def avgEPS(data):
+    """Mean over the tensor components of one medium (reference shg.py:58-60); a medium that mixes
+    numbers and spectra fails with ValueError exactly like the reference."""
+    return np.mean(list(data.values()), axis=0)
+
+
+# ---------------------------------------------------------------------------------------------
+# chi2 rotation  (reference shg.py:63-134)
+# ---------------------------------------------------------------------------------------------
+def rotate(chi2, rotang, xxy_quirk=True):
+    """In-plane rotation; `rotang` in radians as in the reference (which passes radians(gamma))."""
+    shape = np.broadcast_shapes(*[np.shape(chi2[k]) for k in CHI2_KEYS])     # KeyError if a key is missing
+    n = int(np.prod(shape, dtype=np.int64))
+    packed = np.empty((18, n), dtype=np.complex128)
+    for i, k in enumerate(CHI2_KEYS):
+        packed[i] = np.broadcast_to(np.asarray(chi2[k], dtype=np.complex128), shape).ravel()
+    out = _rotate_packed(packed, np.degrees(rotang), xxy_quirk)
+    return {k: out[i].reshape(shape) for i, k in enumerate(CHI2_KEYS)}
+
+
+def _rotate_packed(packed, gamma_deg, xxy_quirk=True):
+    ctx = _lib.context()
+    out = np.empty_like(packed)
+    _lib.check(ctx.lib.sshg_rotate(ctx.handle, packed.ctypes.data, out.ctypes.data, packed.shape[1],
+                                   float(gamma_deg), int(bool(xxy_quirk)), _lib.HOST), ctx.lib)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# K2: the fused yield kernel
+# ---------------------------------------------------------------------------------------------
+def yield_points(energy, eidx, theta, phi, thick, eps1w, eps2w, chi2, mref=True, consts=None,
+                 sinc_normalized=True, zzz_phi_quirk=True):
+    """Independent points: point i uses spectra column eidx[i].  Returns float64 [4, n] (pp, ps, sp, ss)."""
+    ctx = _lib.context()
+    eidx = np.ascontiguousarray(eidx, dtype=np.int64)
+    n = eidx.size
+    a = dict(energy=np.ascontiguousarray(energy, dtype=np.float64),
+             theta=np.ascontiguousarray(np.broadcast_to(theta, (n,)), dtype=np.float64),
+             phi=np.ascontiguousarray(np.broadcast_to(phi, (n,)), dtype=np.float64),
+             thick=np.ascontiguousarray(np.broadcast_to(thick, (n,)), dtype=np.float64),
+             eps1w=np.ascontiguousarray(eps1w, dtype=np.complex128),
+             eps2w=np.ascontiguousarray(eps2w, dtype=np.complex128),
+             chi2=np.ascontiguousarray(chi2, dtype=np.complex128))
+    nE = a["energy"].size
+    if a["eps1w"].shape != (3, nE) or a["eps2w"].shape != (3, nE) or a["chi2"].shape != (18, nE):
+        raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
+    out = np.empty((4, n))
+    if n == 0:
+        return out
+    p = _lib.Points(n=n, nE=nE, energy_eV=a["energy"].ctypes.data, eidx=eidx.ctypes.data,
+                    theta_deg=a["theta"].ctypes.data, phi_deg=a["phi"].ctypes.data, thick_nm=a["thick"].ctypes.data,
+                    eps1w=a["eps1w"].ctypes.data, eps2w=a["eps2w"].ctypes.data, chi2=a["chi2"].ctypes.data,
+                    phys=_physics(consts, mref, sinc_normalized, zzz_phi_quirk))
+    _lib.check(ctx.lib.sshg_yield_points(ctx.handle, C.byref(p), out.ctypes.data, _lib.HOST), ctx.lib)
+    return out
+
+
+def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode):
+    """Reference shg.py:387-426: broaden, resample at E / 2E, average, map the mode, rotate.
+    Returns (eps1w [3,nE], eps2w [3,nE], chi_rot [18,nE], thick) for the flattened energies."""
+    energy = np.asarray(energy, dtype=np.float64)
+    nE = energy.size
+    media = []
+    for eps_m in (eps_m1, eps_m2, eps_m3):
+        num = {k: v for k, v in eps_m.items() if not isinstance(v, dict)}
+        brd = {k: {"energy": v["energy"], "data": broadC(v["data"], sigma_eps)}
+               for k, v in eps_m.items() if isinstance(v, dict)}
+        one, two = splineEPS(brd, energy)
+        one.update(num)
+        two.update(num)
+        media.append((one, two))
+    if mode == "3-layer":
+        e1 = [avgEPS(media[0][0]), avgEPS(media[1][0]), avgEPS(media[2][0])]
+        e2 = [avgEPS(media[0][1]), avgEPS(media[1][1]), avgEPS(media[2][1])]
+    elif mode == "fresnel" or mode == "2-layer":
+        thick = 0
+        e1 = [avgEPS(media[0][0]), avgEPS(media[2][0]), avgEPS(media[2][0])]
+        e2 = [avgEPS(media[0][1]), avgEPS(media[0][1]), avgEPS(media[2][1])]
+    else:
+        # the reference fails here by accident (UnboundLocalError, shg.py:405-420); documented deviation
+        raise ValueError("unknown mode %r (expected '3-layer', 'fresnel' or '2-layer')" % (mode,))
+    eps1w = np.empty((3, nE), dtype=np.complex128)
+    eps2w = np.empty((3, nE), dtype=np.complex128)
+    for m in range(3):
+        eps1w[m] = np.broadcast_to(np.asarray(e1[m], dtype=np.complex128), energy.shape).ravel()
+        eps2w[m] = np.broadcast_to(np.asarray(e2[m], dtype=np.complex128), energy.shape).ravel()
+
+    chi_num = {k: v for k, v in chi2.items() if not isinstance(v, dict)}
+    chi_brd = {k: {"energy": v["energy"], "data": broadC(v["data"], sigma_chi)}
+               for k, v in chi2.items() if isinstance(v, dict)}
+    chi_new = {k: v[0] for k, v in _resample_group(chi_brd, [energy]).items()}
+    chi_new.update(chi_num)
+    packed = np.empty((18, nE), dtype=np.complex128)
+    for i, k in enumerate(CHI2_KEYS):
+        packed[i] = np.broadcast_to(np.asarray(chi_new[k], dtype=np.complex128), energy.shape).ravel()   # KeyError like the reference
+    chi_rot = _rotate_packed(packed, float(gamma)) if nE else packed
+    return eps1w, eps2w, chi_rot, thick
+
+
+def _axes_of(shape, ndim):
+    """Axes (in the ndim-dimensional broadcast result) along which an operand of `shape` varies."""
+    pad = (1,) * (ndim - len(shape)) + tuple(shape)
+    return tuple(i for i, s in enumerate(pad) if s != 1)
+
+
+def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0, sigma_chi=0.0,
+             sigma_out=5.0, mode="3-layer", mref=True):
+    """
+    SSHG yield R_pP, R_pS, R_sP, R_sS (cm^2/W), Eq. (38) of PRB 94, 115314 (2016).
+    Drop-in for the reference's shg.shgyield (shg.py:381-437): angles in degrees, `thick` in nm,
+    sigmas in samples; energy / theta / phi / thick broadcast like NumPy arrays.
+    Returns {'energy': energy, 'phi': phi, 'pp', 'ps', 'sp', 'ss'} (key 'ps' = p in, S out).
+    """
+    consts = physical_constants()
+    e_arr = np.asarray(energy, dtype=np.float64)
+    eps1w, eps2w, chi_rot, thick = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
+                                            sigma_chi, mode)
+    t_arr, p_arr, d_arr = (np.asarray(v, dtype=np.float64) for v in (theta, phi, thick))
+    shape = np.broadcast_shapes(e_arr.shape, t_arr.shape, p_arr.shape, d_arr.shape)
+    ndim = len(shape)
+    n = int(np.prod(shape, dtype=np.int64))
+    res = None
+    if n >= GRID_MIN_POINTS:
+        ax = [_axes_of(a.shape, ndim) for a in (t_arr, d_arr, p_arr, e_arr)]       # cube order T, D, P, E
+        flat = [a for axes in ax for a in axes]
+        if len(set(flat)) == len(flat):                                             # outer-product structure
+            from .grid import yield_grid_host
+            cube = yield_grid_host(e_arr.ravel(), t_arr.ravel(), p_arr.ravel(), d_arr.ravel(), eps1w, eps2w, chi_rot,
+                                   mref=mref, consts=consts)                       # [T, D, 4, P, E]
+            missing = [i for i in range(ndim) if i not in flat]                     # axes of extent 1
+            order = flat + missing
+            blocks = [tuple(shape[i] for i in axes) for axes in ax]
+            res = []
+            for k in range(4):
+                r = cube[:, :, k].reshape(sum(blocks, ()) + (1,) * len(missing))
+                res.append(np.ascontiguousarray(np.transpose(r, np.argsort(order))).reshape(shape))
+    if res is None:
+        if n:
+            eidx = np.broadcast_to(np.arange(e_arr.size, dtype=np.int64).reshape(e_arr.shape), shape).ravel()
+            bc = lambda a: np.broadcast_to(a, shape).ravel()
+            y = yield_points(e_arr.ravel(), eidx, bc(t_arr), bc(p_arr), bc(d_arr), eps1w, eps2w, chi_rot, mref=mref,
+                             consts=consts)
+        else:
+            y = np.empty((4, 0))
+        res = [y[k].reshape(shape) for k in range(4)]
+    out = {"energy": energy, "phi": phi}
+    for k, pol in enumerate(POLS):
+        out[pol] = broad(res[k], sigma_out)
+    return out

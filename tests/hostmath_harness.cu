@@ -1,0 +1,53 @@
+// TEST HARNESS (not part of libsshg.so): runs the __host__ __device__ physics of
+// shgyield_b200/csrc/sshg_math.cuh on the CPU so that the formulas can be checked against the
+// golden vectors in the GPU-less build container.  Built by tests/test_hostmath.py.
+#include "../shgyield_b200/csrc/sshg_math.cuh"
+#include "../include/sshg.h"
+#include <math.h>
+
+using namespace sshg;
+
+extern "C" int hostmath_yield_points(const sshg_points* p, double* out) {
+    Physics ph;
+    ph.kd = 1e-9 / (p->phys.h_eVs * p->phys.c);
+    ph.pref = 100.0 / (p->phys.hbar_eVs * sqrt(2.0 * p->phys.eps0 * p->phys.c * p->phys.c * p->phys.c));
+    ph.mref = p->phys.mref;
+    ph.sinc_normalized = p->phys.sinc_normalized;
+    ph.zzz_phi_quirk = p->phys.zzz_phi_quirk;
+    const long long nE = p->nE, n = p->n;
+    for (long long i = 0; i < n; ++i) {
+        const long long e = p->eidx[i];
+        double st, ct;
+        sincos(p->theta_deg[i] * (3.141592653589793 / 180.0), &st, &ct);
+        cplx e1[3], e2[3];
+        for (int m = 0; m < 3; ++m) {
+            e1[m] = mk(p->eps1w[2 * (m * nE + e)], p->eps1w[2 * (m * nE + e) + 1]);
+            e2[m] = mk(p->eps2w[2 * (m * nE + e)], p->eps2w[2 * (m * nE + e) + 1]);
+        }
+        const Column c = column_setup(e1, e2, p->energy_eV[e], st, ct, p->thick_nm[i], ph);
+        double b[6];
+        phi_basis(p->phi_deg[i], b);
+        auto chi = [&](int r) { return mk(p->chi2[2 * (r * nE + e)], p->chi2[2 * (r * nE + e) + 1]); };
+        for (int pol = 0; pol < 3; ++pol) {
+            cplx k[7];
+            if (pol == 0) coeffs_pp(c, chi, ph, k);
+            else if (pol == 1) coeffs_ps(c, chi, k);
+            else coeffs_sp(c, chi, k);
+            double re = k[0].re, im = k[0].im;
+            for (int j = 0; j < 6; ++j) {
+                re = fma(k[j + 1].re, b[j], re);
+                im = fma(k[j + 1].im, b[j], im);
+            }
+            out[pol * n + i] = fma(re, re, im * im);
+        }
+        cplx k[4];
+        coeffs_ss(c, chi, k);
+        double re = k[0].re * b[2], im = k[0].im * b[2];
+        for (int j = 1; j < 4; ++j) {
+            re = fma(k[j].re, b[j + 2], re);
+            im = fma(k[j].im, b[j + 2], im);
+        }
+        out[3 * n + i] = fma(re, re, im * im);
+    }
+    return 0;
+}

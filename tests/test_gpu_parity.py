@@ -1,0 +1,369 @@
+"""
+GPU parity tests (run with -m gpu on a B200): every call goes through the C ABI of libsshg.so.
+The CPU oracle (oracle/shg_oracle.py) and the golden fixtures (tests/golden/, produced by the
+unmodified reference) are the checkers.  Tolerance: FP64, relative 1e-10 in the metric of
+tests/cases.py::parity_ok (north_star: "within a relative tolerance of 1e-10").
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shg_oracle as orc
+from tests import cases, util
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+G = cases.GOLDEN_DIR
+
+
+@pytest.fixture(scope="module")
+def shg():
+    from shgyield_b200 import shg as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def grid():
+    from shgyield_b200 import grid as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def consts():
+    return util.load_consts()
+
+
+@pytest.fixture(scope="module")
+def spectra():
+    return cases.load_spectra()
+
+
+def test_scipy_constants_match_fixture(shg, consts):
+    assert shg.physical_constants() == consts
+
+
+# ---- K1: Gaussian broadening vs the live SciPy ---------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 7, 126, 1024, 1025, 2001, 20000])
+@pytest.mark.parametrize("sigma", [0.0, 0.2, 3.3, 5.0, 50.0])
+def test_gauss_matches_scipy(shg, n, sigma):
+    from scipy import ndimage
+    x = np.random.default_rng(n).normal(size=n)
+    got = shg.broad(x, sigma)
+    want = ndimage.gaussian_filter(x, sigma)
+    np.testing.assert_allclose(got, want, rtol=0, atol=4e-15 * max(1.0, np.max(np.abs(x))))
+    if sigma == 0.0:
+        np.testing.assert_array_equal(got, x)
+
+
+def test_gauss_huge_radius_and_nd(shg):
+    from scipy import ndimage
+    x = np.random.default_rng(1).normal(size=50)
+    np.testing.assert_allclose(shg.broad(x, 7000.0), ndimage.gaussian_filter(x, 7000.0), rtol=0, atol=1e-13)
+    y = np.random.default_rng(2).normal(size=(6, 1, 33, 5))
+    np.testing.assert_allclose(shg.broad(y, 1.7), ndimage.gaussian_filter(y, 1.7), rtol=0, atol=1e-14)
+    z = np.random.default_rng(3).normal(size=40) + 1j * np.random.default_rng(4).normal(size=40)
+    want = ndimage.gaussian_filter(z.real, 2.5) + 1j * ndimage.gaussian_filter(z.imag, 2.5)
+    np.testing.assert_allclose(shg.broadC(z, 2.5), want, rtol=0, atol=1e-14)
+
+
+def test_gauss_matches_oracle_restatement(shg):
+    x = np.random.default_rng(9).normal(size=(3, 300))
+    np.testing.assert_allclose(shg.broad(x, 4.0), orc.gaussian_filter(x, 4.0), rtol=0, atol=1e-14)
+
+
+# ---- spline resampling vs FITPACK ---------------------------------------------------------------
+def test_spline_matches_fitpack(shg, spectra):
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    e = spectra["energy"]
+    q = np.concatenate([np.linspace(0.0, 20.0, 3777), e[:50], [e[-1]]])
+    for name in ("SiH1x1-chi1-xx", "SiBulk-chi1-zz", "SiH1x1-chi2-zzz"):
+        for row in spectra[name][:2]:
+            want = InterpolatedUnivariateSpline(e, row, ext=2)(q)
+            got = shg.spline(row, e)(q)
+            np.testing.assert_allclose(got, want, rtol=0, atol=2e-13 * np.max(np.abs(row)))
+    re, im = shg.splineC(spectra["SiH1x1-chi1-xx"][0] + 1j * spectra["SiH1x1-chi1-xx"][1], e)
+    assert re(np.array([1.0])).shape == (1,) and im(2.0).shape == ()
+
+
+def test_spline_nonuniform_axis(shg):
+    from scipy.interpolate import InterpolatedUnivariateSpline
+    rng = np.random.default_rng(0)
+    x = np.cumsum(rng.uniform(0.05, 1.0, 57))
+    y = rng.normal(size=57)
+    q = rng.uniform(x[0], x[-1], 500)
+    np.testing.assert_allclose(shg.spline(y, x)(q), InterpolatedUnivariateSpline(x, y, ext=2)(q), rtol=0, atol=1e-11)
+    for n in (4, 5):
+        np.testing.assert_allclose(shg.spline(y[:n], x[:n])(x[:n]), y[:n], rtol=0, atol=1e-13)
+
+
+def test_spline_out_of_range_raises(shg, spectra):
+    e = spectra["energy"]
+    with pytest.raises(ValueError):
+        shg.spline(spectra["SiH1x1-chi1-xx"][0], e)(np.array([1.0, 20.5]))
+    with pytest.raises(ValueError):
+        shg.spline(spectra["SiH1x1-chi1-xx"][0], e)(np.array([-0.1]))
+
+
+# ---- rotate ---------------------------------------------------------------------------------------
+def test_rotate_matches_reference(shg):
+    z = np.load(os.path.join(G, "ref_helpers.npz"))
+    chi = {k: z["rot_in"][i] for i, k in enumerate(cases.CHI2_KEYS)}
+    for g in (0.0, 17.0, 90.0, 123.4, 270.0):
+        r = shg.rotate(chi, np.radians(g))
+        got = np.stack([r[k] for k in cases.CHI2_KEYS])
+        np.testing.assert_allclose(got, z["rot_out_%g" % g], rtol=0, atol=2e-14)
+    with pytest.raises(KeyError):
+        shg.rotate({k: 1.0 for k in cases.CHI2_KEYS[:-1]}, 0.3)
+
+
+def test_rotate_without_quirk_is_a_true_rotation(shg):
+    """rotating by g then by -g (about the internal angle) must return the input only for the
+    true rotation; documents the xxy/yyy sign of the reference (shg.py:92)."""
+    rng = np.random.default_rng(5)
+    chi = {k: rng.normal(size=3) + 1j * rng.normal(size=3) for k in cases.CHI2_KEYS}
+    fwd = shg.rotate(chi, np.radians(90 - 37.0), xxy_quirk=False)       # internal angle +37
+    back = shg.rotate(fwd, np.radians(90 + 37.0), xxy_quirk=False)      # internal angle -37
+    for k in cases.CHI2_KEYS:
+        np.testing.assert_allclose(back[k], chi[k], rtol=0, atol=1e-14)
+
+
+# ---- K2 at kernel level -------------------------------------------------------------------------
+def test_points_kernel_config5_samples(shg, consts):
+    from shgyield_b200.synthetic import synthetic_spectra
+    z = np.load(os.path.join(G, "ref_grid_samples.npz"))
+    idx = z["c5_idx"]
+    energy, eps1w, eps2w, chi = synthetic_spectra(20000)
+    theta, phi = np.linspace(0.0, 90.0, 181), np.linspace(0.0, 360.0, 721)
+    out = shg.yield_points(energy, idx[:, 3], theta[idx[:, 0]], phi[idx[:, 2]], 10.0, eps1w, eps2w, chi, consts=consts)
+    sc = cases.case_scale(z, "c5_")
+    for i, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(out[i], z["c5_" + pol], rtol=RTOL, scale=sc)
+        assert ok, (pol, msg)
+
+
+def _oracle_cube(cfg, consts, **kw):
+    e1 = {"M%d" % (m + 1): cfg["eps1w"][m] for m in range(3)}
+    e2 = {"M%d" % (m + 1): cfg["eps2w"][m] for m in range(3)}
+    ch = {k: cfg["chi2"][i] for i, k in enumerate(cases.CHI2_KEYS)}
+    T, D, P = cfg["theta"].size, cfg["thick"].size, cfg["phi"].size
+    y = orc.yield_points(cfg["energy"], e1, e2, ch, cfg["theta"].reshape(T, 1, 1, 1), cfg["phi"].reshape(1, 1, P, 1),
+                         cfg["thick"].reshape(1, D, 1, 1), consts=consts, **kw)
+    return np.stack([np.broadcast_to(y[p], (T, D, P, cfg["energy"].size)) for p in cases.POLS], axis=2)
+
+
+def _small_cfg(nE, theta, phi, thick, seed=1):
+    from shgyield_b200.synthetic import synthetic_spectra
+    energy, eps1w, eps2w, chi = synthetic_spectra(nE, seed=seed)
+    return dict(energy=energy, theta=np.asarray(theta, float), phi=np.asarray(phi, float),
+                thick=np.asarray(thick, float), eps1w=eps1w, eps2w=eps2w, chi2=chi)
+
+
+GRID_SHAPES = [
+    # nE, theta, phi, thick                                  what it exercises
+    (1, [65.0], [30.0], [10.0]),                             # a single point
+    (126, [65.0], [30.0], [10.0]),                           # config-1 shape
+    (513, [0.0, 33.0, 90.0], np.arange(0, 360, 15.0), [10.0]),    # odd nE (64-bit stores), (phi, phi+180) pairs
+    (600, [10.0, 80.0], np.linspace(0, 360, 41), [0.0, 7.5]),     # pairs + one un-paired row, two thicknesses
+    (64, [45.0], np.linspace(0, 350, 7), [3.0]),             # no pairing possible
+    (1030, [20.0, 40.0], [0.0, 180.0], [5.0]),               # two tiles, one pair
+    (40, np.arange(0, 90, 9.0), [30.0], np.arange(1.0, 31.0)),    # config-4 shape (P = 1)
+    (30, [55.0], np.linspace(0, 360, 1001), [12.0]),         # more than one phi chunk (500 pairs + 1)
+]
+
+
+@pytest.mark.parametrize("nE,theta,phi,thick", GRID_SHAPES, ids=[str(i) for i in range(len(GRID_SHAPES))])
+def test_grid_kernel_matches_oracle(grid, consts, nE, theta, phi, thick):
+    cfg = _small_cfg(nE, theta, phi, thick)
+    got = grid.yield_grid_host(**cfg, consts=consts)
+    want = _oracle_cube(cfg, consts)
+    assert got.shape == want.shape
+    for k, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(got[:, :, k], want[:, :, k], rtol=RTOL, scale=np.max(want))
+        assert ok, (pol, msg)
+
+
+@pytest.mark.parametrize("kw", [dict(mref=False), dict(sinc_normalized=False), dict(zzz_phi_quirk=False)])
+def test_grid_kernel_switches(grid, consts, kw):
+    cfg = _small_cfg(200, [15.0, 70.0], np.arange(0, 360, 20.0), [10.0, 55.0], seed=4)
+    got = grid.yield_grid_host(**cfg, consts=consts, **kw)
+    want = _oracle_cube(cfg, consts, **kw)
+    for k, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(got[:, :, k], want[:, :, k], rtol=RTOL, scale=np.max(want))
+        assert ok, (kw, pol, msg)
+
+
+def test_grid_shards_are_bitwise_slices(grid, consts):
+    """Sharding changes no arithmetic: every shard equals the slice of the full cube bit for bit."""
+    cfg = _small_cfg(300, np.linspace(0, 90, 11), np.arange(0, 360, 10.0), [4.0, 9.0, 14.0], seed=2)
+    full = grid.yield_grid_host(**cfg, consts=consts)
+    for world in (2, 4, 8):
+        for rank in range(world):
+            lo, hi = grid.shard_bounds(11, world, rank)
+            part = grid.yield_grid_host(**cfg, consts=consts, t_range=(lo, hi))
+            assert np.array_equal(part, full[lo:hi])
+    lo, hi = grid.shard_bounds(3, 2, 1)
+    assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, d_range=(lo, hi)), full[:, lo:hi])
+
+
+def test_grid_device_and_host_paths_agree(grid, consts):
+    """Device-resident output vs host output through the slab pipeline (several slabs, pinned)."""
+    import torch
+    cfg = _small_cfg(4096, np.linspace(5, 85, 40), np.arange(0, 360, 2.0), [10.0], seed=6)   # 944 MB cube
+    dev = torch.device("cuda", 0)
+    put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    cube = grid.yield_grid_device(put(cfg["energy"]), put(cfg["theta"]), put(cfg["phi"]), put(cfg["thick"]),
+                                  put(cfg["eps1w"]), put(cfg["eps2w"]), put(cfg["chi2"]), consts=consts)
+    torch.cuda.synchronize()
+    host = grid.yield_grid_host(**cfg, consts=consts, pinned=True)
+    assert np.array_equal(cube.cpu().numpy(), host)
+    # and the sampled oracle
+    rng = np.random.default_rng(0)
+    it, ip, ie = rng.integers(0, 40, 2000), rng.integers(0, 180, 2000), rng.integers(0, 4096, 2000)
+    e1 = {"M%d" % (m + 1): cfg["eps1w"][m][ie] for m in range(3)}
+    e2 = {"M%d" % (m + 1): cfg["eps2w"][m][ie] for m in range(3)}
+    ch = {k: cfg["chi2"][i][ie] for i, k in enumerate(cases.CHI2_KEYS)}
+    want = orc.yield_points(cfg["energy"][ie], e1, e2, ch, cfg["theta"][it], cfg["phi"][ip], 10.0, consts=consts)
+    for k, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(host[it, 0, k, ip, ie], want[pol], rtol=RTOL, scale=max(np.max(want[p]) for p in cases.POLS))
+        assert ok, (pol, msg)
+    from shgyield_b200 import _lib
+    _lib.pinned_free(host)
+
+
+# ---- the drop-in API against the reference's outputs -------------------------------------------------
+@pytest.mark.parametrize("name,mat,kw", cases.API_CASES, ids=[c[0] for c in cases.API_CASES])
+def test_api_cases_match_reference(shg, spectra, name, mat, kw):
+    gold = np.load(os.path.join(G, "ref_api_cases.npz"))
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](spectra)
+    res = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, **kw)
+    assert set(res) == {"energy", "phi", "pp", "ps", "sp", "ss"}
+    assert res["energy"] is kw["energy"] and res["phi"] is kw["phi"]
+    sc = cases.case_scale(gold, name + "_")
+    for pol in cases.POLS:
+        want = np.asarray(gold[name + "_" + pol])
+        assert np.shape(res[pol]) == want.shape and res[pol].dtype == np.float64
+        ok, msg = cases.parity_ok(res[pol], want, rtol=RTOL, scale=sc)
+        assert ok, (name, pol, msg)
+
+
+def test_api_grid_path_matches_points_path(shg, spectra, monkeypatch):
+    """The broadcast call of the 'bcast3d' case through the tiled grid kernel (threshold lowered)."""
+    gold = np.load(os.path.join(G, "ref_api_cases.npz"))
+    name, mat, kw = next(c for c in cases.API_CASES if c[0] == "bcast3d")
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](spectra)
+    monkeypatch.setattr(shg, "GRID_MIN_POINTS", 1)
+    res = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, **kw)
+    sc = cases.case_scale(gold, name + "_")
+    for pol in cases.POLS:
+        ok, msg = cases.parity_ok(res[pol], gold[name + "_" + pol], rtol=RTOL, scale=sc)
+        assert ok, (pol, msg)
+    name, mat, kw = next(c for c in cases.API_CASES if c[0] == "bcast_thick")
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](spectra)
+    res = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, **kw)
+    for pol in cases.POLS:
+        ok, msg = cases.parity_ok(res[pol], gold[name + "_" + pol], rtol=RTOL, scale=cases.case_scale(gold, name + "_"))
+        assert ok, (pol, msg)
+
+
+def test_golden_si111_reference_out(shg, spectra):
+    """The reference's own golden file example/reference/si111-reference.out (printed %.8e)."""
+    gold = np.load(os.path.join(G, "si111_reference_out.npz"))
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    res = shg.shgyield(cases.E_C1, m1, m2, m3, chi2, theta=65, phi=30, thick=10, gamma=0, sigma_eps=0.0,
+                       sigma_chi=0.0, sigma_out=5)
+    for pol in cases.POLS:
+        np.testing.assert_allclose(res[pol], gold[pol], rtol=6e-9, atol=0)
+
+
+def test_golden_selftest_reference(shg, spectra, consts):
+    """REFERENCE of the reference's tests/self_test.py: legacy sS numbers (un-normalised sinc,
+    CODATA-2014 eps0 hard-coded in self_test.py:104), tolerance of the self-test itself."""
+    gold = np.load(os.path.join(G, "selftest_reference.npz"))["REFERENCE"]
+    m1, m2, m3, chi2 = cases.selftest_material(spectra)
+    energy = np.linspace(0.01, 1.00, 100)
+    eps1w, eps2w, chi_rot, thick = shg._prepare(energy, m1, m2, m3, chi2, 10, 0, 0.0, 0.0, "3-layer")
+    c = dict(consts, eps0=8.854187817620389e-12)
+    y = shg.yield_points(energy, np.arange(100), 65.0, 30.0, thick, eps1w, eps2w, chi_rot, consts=c,
+                         sinc_normalized=False)
+    np.testing.assert_allclose(1e20 * y[3], gold, rtol=1e-6, atol=1e-12)
+
+
+def test_error_behaviour(shg, spectra):
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    kw = dict(theta=65, phi=30, thick=10, gamma=0)
+    with pytest.raises(ValueError):                 # 2E leaves the 0-20 eV data (SciPy ext=2)
+        shg.shgyield(np.linspace(9.0, 10.5, 10), m1, m2, m3, chi2, **kw)
+    with pytest.raises(KeyError):                   # a chi2 key is missing (reference shg.py:66-133)
+        shg.shgyield(cases.E_C1, m1, m2, m3, {k: v for k, v in chi2.items() if k != "zxy"}, **kw)
+    with pytest.raises(ValueError):                 # unknown mode (documented deviation: reference -> UnboundLocalError)
+        shg.shgyield(cases.E_C1, m1, m2, m3, chi2, mode="4-layer", **kw)
+    with pytest.raises(ValueError):                 # a medium mixing numbers and spectra (np.mean fails, shg.py:60)
+        shg.shgyield(cases.E_C1, m1, dict(m2, zz=1.0), m3, chi2, **kw)
+    y = shg.shgyield(np.array([0.0, 1.5]), m1, m2, m3, chi2, sigma_out=0.0, **kw)      # E = 0 -> 0, no exception
+    assert y["pp"][0] == 0.0 and np.isfinite(y["pp"][1])
+
+
+# ---- the large grids of BASELINE.json -----------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["c3", "c4"])
+def test_config3_config4_full_size(grid, spectra, tag):
+    """Full-size sweeps of the Si(111)(1x1):H material, device resident, against sampled outputs of
+    the reference plus size-independent properties."""
+    import torch
+    z = np.load(os.path.join(G, "ref_grid_samples.npz"))
+    axes = cases.config3_axes() if tag == "c3" else cases.config4_axes()
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    res = grid.shgyield_grid(axes["energy"], m1, m2, m3, chi2, axes["theta"], axes["phi"], axes["thick"],
+                             gamma=axes["gamma"], sigma_out=0.0)
+    torch.cuda.synchronize()
+    cube = res["cube"]
+    idx = torch.from_numpy(z[tag + "_idx"].astype(np.int64)).to(cube.device)
+    sc = cases.case_scale(z, tag + "_")
+    for k, pol in enumerate(cases.POLS):
+        got = cube[idx[:, 0], idx[:, 1], k, idx[:, 2], idx[:, 3]].cpu().numpy()
+        ok, msg = cases.parity_ok(got, z[tag + "_" + pol], rtol=RTOL, scale=sc)
+        assert ok, (tag, pol, msg)
+    assert bool(torch.isfinite(cube).all()) and float(cube.min()) >= 0.0
+    if tag == "c3":
+        # Si(111) C3v: R(phi) has period 120 deg; sS is symmetric under phi -> phi + 180
+        ss = res["ss"][:, 0]
+        scale = float(ss.max())
+        assert float((ss[:, :120] - ss[:, 120:240]).abs().max()) <= 1e-10 * scale
+        assert float((ss[:, :180] - ss[:, 180:]).abs().max()) <= 1e-10 * scale
+    del cube, res
+    torch.cuda.empty_cache()
+
+
+def test_config5_full_size_in_slabs(grid, consts):
+    """The 20k x 181 x 721 x 4 cube (83.5 GB) computed as theta slabs; every slab is checked against
+    the sampled reference outputs that fall into it, and phi = 0 equals phi = 360."""
+    import torch
+    from shgyield_b200.synthetic import config5
+    z = np.load(os.path.join(G, "ref_grid_samples.npz"))
+    idx_all = z["c5_idx"].astype(np.int64)
+    cfg = config5()
+    dev = torch.device("cuda", 0)
+    put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d = {k: put(v) for k, v in cfg.items()}
+    sc = cases.case_scale(z, "c5_")
+    step = 16
+    out = torch.empty((step, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
+    seen = 0
+    for t0 in range(0, 181, step):
+        t1 = min(181, t0 + step)
+        view = out[: t1 - t0]
+        grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                               out=view, consts=consts, t_range=(t0, t1))
+        torch.cuda.synchronize()
+        sel = (idx_all[:, 0] >= t0) & (idx_all[:, 0] < t1)
+        idx = torch.from_numpy(idx_all[sel]).to(dev)
+        for k, pol in enumerate(cases.POLS):
+            got = view[idx[:, 0] - t0, 0, k, idx[:, 2], idx[:, 3]].cpu().numpy()
+            ok, msg = cases.parity_ok(got, z["c5_" + pol][sel], rtol=RTOL, scale=sc)
+            assert ok, (t0, pol, msg)
+        seen += int(sel.sum())
+        top = float(view.max())
+        assert float((view[:, :, :, 0] - view[:, :, :, 720]).abs().max()) <= 1e-10 * top
+        assert bool(torch.isfinite(view).all())
+    assert seen == idx_all.shape[0]
+    assert float(out[180 - 176].abs().max()) == 0.0          # theta = 90 deg: exactly zero (w_v = 0)

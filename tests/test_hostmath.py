@@ -1,0 +1,117 @@
+"""
+CPU check of the kernel physics: shgyield_b200/csrc/sshg_math.cuh is __host__ __device__, so
+tests/hostmath_harness.cu (a TEST harness, not part of libsshg.so) runs the very same
+column_setup / coeffs_* code on the CPU.  This validates the re-organised formulas against the
+golden vectors without a GPU; the GPU tests then check the kernels themselves.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import shg_oracle as orc
+from shgyield_b200 import _lib
+from shgyield_b200.synthetic import synthetic_spectra
+from tests import cases, util
+
+pytestmark = pytest.mark.skipif(shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"),
+                                reason="nvcc not available")
+
+
+@pytest.fixture(scope="module")
+def harness():
+    src = os.path.join(util.REPO, "tests", "hostmath_harness.cu")
+    outdir = os.path.join(util.REPO, "tests", "_build")
+    os.makedirs(outdir, exist_ok=True)
+    so = os.path.join(outdir, "hostmath.so")
+    deps = [src, os.path.join(util.REPO, "shgyield_b200/csrc/sshg_math.cuh"), os.path.join(util.REPO, "include/sshg.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-fPIC", "-shared",
+                        "-I", os.path.join(util.REPO, "include"), "-o", so, src], check=True)
+    lib = C.CDLL(so)
+    lib.hostmath_yield_points.restype = C.c_int
+    lib.hostmath_yield_points.argtypes = [C.POINTER(_lib.Points), C.c_void_p]
+    return lib
+
+
+def run_points(lib, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, mref=True,
+               sinc_normalized=True, zzz_phi_quirk=True):
+    n = eidx.size
+    arrs = dict(energy=np.ascontiguousarray(energy, dtype=np.float64),
+                eidx=np.ascontiguousarray(eidx, dtype=np.int64),
+                theta=np.ascontiguousarray(np.broadcast_to(theta, (n,)), dtype=np.float64),
+                phi=np.ascontiguousarray(np.broadcast_to(phi, (n,)), dtype=np.float64),
+                thick=np.ascontiguousarray(np.broadcast_to(thick, (n,)), dtype=np.float64),
+                eps1w=np.ascontiguousarray(eps1w, dtype=np.complex128),
+                eps2w=np.ascontiguousarray(eps2w, dtype=np.complex128),
+                chi=np.ascontiguousarray(chi, dtype=np.complex128))
+    p = _lib.Points(n=n, nE=arrs["energy"].size, energy_eV=arrs["energy"].ctypes.data, eidx=arrs["eidx"].ctypes.data,
+                    theta_deg=arrs["theta"].ctypes.data, phi_deg=arrs["phi"].ctypes.data,
+                    thick_nm=arrs["thick"].ctypes.data, eps1w=arrs["eps1w"].ctypes.data,
+                    eps2w=arrs["eps2w"].ctypes.data, chi2=arrs["chi"].ctypes.data,
+                    phys=_lib.Physics(consts["h_eVs"], consts["hbar_eVs"], consts["eps0"], consts["c"],
+                                      int(mref), int(sinc_normalized), int(zzz_phi_quirk), 0))
+    out = np.empty((4, n))
+    assert lib.hostmath_yield_points(C.byref(p), out.ctypes.data) == 0
+    return out
+
+
+def test_config5_samples(harness):
+    consts = util.load_consts()
+    z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_grid_samples.npz"))
+    idx = z["c5_idx"]
+    energy, eps1w, eps2w, chi = synthetic_spectra(20000)
+    theta, phi = np.linspace(0.0, 90.0, 181), np.linspace(0.0, 360.0, 721)
+    out = run_points(harness, energy, idx[:, 3], theta[idx[:, 0]], phi[idx[:, 2]], 10.0, eps1w, eps2w, chi, consts)
+    sc = cases.case_scale(z, "c5_")
+    for i, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(out[i], z["c5_" + pol], rtol=1e-10, scale=sc)
+        assert ok, (pol, msg)
+
+
+@pytest.mark.parametrize("name,mat,kw", [c for c in cases.API_CASES if c[2].get("sigma_out", 5.0) == 0.0],
+                         ids=[c[0] for c in cases.API_CASES if c[2].get("sigma_out", 5.0) == 0.0])
+def test_api_cases_kernel_math(harness, name, mat, kw):
+    """Oracle prepares (broaden, resample, average, rotate); the harness evaluates the yield."""
+    consts = util.load_consts()
+    gold = np.load(os.path.join(cases.GOLDEN_DIR, "ref_api_cases.npz"))
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](cases.load_spectra())
+    kw = dict(kw)
+    energy = np.atleast_1d(np.asarray(kw["energy"], dtype=np.float64))
+    eps1w, eps2w, chi_rot, thick = orc.prepare(energy, m1, m2, m3, chi2, kw["thick"], kw.get("gamma", 90),
+                                               kw.get("sigma_eps", 0.0), kw.get("sigma_chi", 0.0),
+                                               kw.get("mode", "3-layer"))
+    nE = energy.size
+    shape = np.broadcast_shapes(np.shape(kw["energy"]), np.shape(kw["theta"]), np.shape(kw["phi"]), np.shape(thick))
+    eidx = np.broadcast_to(np.arange(nE).reshape(np.shape(kw["energy"]) or (1,)), shape or (1,)).ravel()
+    bc = lambda v: np.broadcast_to(np.asarray(v, dtype=np.float64), shape or (1,)).ravel()
+    out = run_points(harness, energy, eidx, bc(kw["theta"]), bc(kw["phi"]), bc(thick), util.pack_eps(eps1w, nE),
+                     util.pack_eps(eps2w, nE), util.pack_chi(chi_rot, nE), consts, mref=kw.get("mref", True))
+    sc = cases.case_scale(gold, name + "_")
+    for i, pol in enumerate(cases.POLS):
+        want = np.asarray(gold[name + "_" + pol])
+        ok, msg = cases.parity_ok(out[i].reshape(want.shape), want, rtol=1e-10, scale=sc)
+        assert ok, (name, pol, msg)
+
+
+def test_switches(harness):
+    """sinc_normalized=0 and zzz_phi_quirk=0 against the oracle with the same switches."""
+    consts = util.load_consts()
+    energy, eps1w, eps2w, chi = synthetic_spectra(64, seed=3)
+    rng = np.random.default_rng(0)
+    n = 500
+    eidx = rng.integers(0, 64, n)
+    theta, phi, thick = rng.uniform(0, 89, n), rng.uniform(0, 360, n), rng.uniform(0, 50, n)
+    e1 = {"M%d" % (m + 1): eps1w[m][eidx] for m in range(3)}
+    e2 = {"M%d" % (m + 1): eps2w[m][eidx] for m in range(3)}
+    ch = {k: chi[i][eidx] for i, k in enumerate(cases.CHI2_KEYS)}
+    for sn, zq, mr in ((False, True, True), (True, False, True), (True, True, False), (False, False, False)):
+        want = orc.yield_points(energy[eidx], e1, e2, ch, theta, phi, thick, mr, consts, sn, zq)
+        out = run_points(harness, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, mr, sn, zq)
+        for i, pol in enumerate(cases.POLS):
+            ok, msg = cases.parity_ok(out[i], want[pol], rtol=1e-10)
+            assert ok, (sn, zq, mr, pol, msg)
