@@ -118,14 +118,16 @@ def test_rotate_matches_reference(shg):
 
 
 def test_rotate_without_quirk_is_a_true_rotation(shg):
-    """rotating by g then by -g (about the internal angle) must return the input only for the
-    true rotation; documents the xxy/yyy sign of the reference (shg.py:92)."""
+    """Without the xxy/yyy sign of the reference (shg.py:92) the map is a true rotation about z by
+    `rotang`: rotating by +a and then by -a returns the input; with the quirk it does not."""
     rng = np.random.default_rng(5)
     chi = {k: rng.normal(size=3) + 1j * rng.normal(size=3) for k in cases.CHI2_KEYS}
-    fwd = shg.rotate(chi, np.radians(90 - 37.0), xxy_quirk=False)       # internal angle +37
-    back = shg.rotate(fwd, np.radians(90 + 37.0), xxy_quirk=False)      # internal angle -37
+    a = np.radians(37.0)
+    back = shg.rotate(shg.rotate(chi, a, xxy_quirk=False), -a, xxy_quirk=False)
     for k in cases.CHI2_KEYS:
         np.testing.assert_allclose(back[k], chi[k], rtol=0, atol=1e-14)
+    quirky = shg.rotate(shg.rotate(chi, a), -a)
+    assert max(np.max(np.abs(quirky[k] - chi[k])) for k in cases.CHI2_KEYS) > 1e-3
 
 
 # ---- K2 at kernel level -------------------------------------------------------------------------
