@@ -327,6 +327,30 @@ def run_ours(args):
     d2h = int(host_out.nbytes)
     e2e_pts = n_e2e * 4 * N_PHI * N_ENERGY
 
+    # ---- the one collective of the path: gather of the slabs onto rank 0 (reported separately) --------
+    gather = None
+    if world > 1 and not args.no_gather:
+        full = torch.empty((N_THETA, 1, 4, N_PHI, N_ENERGY), dtype=torch.float64, device=dev) if rank == 0 else None
+        g_ms = []
+        for it in range(3):
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record()
+            grid.gather_slabs(out, N_THETA, 1, (rank, world, "theta"), dst=0, out=full)
+            g1.record()
+            barrier()
+            if it:
+                g_ms.append(g0.elapsed_time(g1))
+        gt = torch.tensor([min(g_ms)], dtype=torch.float64, device=dev)
+        dist.all_reduce(gt, op=dist.ReduceOp.MAX)
+        recv_bytes = 8.0 * (total_pts - my_pts) if rank == 0 else 0.0
+        if rank == 0:
+            ok = bool(torch.equal(full[t_lo:t_hi], out))
+            gather = {"ms": float(gt.item()), "bytes_into_rank0": recv_bytes, "gbs": recv_bytes / (gt.item() * 1e-3) / 1e9,
+                      "how": "grouped ncclSend/ncclRecv of the true shard sizes into the cube on rank 0 (NVLink)",
+                      "own_slab_intact": ok}
+        del full
+
     # ---- reduce over ranks (max time; sums of points) ----------------------------------------------
     stats = torch.tensor([total_ms, e2e_s, float(np.mean(step_ms))], dtype=torch.float64, device=dev)
     counts = torch.tensor([float(my_pts), float(e2e_pts), float(launches)], dtype=torch.float64, device=dev)
@@ -366,6 +390,7 @@ def run_ours(args):
                          "fp64_peak_tflops_measured": peaks.get("fp64_tflops"),
                          "alg_fp64_tflops": flops / (k2_ms * 1e-3) / 1e12},
             "cpu_baseline": cpu,
+            "gather": gather,
             "ms_per_step_device_max": mean_step_ms,
         }
         print(json.dumps(line), flush=True)
@@ -382,6 +407,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="skip timing the NCCL gather of the slabs (N > 1)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

@@ -68,8 +68,11 @@ typedef struct {
     int32_t sinc_normalized; /* 1: np.sinc = sin(pi x)/(pi x) as shipped (shg.py:183); 0: sin(x)/x */
     int32_t zzz_phi_quirk;   /* 1: chi_zzz term of r_pP times sin(phi)^3 as shipped (shg.py:269);
                                 0: sin(theta)^3 (Eq. 50 of PRB 94, 115314)          */
-    int32_t reserved;
+    int32_t flags;           /* SSHG_FLAG_* bits, 0 for the yield entry points              */
 } sshg_physics;
+
+/* sshg_physics.flags */
+#define SSHG_FLAG_RADIANS 1  /* theta / phi of a point list are in radians (the reference's helpers) */
 
 /* A rectangular sweep: energy x theta x phi x thickness (x 4 polarisations).
  * Replaces the reference's NumPy broadcast over rad_pp/ps/sp/ss + prefactor
@@ -145,6 +148,21 @@ SSHG_API int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double* 
  * contraction + |Gamma r|^2 (shg.py:137-378, 428-436).  */
 SSHG_API int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where);
 SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
+
+/* ---- the reference's public helper functions, element-wise over n values ------------------
+ * kind: wvec (shg.py:137-141, epsj unused), frefs / frefp (144-156), ftrans / ftranp (159-171);
+ * epsi, epsj, out: complex [n][2]; theta in RADIANS as in the reference. */
+enum { SSHG_F_WVEC = 0, SSHG_F_FREFS = 1, SSHG_F_FREFP = 2, SSHG_F_FTRANS = 3, SSHG_F_FTRANP = 4 };
+SSHG_API int sshg_fresnel(sshg_ctx* ctx, int kind, const double* epsi, const double* epsj, const double* theta_rad,
+                 double* out, int64_t n, int where);
+/* mrc2w (harmonic = 2, shg.py:174-185) and mrc1w (harmonic = 1, shg.py:188-198): energy, theta_rad,
+ * thick_nm real [n]; eps_l, fres1, fres2, out complex [n][2]. */
+SSHG_API int sshg_multiref(sshg_ctx* ctx, int harmonic, const double* energy_eV, const double* eps_l,
+                  const double* fres1, const double* fres2, const double* theta_rad, const double* thick_nm,
+                  const sshg_physics* phys, double* out, int64_t n, int where);
+/* rad_pp / rad_ps / rad_sp / rad_ss (shg.py:201-378): the complex amplitudes Gamma * r of a point
+ * list, out complex [4][n][2]; honours SSHG_FLAG_RADIANS. */
+SSHG_API int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
 
 /* ---- measurement helpers used by bench.py for the roofline denominators ---------------- */
 /* streaming 128-bit stores over `bytes` of device memory; returns achieved GB/s (best of iters) */

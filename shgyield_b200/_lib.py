@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(HERE, "libsshg.so")
 SSHG_OK, SSHG_EINVAL, SSHG_ECUDA, SSHG_ENOMEM = 0, -1, -2, -3
 HOST, IN_DEVICE, OUT_DEVICE, DEVICE = 0, 1, 2, 3
 ABI_VERSION = 1
+FLAG_RADIANS = 1
 
 c_double_p = C.POINTER(C.c_double)
 c_int64_p = C.POINTER(C.c_int64)
@@ -27,7 +28,7 @@ c_int64_p = C.POINTER(C.c_int64)
 class Physics(C.Structure):
     _fields_ = [("h_eVs", C.c_double), ("hbar_eVs", C.c_double), ("eps0", C.c_double), ("c", C.c_double),
                 ("mref", C.c_int32), ("sinc_normalized", C.c_int32), ("zzz_phi_quirk", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("flags", C.c_int32)]
 
 
 class Problem(C.Structure):
@@ -66,6 +67,10 @@ SYMBOLS = {
                                        C.c_int64, C.c_void_p, C.c_int]),
     "sshg_yield": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_void_p, C.c_int]),
     "sshg_yield_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
+    "sshg_fresnel": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
+    "sshg_multiref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_void_p, C.POINTER(Physics), C.c_void_p, C.c_int64, C.c_int]),
+    "sshg_amplitudes_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
     "sshg_peak_store": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "sshg_peak_dfma": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
 }

@@ -72,6 +72,8 @@ struct Physics {
     int mref;
     int sinc_normalized;
     int zzz_phi_quirk;
+    int raw;              // 1: leave sqrt(prefactor) / n_l out of the Gamma's (amplitudes of rad_pp .. rad_ss)
+    int radians;          // 1: theta / phi of point lists are in radians (the reference's helper functions)
 };
 
 // Everything of one (energy, theta, thickness) column that the four polarisations share.
@@ -141,7 +143,7 @@ SSHG_HD Column column_setup(const cplx e1[3], const cplx e2[3], double energy,
 
     const cplx inl = crecip(csqrt_(e1[1]));              // 1 / n_l(w)
     const cplx iNl = crecip(csqrt_(e2[1]));              // 1 / N_l(2w)
-    const cplx q = (ph.pref * energy / fabs(cos_t)) * inl;   // sqrt(prefactor) / n_l
+    const cplx q = ph.raw ? mk(1.0, 0.0) : (ph.pref * energy / fabs(cos_t)) * inl;   // sqrt(prefactor) / n_l
     const cplx out_p = f2.t_p * iNl;                     // T_p / N_l
     const cplx out_s = f2.t_s * (1.0 + Rs);              // T_s (1 + R^M_s)
     const cplx in_p = csq(f1.t_p * inl);                 // (t_p / n_l)^2
@@ -242,15 +244,54 @@ SSHG_HD void coeffs_ss(const Column& c, ChiFn chi, cplx k[4]) {
 }
 
 // basis row for one azimuth: b[0..5] = {c^2, s c, c^3, s c^2, s^2 c, s^3}
-SSHG_HD void phi_basis(double phi_deg, double b[6]) {
+SSHG_HD void phi_basis_rad(double phi, double b[6]) {
     double s, c;
-    sincos(phi_deg * (3.141592653589793 / 180.0), &s, &c);
+    sincos(phi, &s, &c);
     b[0] = c * c;
     b[1] = s * c;
     b[2] = b[0] * c;
     b[3] = b[1] * c;
     b[4] = b[1] * s;
     b[5] = s * s * s;
+}
+
+SSHG_HD void phi_basis(double phi_deg, double b[6]) { phi_basis_rad(phi_deg * (3.141592653589793 / 180.0), b); }
+
+// ---- the reference's small helpers, one formula each (shg.py:137-198) -----------------------
+SSHG_HD cplx wvec_(cplx eps, double sin_t) { return csqrt_(mk(eps.re - sin_t * sin_t, eps.im)); }
+SSHG_HD cplx frefs_(cplx ei, cplx ej, double st) {
+    cplx wi = wvec_(ei, st), wj = wvec_(ej, st);
+    return (wi - wj) / (wi + wj);
+}
+SSHG_HD cplx frefp_(cplx ei, cplx ej, double st) {
+    cplx wi = wvec_(ei, st), wj = wvec_(ej, st);
+    return (wi * ej - wj * ei) / (wi * ej + wj * ei);
+}
+SSHG_HD cplx ftrans_(cplx ei, cplx ej, double st) {
+    cplx wi = wvec_(ei, st), wj = wvec_(ej, st);
+    return (2.0 * wi) / (wi + wj);
+}
+SSHG_HD cplx ftranp_(cplx ei, cplx ej, double st) {
+    cplx wi = wvec_(ei, st), wj = wvec_(ej, st);
+    return ((2.0 * wi) * csqrt_(ei * ej)) / (wi * ej + wj * ei);
+}
+// mrc2w (harmonic = 2, shg.py:174-185) / mrc1w (harmonic = 1, shg.py:188-198)
+SSHG_HD cplx multiref_(int harmonic, double energy, cplx eps_l, cplx f1, cplx f2, double st, double thick,
+                       const Physics& ph) {
+    if (!ph.mref) return f1;
+    const double PI = 3.141592653589793;
+    const double x = energy * thick * ph.kd;
+    const cplx w = wvec_(eps_l, st);
+    if (harmonic == 1) {
+        cplx ev = cexp_i((4.0 * PI * x) * w);
+        return (f1 * ev) / (1.0 + f2 * f1 * ev);
+    }
+    cplx hd = (4.0 * PI * x) * w;
+    cplx eh = cexp_i(hd), ed = cexp_i(2.0 * hd);
+    cplx arg = hd;
+    if (arg.re == 0.0 && arg.im == 0.0) arg = mk(1.0e-20, 0.0);
+    if (ph.sinc_normalized) arg = PI * arg;
+    return ((f1 * eh) / (1.0 + f2 * f1 * ed)) * (csin_(arg) / arg);
 }
 
 }  // namespace sshg

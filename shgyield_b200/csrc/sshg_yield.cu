@@ -279,12 +279,16 @@ struct PointArgs {
     Physics ph;
 };
 
+// AMP = false: yields [4][n];  AMP = true: complex amplitudes Gamma * r, [4][n] double2
+// (rad_pp / rad_ps / rad_sp / rad_ss of the reference, shg.py:201-378).
+template <bool AMP>
 __global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const long long e = a.eidx[i], nE = a.nE;
+    const double to_rad = a.ph.radians ? 1.0 : (3.141592653589793 / 180.0);
     double st, ct;
-    sincos(a.theta_deg[i] * (3.141592653589793 / 180.0), &st, &ct);
+    sincos(a.theta_deg[i] * to_rad, &st, &ct);
     cplx e1[3], e2[3];
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
@@ -293,8 +297,12 @@ __global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
     }
     const Column c = column_setup(e1, e2, a.energy[e], st, ct, a.thick_nm[i], a.ph);
     double b[6];
-    phi_basis(a.phi_deg[i], b);
+    phi_basis_rad(a.phi_deg[i] * to_rad, b);
     auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+    auto emit = [&](int pol, double re, double im) {
+        if (AMP) reinterpret_cast<double2*>(a.out)[pol * a.n + i] = make_double2(re, im);
+        else a.out[pol * a.n + i] = fma(re, re, im * im);
+    };
 #pragma unroll 1
     for (int pol = 0; pol < 3; ++pol) {
         cplx k[7];
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
             re = fma(k[j + 1].re, b[j], re);
             im = fma(k[j + 1].im, b[j], im);
         }
-        a.out[pol * a.n + i] = fma(re, re, im * im);
+        emit(pol, re, im);
     }
     {
         cplx k[4];
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
             re = fma(k[j].re, b[j + 2], re);
             im = fma(k[j].im, b[j + 2], im);
         }
-        a.out[3 * a.n + i] = fma(re, re, im * im);
+        emit(3, re, im);
     }
 }
 
@@ -329,6 +337,8 @@ Physics make_physics(const sshg_physics& p) {
     ph.mref = p.mref;
     ph.sinc_normalized = p.sinc_normalized;
     ph.zzz_phi_quirk = p.zzz_phi_quirk;
+    ph.raw = 0;
+    ph.radians = (p.flags & SSHG_FLAG_RADIANS) ? 1 : 0;
     return ph;
 }
 
@@ -445,7 +455,7 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     return SSHG_OK;
 }
 
-extern "C" int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where) {
+static int points_impl(sshg_ctx* ctx, const sshg_points* p, double* out, int where, bool amp) {
     SSHG_REQUIRE(ctx && p && out, "sshg_yield_points: null argument");
     SSHG_REQUIRE(p->n > 0 && p->nE > 0, "sshg_yield_points: n and nE must be positive");
     SSHG_REQUIRE(p->energy_eV && p->eidx && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
@@ -480,17 +490,28 @@ extern "C" int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* ou
     a.n = p->n;
     a.nE = p->nE;
     a.ph = make_physics(p->phys);
+    a.ph.raw = amp ? 1 : 0;
+    const size_t out_bytes = 4 * n * (amp ? 16 : 8);
     void* dout = out;
     if (!out_dev) {
-        if (int rc = sshg_scratch(ctx, 8, 4 * n * 8, &dout)) return rc;
+        if (int rc = sshg_scratch(ctx, 8, out_bytes, &dout)) return rc;
     }
     a.out = (double*)dout;
-    yield_points_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+    if (amp) yield_points_kernel<true><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
+    else yield_points_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(a);
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
     if (!out_dev) {
-        SSHG_CUDA(cudaMemcpyAsync(out, dout, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     return SSHG_OK;
+}
+
+extern "C" int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where) {
+    return points_impl(ctx, p, out, where, false);
+}
+
+extern "C" int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where) {
+    return points_impl(ctx, p, out, where, true);
 }

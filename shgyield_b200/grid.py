@@ -121,7 +121,7 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
     `device` (default), else NumPy arrays.
 
     shard=(rank, world[, 'theta'|'thick']) computes only that rank's slab; with gather=True and an
-    initialised torch.distributed process group the slabs are gathered on every rank (all_gather).
+    initialised torch.distributed process group the slabs are gathered onto rank 0 (`gather_slabs`).
     sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles).
     """
     energy = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
@@ -175,10 +175,14 @@ def broaden_energy_device(cube, sigma):
     return out
 
 
-def gather_slabs(slab, nT: int, nD: int, shard):
-    """all_gather of the per-rank slabs into the full cube [T, D, 4, P, E] (every rank gets it).
-    Works on CUDA tensors (NCCL) and CPU tensors (gloo; used by the CPU tests of the host logic).
-    Theta shards are contiguous blocks of the cube; uneven shards are padded to the largest."""
+def gather_slabs(slab, nT: int, nD: int, shard, dst: int = 0, out=None, all_ranks: bool = False):
+    """The one collective of the path: gathers the per-rank slabs into the full cube [T, D, 4, P, E].
+
+    Default: a gather onto rank `dst` with the true (uneven) shard sizes -- grouped point-to-point
+    send / recv (ncclSend / ncclRecv under NCCL, over NVLink), received straight into the slices of
+    the full cube, no padding and no staging copy for theta shards (they are contiguous blocks).
+    Returns the cube on `dst` and None elsewhere.  all_ranks=True gives every rank the cube
+    (one broadcast per shard).  Works on CUDA tensors (NCCL) and CPU tensors (gloo, CPU tests)."""
     import torch
     import torch.distributed as dist
     rank, world = int(shard[0]), int(shard[1])
@@ -186,19 +190,48 @@ def gather_slabs(slab, nT: int, nD: int, shard):
     n_axis = nT if axis == "theta" else nD
     dim = 0 if axis == "theta" else 1
     bounds = [shard_bounds(n_axis, world, r) for r in range(world)]
-    widest = max(hi - lo for lo, hi in bounds)
-    pad_shape = list(slab.shape)
-    pad_shape[dim] = widest
-    if slab.shape[dim] == widest:
-        mine = slab.contiguous()
-    else:
-        mine = torch.zeros(pad_shape, dtype=slab.dtype, device=slab.device)
-        mine.narrow(dim, 0, slab.shape[dim]).copy_(slab)
-    parts = [torch.empty(pad_shape, dtype=slab.dtype, device=slab.device) for _ in range(world)]
-    dist.all_gather(parts, mine)
     full_shape = list(slab.shape)
     full_shape[dim] = n_axis
-    full = torch.empty(full_shape, dtype=slab.dtype, device=slab.device)
-    for (lo, hi), part in zip(bounds, parts):
-        full.narrow(dim, lo, hi - lo).copy_(part.narrow(dim, 0, hi - lo))
+    if slab.shape[dim] != bounds[rank][1] - bounds[rank][0]:
+        raise ValueError("slab extent %d does not match shard %s" % (slab.shape[dim], bounds[rank]))
+    want_full = all_ranks or rank == dst
+    full = None
+    if want_full:
+        if out is not None:
+            if list(out.shape) != full_shape or out.dtype != slab.dtype or not out.is_contiguous():
+                raise ValueError("out must be a contiguous tensor of shape %s" % (full_shape,))
+            full = out
+        else:
+            full = torch.empty(full_shape, dtype=slab.dtype, device=slab.device)
+        lo, hi = bounds[rank]
+        mine = full.narrow(dim, lo, hi - lo)
+        if mine.data_ptr() != slab.data_ptr():
+            mine.copy_(slab)
+    if all_ranks:
+        for r, (lo, hi) in enumerate(bounds):
+            if hi == lo:
+                continue
+            view = full.narrow(dim, lo, hi - lo)
+            buf = view if view.is_contiguous() else view.contiguous()
+            dist.broadcast(buf, src=r)
+            if buf.data_ptr() != view.data_ptr():
+                view.copy_(buf)
+        return full
+    ops, staged = [], []
+    if rank == dst:
+        for r, (lo, hi) in enumerate(bounds):
+            if r == dst or hi == lo:
+                continue
+            view = full.narrow(dim, lo, hi - lo)
+            buf = view if view.is_contiguous() else torch.empty(view.shape, dtype=slab.dtype, device=slab.device)
+            if buf is not view:
+                staged.append((view, buf))
+            ops.append(dist.P2POp(dist.irecv, buf, r))
+    elif slab.shape[dim] > 0:
+        ops.append(dist.P2POp(dist.isend, slab.contiguous(), dst))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    for view, buf in staged:
+        view.copy_(buf)
     return full

@@ -315,3 +315,132 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     for k, pol in enumerate(POLS):
         out[pol] = broad(res[k], sigma_out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's small public helpers (shg.py:137-198, 201-378), element-wise on the device.
+# shgyield() does not use them -- the fused kernel shares sub-expressions across them -- but every
+# function of the reference's module stays callable with the same argument meaning
+# (theta / phi in RADIANS here, exactly like the reference's helpers).
+# ---------------------------------------------------------------------------------------------
+def _elementwise(fn, *args):
+    """Broadcasts the arguments, flattens, calls fn(flat arrays, n) -> complex flat, restores the shape."""
+    shape = np.broadcast_shapes(*[np.shape(a) for a in args])
+    n = int(np.prod(shape, dtype=np.int64))
+    out = np.empty(n, dtype=np.complex128)
+    if n:
+        fn([np.ascontiguousarray(np.broadcast_to(a, shape)).ravel() for a in args], n, out)
+    res = out.reshape(shape)
+    return res if shape else res[()]
+
+
+def _fresnel(kind, epsi, epsj, theta):
+    ctx = _lib.context()
+
+    def run(flat, n, out):
+        ei, ej, th = (np.ascontiguousarray(flat[0], dtype=np.complex128),
+                      np.ascontiguousarray(flat[1], dtype=np.complex128),
+                      np.ascontiguousarray(flat[2], dtype=np.float64))
+        _lib.check(ctx.lib.sshg_fresnel(ctx.handle, kind, ei.ctypes.data, ej.ctypes.data, th.ctypes.data,
+                                        out.ctypes.data, n, _lib.HOST), ctx.lib)
+    return _elementwise(run, epsi, epsj, theta)
+
+
+def wvec(eps, theta):
+    """w = sqrt(eps - sin(theta)^2)  (reference shg.py:137-141)."""
+    return _fresnel(0, eps, eps, theta)
+
+
+def frefs(epsi, epsj, theta):
+    """s-polarised reflection Fresnel factor (reference shg.py:144-148)."""
+    return _fresnel(1, epsi, epsj, theta)
+
+
+def frefp(epsi, epsj, theta):
+    """p-polarised reflection Fresnel factor (reference shg.py:151-156)."""
+    return _fresnel(2, epsi, epsj, theta)
+
+
+def ftrans(epsi, epsj, theta):
+    """s-polarised transmission Fresnel factor (reference shg.py:159-163)."""
+    return _fresnel(3, epsi, epsj, theta)
+
+
+def ftranp(epsi, epsj, theta):
+    """p-polarised transmission Fresnel factor (reference shg.py:166-171)."""
+    return _fresnel(4, epsi, epsj, theta)
+
+
+def _multiref(harmonic, energy, eps0, fres1, fres2, theta, thick, mref):
+    ctx = _lib.context()
+    phys = _physics(None, mref)
+
+    def run(flat, n, out):
+        en, el, f1, f2, th, dd = flat
+        arrs = [np.ascontiguousarray(en, dtype=np.float64), np.ascontiguousarray(el, dtype=np.complex128),
+                np.ascontiguousarray(f1, dtype=np.complex128), np.ascontiguousarray(f2, dtype=np.complex128),
+                np.ascontiguousarray(th, dtype=np.float64), np.ascontiguousarray(dd, dtype=np.float64)]
+        _lib.check(ctx.lib.sshg_multiref(ctx.handle, harmonic, arrs[0].ctypes.data, arrs[1].ctypes.data,
+                                         arrs[2].ctypes.data, arrs[3].ctypes.data, arrs[4].ctypes.data,
+                                         arrs[5].ctypes.data, C.byref(phys), out.ctypes.data, n, _lib.HOST), ctx.lib)
+    return _elementwise(run, energy, eps0, fres1, fres2, theta, thick)
+
+
+def mrc2w(energy, eps0, fres1, fres2, theta, thick, mref):
+    """2w multiple-reflection coefficient, Eq. (18) of PRB 94, 115314 (reference shg.py:174-185)."""
+    return _multiref(2, energy, eps0, fres1, fres2, theta, thick, mref)
+
+
+def mrc1w(energy, eps0, fres1, fres2, theta, thick, mref):
+    """1w multiple-reflection coefficient, Eq. (21) of PRB 94, 115314 (reference shg.py:188-198)."""
+    return _multiref(1, energy, eps0, fres1, fres2, theta, thick, mref)
+
+
+def _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
+    """Gamma * r for the four polarisations on the NumPy broadcast of all arguments: complex [4, ...]."""
+    ctx = _lib.context()
+    ops = [energy, theta, phi, thick] + [eps1w[k] for k in ("M1", "M2", "M3")] + \
+          [eps2w[k] for k in ("M1", "M2", "M3")] + [chi2[k] for k in CHI2_KEYS]
+    shape = np.broadcast_shapes(*[np.shape(o) for o in ops])
+    n = int(np.prod(shape, dtype=np.int64))
+    flat = lambda a, dt: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dt), shape)).ravel()
+    out = np.empty((4, n), dtype=np.complex128)
+    if n:
+        a = dict(energy=flat(energy, np.float64), theta=flat(theta, np.float64), phi=flat(phi, np.float64),
+                 thick=flat(thick, np.float64), eidx=np.arange(n, dtype=np.int64),
+                 eps1w=np.stack([flat(eps1w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                 eps2w=np.stack([flat(eps2w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                 chi2=np.stack([flat(chi2[k], np.complex128) for k in CHI2_KEYS]))
+        phys = _physics(None, mref)
+        phys.flags = _lib.FLAG_RADIANS
+        p = _lib.Points(n=n, nE=n, energy_eV=a["energy"].ctypes.data, eidx=a["eidx"].ctypes.data,
+                        theta_deg=a["theta"].ctypes.data, phi_deg=a["phi"].ctypes.data,
+                        thick_nm=a["thick"].ctypes.data, eps1w=a["eps1w"].ctypes.data, eps2w=a["eps2w"].ctypes.data,
+                        chi2=a["chi2"].ctypes.data, phys=phys)
+        _lib.check(ctx.lib.sshg_amplitudes_points(ctx.handle, C.byref(p), out.ctypes.data, _lib.HOST), ctx.lib)
+    res = out.reshape((4,) + shape)
+    return res
+
+
+def rad_pp(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
+    """Gamma_pP r_pP, Eq. (50) of PRB 94, 115314 as shipped (reference shg.py:201-270)."""
+    r = _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref)[0]
+    return r if r.shape else r[()]
+
+
+def rad_ps(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
+    """Gamma_pS r_pS, Eq. (55) (reference shg.py:273-314)."""
+    r = _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref)[1]
+    return r if r.shape else r[()]
+
+
+def rad_sp(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
+    """Gamma_sP r_sP, Eq. (60) (reference shg.py:317-352)."""
+    r = _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref)[2]
+    return r if r.shape else r[()]
+
+
+def rad_ss(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
+    """Gamma_sS r_sS, Eq. (65) (reference shg.py:355-378)."""
+    r = _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref)[3]
+    return r if r.shape else r[()]

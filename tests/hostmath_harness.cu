@@ -14,6 +14,8 @@ extern "C" int hostmath_yield_points(const sshg_points* p, double* out) {
     ph.mref = p->phys.mref;
     ph.sinc_normalized = p->phys.sinc_normalized;
     ph.zzz_phi_quirk = p->phys.zzz_phi_quirk;
+    ph.raw = 0;
+    ph.radians = 0;
     const long long nE = p->nE, n = p->n;
     for (long long i = 0; i < n; ++i) {
         const long long e = p->eidx[i];

@@ -52,8 +52,13 @@ def _gather_worker(rank, world, port, axis, q):
         else:
             lo, hi = grid.shard_bounds(nD, world, rank)
             slab = full[:, lo:hi].clone()
-        got = grid.gather_slabs(slab, nT, nD, (rank, world, axis))
-        q.put((rank, bool(torch.equal(got, full))))
+        got = grid.gather_slabs(slab, nT, nD, (rank, world, axis))              # gather onto rank 0
+        ok = bool(torch.equal(got, full)) if rank == 0 else got is None
+        everywhere = grid.gather_slabs(slab, nT, nD, (rank, world, axis), all_ranks=True)
+        pre = torch.zeros_like(full)
+        into = grid.gather_slabs(slab, nT, nD, (rank, world, axis), dst=1, out=pre if rank == 1 else None)
+        ok = ok and bool(torch.equal(everywhere, full)) and (bool(torch.equal(into, full)) if rank == 1 else into is None)
+        q.put((rank, ok))
     finally:
         dist.destroy_process_group()
 
