@@ -22,9 +22,7 @@ Python and /root/reference does not exist on the GPU box) on all host cores.
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -162,55 +160,71 @@ def run_reference(args):
 # GPU leg
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and clock-event reasons of one GPU DURING the timed region: an NVML
+    polling thread (2 ms period; the timed region of this bench is ~0.1 s, too short for
+    `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
 
-    def __init__(self, index):
-        self.index = index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+    def __init__(self, torch_index):
+        self.samples = []
+        self.thread = None
+        self.stop_flag = False
+        self.h = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_index).uuid)
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+                idx = int(vis.split(",")[torch_index]) if vis and vis.split(",")[torch_index].isdigit() else torch_index
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        except Exception as e:                      # NVML missing: the record says so
+            self.err = repr(e)
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((clk, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+        if self.h is None:
+            return
+        import threading
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        self.f.seek(0)
-        sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.f.read().splitlines():
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1]))
-                smax.append(float(c[2]))
-                power.append(float(c[3]))
-            except ValueError:
-                continue
-            for name, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        self.f.close()
-        os.unlink(self.f.name)
-        if not sm:
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": float(max(power))}
+        clk = [s[0] for s in self.samples]
+        pw = [s[1] for s in self.samples]
+        bits = 0
+        for s in self.samples:
+            bits |= s[2]
+        smax = self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)
+        busy = [c for c, p in zip(clk, pw) if p >= 0.5 * max(pw)] or clk
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(smax),
+                "reasons": sorted(n for b, n in self.REASONS.items() if bits & b),
+                "samples": len(clk), "sm_mhz_min": float(min(clk)), "power_w_max": float(max(pw))}
 
 
 def measured_peaks():

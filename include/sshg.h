@@ -144,6 +144,11 @@ SSHG_API int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, i
 SSHG_API int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
                          const double* xq, int64_t nq, double* out, int where);
 
+/* broadC -> splineC -> evaluation in one call (shg.py:388-389, 423-424): rows are broadened with
+ * sigma (samples; <= 1e-15: none) and resampled at xq without leaving the device. */
+SSHG_API int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
+                          double sigma, const double* xq, int64_t nq, double* out, int where);
+
 /* ---- the fused yield kernel: Fresnel factors + three-layer multiple reflection + chi2
  * contraction + |Gamma r|^2 (shg.py:137-378, 428-436).  */
 SSHG_API int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where);

@@ -1,28 +1,112 @@
-// K1: Gaussian broadening of real signals (sm_100a, FP64) -- a shared-memory tiled 1-D FIR.
+// K1: Gaussian broadening of real signals (sm_100a, FP64) -- shared-memory tiled 1-D FIR.
 //
 // Replaces broad / broadC of the reference (shgyield/shg.py:26-35), i.e. one axis of
 // scipy.ndimage.gaussian_filter: taps w_k = exp(-k^2 / (2 sigma^2)) / sum, radius
 // int(4 sigma + 0.5), boundary 'reflect' (d c b a | a b c d | d c b a, repeated when the radius
-// exceeds the signal), sigma <= 1e-15 -> copy.  The accumulation order is SciPy's symmetric
-// correlate1d loop: centre tap first, then tap pairs from the farthest inwards.
+// exceeds the signal), sigma <= 1e-15 -> copy.
+//
+// Contiguous signals (the spectra rows and the energy axis of a yield cube) use
+// `gauss_stream_kernel`: a CTA stages a tile + halo in shared memory, each thread then produces
+// R = 9 consecutive outputs from a register window -- per staged sample one conflict-free LDS,
+// one broadcast LDS for the tap entering the window and 9 DFMAs, so the loop is bound by the FP64
+// pipe, not by shared memory.  Results return through shared memory for coalesced stores.
+// Strided signals (blurring a non-contiguous axis of an N-D array, which the reference does when a
+// broadcast call has sigma_out > 0) use `gauss_tiled_kernel` (SciPy's accumulation order: centre
+// tap, then pairs from the farthest inwards); radii whose halo exceeds shared memory use
+// `gauss_direct_kernel`.
 //
 // HBM traffic: 8 B read + 8 B written per sample (halo re-reads hit L2).
 #include "sshg_internal.h"
 
 #include <math.h>
 #include <stdlib.h>
+#include <type_traits>
 
 namespace {
-
-constexpr int GT = 256;          // threads per CTA
-constexpr int GPT = 4;           // outputs per thread
-constexpr int GTILE = GT * GPT;  // outputs per CTA
 
 __device__ __forceinline__ long long reflect(long long i, long long n) {
     long long m = i % (2 * n);
     if (m < 0) m += 2 * n;
     return m >= n ? 2 * n - 1 - m : m;
 }
+
+// ---- contiguous rows: register-window FIR ----------------------------------------------------
+constexpr int ST = 128;             // threads per CTA
+constexpr int SR = 9;               // consecutive outputs per thread (odd: stride-9 LDS.64 is conflict-free)
+constexpr int STILE = ST * SR;      // outputs per CTA
+
+// smem: xs[STILE + 2r + SR] samples (zero padded), then wext[2r + 1 + 3 SR] taps:
+// wext[k] = w_full[k - (SR-1)] for 0 <= k - (SR-1) <= 2r, else 0.
+__global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                          const double* __restrict__ taps, long long n,
+                                                          long long row_stride, int r, int tiles_per_row) {
+    extern __shared__ double sm[];
+    const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding of the last steps)
+    const int ntap = 2 * r + 1 + 3 * SR;
+    double* xs = sm;
+    double* wext = sm + span;
+    const long long row = blockIdx.x / tiles_per_row;
+    const long long i0 = (long long)(blockIdx.x % tiles_per_row) * STILE;
+    const double* src = in + row * row_stride;
+    double* dst = out + row * row_stride;
+    for (int k = threadIdx.x; k < span; k += ST) {
+        const long long i = i0 - r + k;
+        double v = 0.0;
+        if (k < STILE + 2 * r) {
+            if (i >= 0 && i < n) v = src[i];
+            else if (i < n + r) v = src[reflect(i, n)];
+        }
+        xs[k] = v;
+    }
+    for (int k = threadIdx.x; k < ntap; k += ST) {
+        const int j = k - (SR - 1);                // index into the full symmetric kernel
+        wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
+    }
+    __syncthreads();
+
+    const double* xw = xs + threadIdx.x * SR;      // window of this thread: xw[t], t = 0 .. 2r + SR - 1
+    double acc[SR], wr[SR];
+#pragma unroll
+    for (int q = 0; q < SR; ++q) {
+        acc[q] = 0.0;
+        wr[q] = wext[q];                           // wr[k % SR] = wext[k] for the current window [t, t + SR - 1]
+    }
+    // Output q of this thread takes tap j = t - q of sample t; only 0 <= j <= 2r exist.  The first
+    // block needs the lower bound (static), the last blocks the upper one (r is a run-time value);
+    // the blocks in between are unconditional.  Skipping (rather than multiplying by a zero tap)
+    // keeps an Inf/NaN sample from reaching outputs beyond the true radius.
+    const int steps = 2 * r + SR;                  // t = 0 .. steps - 1
+    auto block = [&](int t0, auto first, auto tail) {
+#pragma unroll
+        for (int u = 0; u < SR; ++u) {
+            const double v = xw[t0 + u];
+#pragma unroll
+            for (int q = 0; q < SR; ++q) {
+                if (decltype(first)::value && q > u) continue;
+                if (decltype(tail)::value && t0 + u - q > 2 * r) continue;
+                acc[q] = fma(wr[(u + SR - 1 - q) % SR], v, acc[q]);
+            }
+            wr[u] = wext[t0 + u + SR];             // tap entering the window (zero beyond the kernel)
+        }
+    };
+    block(0, std::true_type{}, std::true_type{});
+    int t0 = SR;
+    for (; t0 + SR - 1 <= 2 * r; t0 += SR) block(t0, std::false_type{}, std::false_type{});
+    for (; t0 < steps; t0 += SR) block(t0, std::false_type{}, std::true_type{});
+    __syncthreads();                               // every window read is done: reuse xs for the results
+#pragma unroll
+    for (int q = 0; q < SR; ++q) xs[threadIdx.x * SR + q] = acc[q];
+    __syncthreads();
+    for (int k = threadIdx.x; k < STILE; k += ST) {
+        const long long i = i0 + k;
+        if (i < n) dst[i] = xs[k];
+    }
+}
+
+// ---- strided rows: SciPy-order tiled kernel -------------------------------------------------------
+constexpr int GT = 256;          // threads per CTA
+constexpr int GPT = 4;           // outputs per thread
+constexpr int GTILE = GT * GPT;  // outputs per CTA
 
 // smem: [GTILE + 2r] samples, then [r + 1] taps (w[0] = centre)
 __global__ void __launch_bounds__(GT) gauss_tiled_kernel(const double* __restrict__ in, double* __restrict__ out,
@@ -86,40 +170,26 @@ __global__ void copy_strided_kernel(const double* __restrict__ in, double* __res
     out[off] = in[off];
 }
 
+constexpr size_t SMEM_CAP = 200 * 1024;
+
 }  // namespace
 
-extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_t rows, int64_t n,
-                            int64_t row_stride, int64_t elem_stride, double sigma, int where) {
-    SSHG_REQUIRE(ctx && in && out, "sshg_gauss1d: null argument");
-    SSHG_REQUIRE(in != out, "sshg_gauss1d: in-place filtering is not supported");
-    SSHG_REQUIRE(rows > 0 && n > 0, "sshg_gauss1d: rows and n must be positive");
-    SSHG_REQUIRE(elem_stride >= 1 && row_stride >= 1, "sshg_gauss1d: strides must be positive");
-    SSHG_REQUIRE(sigma >= 0.0 && isfinite(sigma), "sshg_gauss1d: sigma must be finite and >= 0 (got %g)", sigma);
-    SSHG_CUDA(cudaSetDevice(ctx->device));
-    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
-
-    // extent of the (possibly strided) block of memory the rows live in
-    int64_t extent = 0;
-    {
-        // rows may interleave (row_stride < n * elem_stride when filtering a non-last axis)
-        const int64_t a = (rows - 1) * row_stride + (n - 1) * elem_stride + 1;
-        extent = a;
-    }
-    const size_t bytes = (size_t)extent * 8;
-    const void* din = in;
-    if (int rc = sshg_stage_in(ctx, 10, in, bytes, in_dev, &din)) return rc;
-    void* dout = out;
-    if (!out_dev) {
-        if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
-    }
-
+// Device-level filter: din / dout are device pointers; queued on ctx->stream.
+int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
+                      int64_t elem_stride, double sigma) {
     const long long total = (long long)rows * n;
     if (!(sigma > 1e-15)) {
-        copy_strided_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-            (const double*)din, (double*)dout, rows, n, row_stride, elem_stride);
-    } else {
-        const long long r = (long long)(4.0 * sigma + 0.5);
-        SSHG_REQUIRE(r < (1LL << 28), "sshg_gauss1d: sigma %g is too large", sigma);
+        copy_strided_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(din, dout, rows, n, row_stride,
+                                                                                   elem_stride);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SSHG_OK;
+    }
+    const long long r = (long long)(4.0 * sigma + 0.5);
+    SSHG_REQUIRE(r < (1LL << 28), "sshg_gauss1d: sigma %g is too large", sigma);
+    void* dw;
+    if (int rc = sshg_scratch(ctx, SCR_TAPS, (size_t)(r + 1) * 8, &dw)) return rc;
+    if (!(ctx->tap_sigma == sigma && ctx->tap_ptr == dw)) {
         double* w = (double*)malloc((size_t)(r + 1) * 8);
         if (!w) {
             sshg_set_error("out of host memory");
@@ -135,29 +205,55 @@ extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_
         w[0] = 1.0;
         sum += 1.0;
         for (long long k = 0; k <= r; ++k) w[k] /= sum;
-        void* dw;
-        int rc = sshg_scratch(ctx, 12, (size_t)(r + 1) * 8, &dw);
-        if (rc == SSHG_OK) {
-            cudaError_t e = cudaMemcpyAsync(dw, w, (size_t)(r + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);   // w is freed below
-            if (e != cudaSuccess) rc = sshg_cuda_fail(e, "tap upload", __FILE__, __LINE__);
-        }
+        // pageable source: the runtime copies it to a staging buffer before returning
+        cudaError_t e = cudaMemcpyAsync(dw, w, (size_t)(r + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
         free(w);
-        if (rc) return rc;
-        const size_t smem = (size_t)(GTILE + 2 * r + r + 1) * 8;
-        if (smem <= 200 * 1024) {
-            const int tiles = (int)((n + GTILE - 1) / GTILE);
-            SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
-            SSHG_CUDA(cudaFuncSetAttribute(gauss_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-            gauss_tiled_kernel<<<(unsigned)(rows * tiles), GT, smem, ctx->stream>>>(
-                (const double*)din, (double*)dout, (const double*)dw, rows, n, row_stride, elem_stride, (int)r, tiles);
-        } else {
-            gauss_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-                (const double*)din, (double*)dout, (const double*)dw, rows, n, row_stride, elem_stride, r);
-        }
+        if (e != cudaSuccess) return sshg_cuda_fail(e, "tap upload", __FILE__, __LINE__);
+        ctx->tap_sigma = sigma;
+        ctx->tap_ptr = dw;
+    }
+    const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
+    const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;
+    if (elem_stride == 1 && smem_stream <= SMEM_CAP) {
+        const int tiles = (int)((n + STILE - 1) / STILE);
+        SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
+        SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+        gauss_stream_kernel<<<(unsigned)(rows * tiles), ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n,
+                                                                                      row_stride, (int)r, tiles);
+    } else if (smem_tiled <= SMEM_CAP) {
+        const int tiles = (int)((n + GTILE - 1) / GTILE);
+        SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
+        SSHG_CUDA(cudaFuncSetAttribute(gauss_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+        gauss_tiled_kernel<<<(unsigned)(rows * tiles), GT, smem_tiled, ctx->stream>>>(din, dout, (const double*)dw, rows, n,
+                                                                                    row_stride, elem_stride, (int)r, tiles);
+    } else {
+        gauss_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(din, dout, (const double*)dw, rows, n,
+                                                                                   row_stride, elem_stride, r);
     }
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
+    return SSHG_OK;
+}
+
+extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_t rows, int64_t n,
+                            int64_t row_stride, int64_t elem_stride, double sigma, int where) {
+    SSHG_REQUIRE(ctx && in && out, "sshg_gauss1d: null argument");
+    SSHG_REQUIRE(in != out, "sshg_gauss1d: in-place filtering is not supported");
+    SSHG_REQUIRE(rows > 0 && n > 0, "sshg_gauss1d: rows and n must be positive");
+    SSHG_REQUIRE(elem_stride >= 1 && row_stride >= 1, "sshg_gauss1d: strides must be positive");
+    SSHG_REQUIRE(sigma >= 0.0 && isfinite(sigma), "sshg_gauss1d: sigma must be finite and >= 0 (got %g)", sigma);
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    // extent of the block of memory the rows live in (rows interleave when a non-last axis is filtered)
+    const int64_t extent = (rows - 1) * row_stride + (n - 1) * elem_stride + 1;
+    const size_t bytes = (size_t)extent * 8;
+    const void* din = in;
+    if (int rc = sshg_stage_in(ctx, 10, in, bytes, in_dev, &din)) return rc;
+    void* dout = out;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
+    }
+    if (int rc = sshg_gauss_device(ctx, (const double*)din, (double*)dout, rows, n, row_stride, elem_stride, sigma)) return rc;
     if (!out_dev) {
         SSHG_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         SSHG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -5,7 +5,9 @@
 #include <stddef.h>
 #include "../../include/sshg.h"
 
-#define SSHG_NSCRATCH 16
+#define SSHG_NSCRATCH 24
+#define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
+#define SCR_BROAD 16     // broadened rows handed from K1 to the spline kernels
 
 struct sshg_ctx {
     int device;
@@ -16,6 +18,8 @@ struct sshg_ctx {
     cudaEvent_t ev_copied[2];   // slab k copied to the host
     int num_sms;
     int64_t launches;
+    double tap_sigma;           // sigma whose taps are in scratch[SCR_TAPS] (tap_ptr guards reallocation)
+    void* tap_ptr;
     // growable device scratch buffers (inputs copied from the host, staged outputs)
     void* scratch[SSHG_NSCRATCH];
     size_t scratch_bytes[SSHG_NSCRATCH];
@@ -38,6 +42,12 @@ int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out);   // grows 
             return SSHG_EINVAL;                                                           \
         }                                                                                 \
     } while (0)
+
+// Device-level stages (all pointers on the device, queued on ctx->stream)
+int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
+                      int64_t elem_stride, double sigma);
+int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
+                       int64_t nq, double* dout, int* dflag);
 
 // Copies a host array to a scratch slot (or passes a device pointer through).
 int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device,

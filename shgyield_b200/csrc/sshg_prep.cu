@@ -132,6 +132,9 @@ __global__ void spline_eval_kernel(const double* __restrict__ x, const double* _
 
 }  // namespace
 
+static int spline_finish(sshg_ctx* ctx, void* dflag, void* dout, double* out, size_t out_bytes, int out_dev,
+                         const char* who);
+
 extern "C" int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, int64_t nE, double gamma_deg,
                            int xxy_quirk, int where) {
     SSHG_REQUIRE(ctx && chi_in && chi_out, "sshg_rotate: null argument");
@@ -189,29 +192,77 @@ extern "C" int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double
     if (int rc = sshg_stage_in(ctx, 10, x, (size_t)n * 8, in_dev, &dx)) return rc;
     if (int rc = sshg_stage_in(ctx, 11, y, (size_t)rows * n * 8, in_dev, &dy)) return rc;
     if (int rc = sshg_stage_in(ctx, 12, xq, (size_t)nq * 8, in_dev, &dq)) return rc;
-    void *dM, *dcp, *ddp, *dflag;
-    if (int rc = sshg_scratch(ctx, 13, (size_t)rows * n * 8, &dM)) return rc;
-    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 16, &dcp)) return rc;
-    ddp = (char*)dcp + (size_t)rows * n * 8;
+    void *dflag, *dout = out;
     if (int rc = sshg_scratch(ctx, 15, 16, &dflag)) return rc;
-    void* dout = out;
     if (!out_dev) {
         if (int rc = sshg_scratch(ctx, 9, (size_t)rows * nq * 8, &dout)) return rc;
     }
+    if (int rc = sshg_spline_device(ctx, (const double*)dx, (const double*)dy, rows, n, (const double*)dq, nq,
+                                    (double*)dout, (int*)dflag)) return rc;
+    return spline_finish(ctx, dflag, dout, out, (size_t)rows * nq * 8, out_dev, "sshg_spline_resample");
+}
+
+// Second derivatives + evaluation, all pointers on the device; *dflag is set when a query is out of range.
+int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
+                       int64_t nq, double* dout, int* dflag) {
+    void *dM, *dcp;
+    if (int rc = sshg_scratch(ctx, 13, (size_t)rows * n * 8, &dM)) return rc;
+    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 16, &dcp)) return rc;
+    void* ddp = (char*)dcp + (size_t)rows * n * 8;
     SSHG_CUDA(cudaMemsetAsync(dflag, 0, 4, ctx->stream));
-    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(
-        (const double*)dx, (const double*)dy, (double*)dM, (double*)dcp, (double*)ddp, rows, n);
+    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (double*)dM, (double*)dcp,
+                                                                            (double*)ddp, rows, n);
     SSHG_CUDA(cudaGetLastError());
     const long long total = (long long)rows * nq;
-    spline_eval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
-        (const double*)dx, (const double*)dy, (const double*)dM, rows, n, (const double*)dq, nq, (double*)dout,
-        (int*)dflag);
+    spline_eval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dx, dy, (const double*)dM, rows, n, dq,
+                                                                               nq, dout, dflag);
     SSHG_CUDA(cudaGetLastError());
     ctx->launches += 2;
+    return SSHG_OK;
+}
+
+// Reads the range flag (and the result when it goes to the host); one synchronisation.
+static int spline_finish(sshg_ctx* ctx, void* dflag, void* dout, double* out, size_t out_bytes, int out_dev,
+                         const char* who) {
     int flag = 0;
     SSHG_CUDA(cudaMemcpyAsync(&flag, dflag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (!out_dev) SSHG_CUDA(cudaMemcpyAsync(out, dout, (size_t)rows * nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (!out_dev) SSHG_CUDA(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
-    SSHG_REQUIRE(flag == 0, "sshg_spline_resample: a query lies outside the sampled range [x[0], x[n-1]] (ext=2)");
+    SSHG_REQUIRE(flag == 0, "%s: a query lies outside the sampled range [x[0], x[n-1]] (ext=2)", who);
     return SSHG_OK;
+}
+
+// broadC -> splineC -> evaluation in one call (reference shg.py:388-389, 423-424): the broadened
+// rows stay on the device between K1 and the spline kernels.
+extern "C" int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
+                                     double sigma, const double* xq, int64_t nq, double* out, int where) {
+    SSHG_REQUIRE(ctx && x && y && xq && out, "sshg_broaden_resample: null argument");
+    SSHG_REQUIRE(rows > 0 && nq > 0, "sshg_broaden_resample: rows and nq must be positive");
+    SSHG_REQUIRE(n >= 4, "sshg_broaden_resample: a cubic interpolating spline needs at least 4 samples (got %lld)",
+                 (long long)n);
+    SSHG_REQUIRE(sigma >= 0.0 && isfinite(sigma), "sshg_broaden_resample: sigma must be finite and >= 0 (got %g)", sigma);
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    if (!in_dev) {
+        for (int64_t i = 1; i < n; ++i)
+            SSHG_REQUIRE(x[i] > x[i - 1], "sshg_broaden_resample: x must be strictly increasing (x[%lld])", (long long)i);
+    }
+    const void *dx, *dy, *dq;
+    if (int rc = sshg_stage_in(ctx, 10, x, (size_t)n * 8, in_dev, &dx)) return rc;
+    if (int rc = sshg_stage_in(ctx, 11, y, (size_t)rows * n * 8, in_dev, &dy)) return rc;
+    if (int rc = sshg_stage_in(ctx, 12, xq, (size_t)nq * 8, in_dev, &dq)) return rc;
+    if (sigma > 1e-15) {
+        void* db;
+        if (int rc = sshg_scratch(ctx, SCR_BROAD, (size_t)rows * n * 8, &db)) return rc;
+        if (int rc = sshg_gauss_device(ctx, (const double*)dy, (double*)db, rows, n, n, 1, sigma)) return rc;
+        dy = db;
+    }
+    void *dflag, *dout = out;
+    if (int rc = sshg_scratch(ctx, 15, 16, &dflag)) return rc;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 9, (size_t)rows * nq * 8, &dout)) return rc;
+    }
+    if (int rc = sshg_spline_device(ctx, (const double*)dx, (const double*)dy, rows, n, (const double*)dq, nq,
+                                    (double*)dout, (int*)dflag)) return rc;
+    return spline_finish(ctx, dflag, dout, out, (size_t)rows * nq * 8, out_dev, "sshg_broaden_resample");
 }

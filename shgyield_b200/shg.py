@@ -132,28 +132,40 @@ def splineC(data, energy):
     return (_DeviceSpline(data.real, energy), _DeviceSpline(data.imag, energy))
 
 
-def _resample_group(specs: dict, queries):
-    """{key: {'energy', 'data'}} -> {key: [complex array per query vector]}; spectra that share
-    an energy axis go through one kernel call."""
+def _resample_group(specs: dict, queries, sigma: float = 0.0):
+    """{key: {'energy', 'data'}} -> {key: [complex array per query vector]}.  Every spectrum is
+    broadened with `sigma` (samples) and resampled in ONE library call per distinct energy axis
+    (sshg_broaden_resample: K1 and the spline kernels chained on the device); spectra that are the
+    same object (symmetry aliases such as chi_yyz = chi_xxz) are computed once."""
     out = {k: [None] * len(queries) for k in specs}
+    if not specs or not queries:
+        return out
+    ctx = _lib.context()
     groups = {}
     for k, v in specs.items():
         x = np.ascontiguousarray(v["energy"], dtype=np.float64)
-        groups.setdefault((x.size, x.tobytes()), (x, []))[1].append(k)
+        g = groups.setdefault((x.size, x.tobytes()), {"x": x, "uniq": {}, "keys": {}})
+        slot = g["uniq"].setdefault(id(v["data"]), (len(g["uniq"]), v["data"]))[0]
+        g["keys"][k] = slot
     sizes = [np.asarray(q).size for q in queries]
-    allq = np.concatenate([np.asarray(q, dtype=np.float64).ravel() for q in queries]) if queries else np.empty(0)
-    for x, keys in groups.values():
-        rows = np.empty((2 * len(keys), x.size))
-        for i, k in enumerate(keys):
-            d = np.asarray(specs[k]["data"])
-            if d.shape != x.shape:
+    allq = np.ascontiguousarray(np.concatenate([np.asarray(q, dtype=np.float64).ravel() for q in queries]))
+    for g in groups.values():
+        x = g["x"]
+        rows = np.empty((2 * len(g["uniq"]), x.size))
+        for slot, data in g["uniq"].values():
+            d = np.asarray(data)
+            if x.ndim != 1 or d.shape != x.shape:
                 raise ValueError("x and y should have a same length")
-            rows[2 * i], rows[2 * i + 1] = d.real, d.imag
-        res = _resample_rows(x, rows, allq)
+            rows[2 * slot], rows[2 * slot + 1] = d.real, d.imag
+        res = np.empty((rows.shape[0], allq.size))
+        if allq.size:
+            _lib.check(ctx.lib.sshg_broaden_resample(ctx.handle, x.ctypes.data, rows.ctypes.data, rows.shape[0], x.size,
+                                                     float(sigma), allq.ctypes.data, allq.size, res.ctypes.data,
+                                                     _lib.HOST), ctx.lib)
         off = 0
         for j, (q, sz) in enumerate(zip(queries, sizes)):
-            for i, k in enumerate(keys):
-                out[k][j] = (res[2 * i, off:off + sz] + 1j * res[2 * i + 1, off:off + sz]).reshape(np.shape(q))
+            for k, slot in g["keys"].items():
+                out[k][j] = (res[2 * slot, off:off + sz] + 1j * res[2 * slot + 1, off:off + sz]).reshape(np.shape(q))
             off += sz
     return out
 
@@ -228,12 +240,15 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
     Returns (eps1w [3,nE], eps2w [3,nE], chi_rot [18,nE], thick) for the flattened energies."""
     energy = np.asarray(energy, dtype=np.float64)
     nE = energy.size
+    # all spectra of the three media: one broaden + resample call (queries E and 2E)
+    specs = {(m, k): v for m, eps_m in enumerate((eps_m1, eps_m2, eps_m3)) for k, v in eps_m.items()
+             if isinstance(v, dict)}
+    rs = _resample_group(specs, [energy, 2 * energy], sigma_eps)
     media = []
-    for eps_m in (eps_m1, eps_m2, eps_m3):
+    for m, eps_m in enumerate((eps_m1, eps_m2, eps_m3)):
+        one = {k: rs[(m, k)][0] for k, v in eps_m.items() if isinstance(v, dict)}
+        two = {k: rs[(m, k)][1] for k, v in eps_m.items() if isinstance(v, dict)}
         num = {k: v for k, v in eps_m.items() if not isinstance(v, dict)}
-        brd = {k: {"energy": v["energy"], "data": broadC(v["data"], sigma_eps)}
-               for k, v in eps_m.items() if isinstance(v, dict)}
-        one, two = splineEPS(brd, energy)
         one.update(num)
         two.update(num)
         media.append((one, two))
@@ -254,9 +269,8 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
         eps2w[m] = np.broadcast_to(np.asarray(e2[m], dtype=np.complex128), energy.shape).ravel()
 
     chi_num = {k: v for k, v in chi2.items() if not isinstance(v, dict)}
-    chi_brd = {k: {"energy": v["energy"], "data": broadC(v["data"], sigma_chi)}
-               for k, v in chi2.items() if isinstance(v, dict)}
-    chi_new = {k: v[0] for k, v in _resample_group(chi_brd, [energy]).items()}
+    chi_spec = {k: v for k, v in chi2.items() if isinstance(v, dict)}
+    chi_new = {k: v[0] for k, v in _resample_group(chi_spec, [energy], sigma_chi).items()}
     chi_new.update(chi_num)
     packed = np.empty((18, nE), dtype=np.complex128)
     for i, k in enumerate(CHI2_KEYS):
