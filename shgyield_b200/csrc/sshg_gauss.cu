@@ -17,6 +17,7 @@
 //
 // HBM traffic: 8 B read + 8 B written per sample (halo re-reads hit L2).
 #include "sshg_internal.h"
+#include "sshg_fir.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -30,76 +31,76 @@ __device__ __forceinline__ long long reflect(long long i, long long n) {
     return m >= n ? 2 * n - 1 - m : m;
 }
 
-// ---- contiguous rows: register-window FIR ----------------------------------------------------
+// ---- contiguous rows: register-window FIR (window arithmetic in sshg_fir.cuh) ------------------
 constexpr int ST = 128;             // threads per CTA
-constexpr int SR = 9;               // consecutive outputs per thread (odd: stride-9 LDS.64 is conflict-free)
+constexpr int SR = sshg::SR;        // consecutive outputs per thread
 constexpr int STILE = ST * SR;      // outputs per CTA
+using sshg::fir_full;
+using sshg::fir_head;
+using sshg::fir_tail;
 
 // smem: xs[STILE + 2r + SR] samples (zero padded), then wext[2r + 1 + 3 SR] taps:
 // wext[k] = w_full[k - (SR-1)] for 0 <= k - (SR-1) <= 2r, else 0.
+// Taps that do not exist are skipped rather than multiplied by zero, so that an Inf/NaN sample
+// never reaches outputs beyond the true radius (the reference's NaN pattern).
 __global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                           const double* __restrict__ taps, long long n,
                                                           long long row_stride, int r, int tiles_per_row) {
     extern __shared__ double sm[];
-    const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding of the last steps)
+    const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding)
+    const int used = STILE + 2 * r;                // samples that feed an output of this tile
     const int ntap = 2 * r + 1 + 3 * SR;
     double* xs = sm;
     double* wext = sm + span;
+    const int tid = threadIdx.x;
     const long long row = blockIdx.x / tiles_per_row;
     const long long i0 = (long long)(blockIdx.x % tiles_per_row) * STILE;
     const double* src = in + row * row_stride;
     double* dst = out + row * row_stride;
-    for (int k = threadIdx.x; k < span; k += ST) {
-        const long long i = i0 - r + k;
-        double v = 0.0;
-        if (k < STILE + 2 * r) {
-            if (i >= 0 && i < n) v = src[i];
-            else if (i < n + r) v = src[reflect(i, n)];
+    const bool interior = (i0 - r >= 0) && (i0 + STILE + r <= n);
+    constexpr int NB = 5;                          // loads in flight per thread
+    for (int k0 = 0; k0 < span; k0 += ST * NB) {
+        double v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * ST + tid;
+            v[b] = 0.0;
+            if (k < used) {
+                const long long i = i0 - r + k;
+                if (interior || (i >= 0 && i < n)) v[b] = src[i];
+                else if (i < n + r) v[b] = src[reflect(i, n)];
+            }
         }
-        xs[k] = v;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * ST + tid;
+            if (k < span) xs[k] = v[b];
+        }
     }
-    for (int k = threadIdx.x; k < ntap; k += ST) {
+    for (int k = tid; k < ntap; k += ST) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
         wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
     __syncthreads();
 
-    const double* xw = xs + threadIdx.x * SR;      // window of this thread: xw[t], t = 0 .. 2r + SR - 1
+    const double* xw = xs + tid * SR;              // window of this thread: xw[t], t = 0 .. 2r + SR - 1
     double acc[SR], wr[SR];
 #pragma unroll
     for (int q = 0; q < SR; ++q) {
         acc[q] = 0.0;
-        wr[q] = wext[q];                           // wr[k % SR] = wext[k] for the current window [t, t + SR - 1]
+        wr[q] = wext[q];
     }
-    // Output q of this thread takes tap j = t - q of sample t; only 0 <= j <= 2r exist.  The first
-    // block needs the lower bound (static), the last blocks the upper one (r is a run-time value);
-    // the blocks in between are unconditional.  Skipping (rather than multiplying by a zero tap)
-    // keeps an Inf/NaN sample from reaching outputs beyond the true radius.
-    const int steps = 2 * r + SR;                  // t = 0 .. steps - 1
-    auto block = [&](int t0, auto first, auto tail) {
-#pragma unroll
-        for (int u = 0; u < SR; ++u) {
-            const double v = xw[t0 + u];
-#pragma unroll
-            for (int q = 0; q < SR; ++q) {
-                if (decltype(first)::value && q > u) continue;
-                if (decltype(tail)::value && t0 + u - q > 2 * r) continue;
-                acc[q] = fma(wr[(u + SR - 1 - q) % SR], v, acc[q]);
-            }
-            wr[u] = wext[t0 + u + SR];             // tap entering the window (zero beyond the kernel)
-        }
-    };
-    block(0, std::true_type{}, std::true_type{});
-    int t0 = SR;
-    for (; t0 + SR - 1 <= 2 * r; t0 += SR) block(t0, std::false_type{}, std::false_type{});
-    for (; t0 < steps; t0 += SR) block(t0, std::false_type{}, std::true_type{});
+    sshg::fir_window(xw, wext, r, acc, wr);
     __syncthreads();                               // every window read is done: reuse xs for the results
 #pragma unroll
-    for (int q = 0; q < SR; ++q) xs[threadIdx.x * SR + q] = acc[q];
+    for (int q = 0; q < SR; ++q) xs[tid * SR + q] = acc[q];
     __syncthreads();
-    for (int k = threadIdx.x; k < STILE; k += ST) {
-        const long long i = i0 + k;
-        if (i < n) dst[i] = xs[k];
+    if (i0 + STILE <= n) {
+#pragma unroll
+        for (int k = 0; k < SR; ++k) dst[i0 + k * ST + tid] = xs[k * ST + tid];
+    } else {
+        for (int k = tid; k < STILE; k += ST)
+            if (i0 + k < n) dst[i0 + k] = xs[k];
     }
 }
 

@@ -7,6 +7,7 @@
 
 #define SSHG_NSCRATCH 24
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
+#define SCR_SPLFAC 17    // spline elimination coefficients of the last axis (cached)
 #define SCR_BROAD 16     // broadened rows handed from K1 to the spline kernels
 
 struct sshg_ctx {
@@ -20,6 +21,9 @@ struct sshg_ctx {
     int64_t launches;
     double tap_sigma;           // sigma whose taps are in scratch[SCR_TAPS] (tap_ptr guards reallocation)
     void* tap_ptr;
+    uint64_t spl_hash;          // axis whose spline factorisation is in scratch[SCR_SPLFAC] (0: none)
+    int64_t spl_n;
+    void* spl_ptr;
     // growable device scratch buffers (inputs copied from the host, staged outputs)
     void* scratch[SSHG_NSCRATCH];
     size_t scratch_bytes[SSHG_NSCRATCH];
@@ -47,7 +51,7 @@ int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out);   // grows 
 int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                       int64_t elem_stride, double sigma);
 int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
-                       int64_t nq, double* dout, int* dflag);
+                       int64_t nq, double* dout, int* dflag, uint64_t axis_hash);
 
 // Copies a host array to a scratch slot (or passes a device pointer through).
 int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device,

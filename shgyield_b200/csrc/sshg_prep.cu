@@ -63,43 +63,77 @@ __global__ void rotate_kernel(const double2* __restrict__ in, double2* __restric
 }
 
 // ---- spline -------------------------------------------------------------------------------
-// Second derivatives of the not-a-knot cubic spline, one thread per signal.
-// cp/dp: scratch [n][rows] (thread-contiguous).  y, M: [rows][n].
-__global__ void spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                                    double* __restrict__ M, double* __restrict__ cp, double* __restrict__ dp,
-                                    long long rows, long long n) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const double* yr = y + r * n;
-    double* Mr = M + r * n;
+// Not-a-knot cubic spline through its second derivatives M: tridiagonal system in M_1..M_{n-2}
+// (Thomas algorithm).  The elimination coefficients depend on the axis x only, so they are
+// factored once per axis by one thread (`spline_factor_kernel`; cached in the context while the
+// same axis keeps coming) and every signal then needs two short first-order recurrences
+// (`spline_solve_kernel`, one thread per signal, FMA-latency bound).
+//
+// fac layout, m = n - 2:  cp[m] | inv[m] | low[m] | ih[n-1]   (ih[i] = 1 / (x[i+1] - x[i]))
+__global__ void spline_factor_kernel(const double* __restrict__ x, double* __restrict__ fac, long long n) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const long long m = n - 2;
+    double* cp = fac;
+    double* inv = fac + m;
+    double* low = fac + 2 * m;
+    double* ih = fac + 3 * m;
     const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
     const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
-    double cprev = 0.0, dprev = 0.0;
+    double cprev = 0.0;
     for (long long i = 0; i < m; ++i) {
         const double hl = x[i + 1] - x[i], hr = x[i + 2] - x[i + 1];
         double lower = hl, diag = 2.0 * (hl + hr), upper = hr;
-        const double rhs = 6.0 * ((yr[i + 2] - yr[i + 1]) / hr - (yr[i + 1] - yr[i]) / hl);
-        if (i == 0) {
+        if (i == 0) {                           // not-a-knot at x_1: M_0 = (1 + q0) M_1 - q0 M_2
             diag += hl * (1.0 + q0);
             upper -= hl * q0;
         }
-        if (i == m - 1) {
+        if (i == m - 1) {                       // not-a-knot at x_{n-2}
             diag += hr * (1.0 + q1);
             lower -= hr * q1;
         }
         const double den = (i == 0) ? diag : diag - lower * cprev;
-        cprev = upper / den;
-        dprev = (i == 0) ? rhs / den : (rhs - lower * dprev) / den;
-        cp[i * rows + r] = cprev;
+        const double r = 1.0 / den;
+        cprev = upper * r;
+        cp[i] = cprev;
+        inv[i] = r;
+        low[i] = (i == 0) ? 0.0 : lower;
+        ih[i] = 1.0 / hl;
+        if (i == m - 1) ih[i + 1] = 1.0 / hr;
+    }
+}
+
+// y, M: [rows][n]; dp: scratch [m][rows] (thread-contiguous).
+__global__ void spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                    const double* __restrict__ fac, double* __restrict__ M, double* __restrict__ dp,
+                                    long long rows, long long n) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const long long m = n - 2;
+    const double* cp = fac;
+    const double* inv = fac + m;
+    const double* low = fac + 2 * m;
+    const double* ih = fac + 3 * m;
+    const double* yr = y + r * n;
+    double* Mr = M + r * n;
+    double dprev = 0.0;
+    double s_lo = (yr[1] - yr[0]) * ih[0];      // slope of the interval left of node i + 1
+#pragma unroll 8
+    for (long long i = 0; i < m; ++i) {
+        const double s_hi = (yr[i + 2] - yr[i + 1]) * ih[i + 1];
+        const double rhs = 6.0 * (s_hi - s_lo);
+        s_lo = s_hi;
+        dprev = (rhs - low[i] * dprev) * inv[i];
         dp[i * rows + r] = dprev;
     }
     double next = dprev;                        // M_{n-2}
     Mr[m] = next;
+#pragma unroll 8
     for (long long i = m - 2; i >= 0; --i) {
-        next = dp[i * rows + r] - cp[i * rows + r] * next;
+        next = dp[i * rows + r] - cp[i] * next;
         Mr[i + 1] = next;
     }
+    const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
+    const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
     Mr[0] = (1.0 + q0) * Mr[1] - q0 * Mr[2];
     Mr[n - 1] = (1.0 + q1) * Mr[n - 2] - q1 * Mr[n - 3];
 }
@@ -134,6 +168,14 @@ __global__ void spline_eval_kernel(const double* __restrict__ x, const double* _
 
 static int spline_finish(sshg_ctx* ctx, void* dflag, void* dout, double* out, size_t out_bytes, int out_dev,
                          const char* who);
+
+// FNV-1a over the bytes of a host axis (never 0): key of the cached spline factorisation.
+static uint64_t axis_hash_of(const double* x, int64_t n) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* p = (const unsigned char*)x;
+    for (size_t i = 0; i < (size_t)n * 8; ++i) h = (h ^ p[i]) * 1099511628211ull;
+    return h ? h : 1;
+}
 
 extern "C" int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, int64_t nE, double gamma_deg,
                            int xxy_quirk, int where) {
@@ -198,19 +240,28 @@ extern "C" int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double
         if (int rc = sshg_scratch(ctx, 9, (size_t)rows * nq * 8, &dout)) return rc;
     }
     if (int rc = sshg_spline_device(ctx, (const double*)dx, (const double*)dy, rows, n, (const double*)dq, nq,
-                                    (double*)dout, (int*)dflag)) return rc;
+                                    (double*)dout, (int*)dflag, in_dev ? 0 : axis_hash_of(x, n))) return rc;
     return spline_finish(ctx, dflag, dout, out, (size_t)rows * nq * 8, out_dev, "sshg_spline_resample");
 }
 
 // Second derivatives + evaluation, all pointers on the device; *dflag is set when a query is out of range.
 int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
-                       int64_t nq, double* dout, int* dflag) {
-    void *dM, *dcp;
+                       int64_t nq, double* dout, int* dflag, uint64_t axis_hash) {
+    void *dM, *ddp, *dfac;
     if (int rc = sshg_scratch(ctx, 13, (size_t)rows * n * 8, &dM)) return rc;
-    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 16, &dcp)) return rc;
-    void* ddp = (char*)dcp + (size_t)rows * n * 8;
+    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 8, &ddp)) return rc;
+    if (int rc = sshg_scratch(ctx, SCR_SPLFAC, (size_t)(4 * n) * 8, &dfac)) return rc;
     SSHG_CUDA(cudaMemsetAsync(dflag, 0, 4, ctx->stream));
-    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (double*)dM, (double*)dcp,
+    // the factorisation is reused while the same axis (same host bytes) keeps coming
+    if (!(axis_hash != 0 && ctx->spl_hash == axis_hash && ctx->spl_n == n && ctx->spl_ptr == dfac)) {
+        spline_factor_kernel<<<1, 32, 0, ctx->stream>>>(dx, (double*)dfac, n);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        ctx->spl_hash = axis_hash;
+        ctx->spl_n = n;
+        ctx->spl_ptr = dfac;
+    }
+    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM,
                                                                             (double*)ddp, rows, n);
     SSHG_CUDA(cudaGetLastError());
     const long long total = (long long)rows * nq;
@@ -263,6 +314,6 @@ extern "C" int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const doubl
         if (int rc = sshg_scratch(ctx, 9, (size_t)rows * nq * 8, &dout)) return rc;
     }
     if (int rc = sshg_spline_device(ctx, (const double*)dx, (const double*)dy, rows, n, (const double*)dq, nq,
-                                    (double*)dout, (int*)dflag)) return rc;
+                                    (double*)dout, (int*)dflag, in_dev ? 0 : axis_hash_of(x, n))) return rc;
     return spline_finish(ctx, dflag, dout, out, (size_t)rows * nq * 8, out_dev, "sshg_broaden_resample");
 }

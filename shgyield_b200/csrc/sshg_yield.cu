@@ -15,13 +15,17 @@
 #include "sshg_internal.h"
 #include "sshg_math.cuh"
 
+#include <stdlib.h>
+
 using namespace sshg;
 
 namespace {
 
-constexpr int NT = 256;        // threads per CTA
+constexpr int NT_BIG = 256;    // threads per CTA for large launches (512-energy tiles)
+constexpr int NT_SMALL = 128;  // ... and for launches of only a few waves (shorter tail)
 constexpr int EPT = 2;         // energies per thread
-constexpr int CHUNK = 384;     // phi items per shared-memory table chunk
+constexpr int CHUNK_BIG = 384;    // phi items per shared-memory table chunk (18 KB)
+constexpr int CHUNK_SMALL = 256;  // ... 12 KB, so that four 128-thread CTAs fit one SM
 constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
 
 struct YieldArgs {
@@ -155,7 +159,8 @@ __device__ __forceinline__ cplx ldc(const double2* p) {
     return mk(v.x, v.y);
 }
 
-__global__ void __launch_bounds__(NT, 2) yield_grid_kernel(const YieldArgs a) {
+template <int NT, int CHUNK>
+__global__ void __launch_bounds__(NT, 512 / NT) yield_grid_kernel(const YieldArgs a) {
     extern __shared__ double smem[];
     double* tabs = smem;                        // [CHUNK][6]
     double* cols = smem + CHUNK * 6;            // [EPT][NCOL][NT]
@@ -348,7 +353,7 @@ int check_physics(const sshg_physics& p) {
     return SSHG_OK;
 }
 
-constexpr size_t GRID_SMEM = (size_t)(CHUNK * 6 + EPT * NCOL * NT) * sizeof(double);
+constexpr size_t grid_smem(int nt, int chunk) { return (size_t)(chunk * 6 + EPT * NCOL * nt) * sizeof(double); }
 
 }  // namespace
 
@@ -402,20 +407,39 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     a.nDs = (int)(d1 - d0);
     a.t0 = (int)t0;
     a.d0 = (int)d0;
-    a.n_tiles = (int)((p->nE + NT * EPT - 1) / (NT * EPT));
+    // CTA size: 256 threads unless the launch would be only a few waves, where 128-thread CTAs
+    // (half as long, twice as many) keep more SMs busy at the tail.  SSHG_K2_NT=128|256 overrides.
+    int nt = NT_BIG;
+    {
+        const int64_t ncol = (t1 - t0) * (d1 - d0);
+        const int64_t ctas_big = ncol * ((p->nE + NT_BIG * EPT - 1) / (NT_BIG * EPT));
+        if (ctas_big < 6LL * 2 * ctx->num_sms) nt = NT_SMALL;
+        if (const char* env = getenv("SSHG_K2_NT")) {
+            if (atoi(env) == NT_SMALL) nt = NT_SMALL;
+            else if (atoi(env) == NT_BIG) nt = NT_BIG;
+        }
+    }
+    a.n_tiles = (int)((p->nE + nt * EPT - 1) / (nt * EPT));
     a.ph = make_physics(p->phys);
 
     const int64_t cols = (int64_t)a.nTs * a.nDs;
     const int64_t per_col = 4 * p->nP * p->nE;            // doubles per column
     SSHG_REQUIRE(cols * a.n_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
-    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRID_SMEM));
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_BIG, CHUNK_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)grid_smem(NT_BIG, CHUNK_BIG)));
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
 
     auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
         YieldArgs b = a;
         b.col0 = c0;
         b.out = dst;
         b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
-        yield_grid_kernel<<<(unsigned)(nc * a.n_tiles), NT, GRID_SMEM, st>>>(b);
+        if (nt == NT_BIG)
+            yield_grid_kernel<NT_BIG, CHUNK_BIG><<<(unsigned)(nc * a.n_tiles), NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
+        else
+            yield_grid_kernel<NT_SMALL, CHUNK_SMALL>
+                <<<(unsigned)(nc * a.n_tiles), NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;

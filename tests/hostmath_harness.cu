@@ -53,3 +53,38 @@ extern "C" int hostmath_yield_points(const sshg_points* p, double* out) {
     }
     return 0;
 }
+
+// ---- K1 register-window FIR (sshg_fir.cuh) on the CPU: one "thread" = SR consecutive outputs -------
+#include "../shgyield_b200/csrc/sshg_fir.cuh"
+#include <vector>
+
+// x: n samples, w: r + 1 taps (w[0] centre); out: n outputs with the 'reflect' boundary.
+extern "C" int hostmath_fir(const double* x, long long n, const double* w, int r, double* out) {
+    const int SR = sshg::SR;
+    const int ntap = 2 * r + 1 + 3 * SR;
+    std::vector<double> wext(ntap);
+    for (int k = 0; k < ntap; ++k) {
+        const int j = k - (SR - 1);
+        wext[k] = (j >= 0 && j <= 2 * r) ? w[j <= r ? r - j : j - r] : 0.0;
+    }
+    auto reflect = [&](long long i) {
+        long long m = i % (2 * n);
+        if (m < 0) m += 2 * n;
+        return m >= n ? 2 * n - 1 - m : m;
+    };
+    std::vector<double> xw(2 * r + 3 * SR);
+    for (long long base = 0; base < n; base += SR) {
+        for (int t = 0; t < (int)xw.size(); ++t) {
+            const long long i = base - r + t;
+            xw[t] = (t < 2 * r + SR && i < n + r) ? x[reflect(i)] : 0.0;
+        }
+        double acc[sshg::SR], wr[sshg::SR];
+        for (int q = 0; q < SR; ++q) {
+            acc[q] = 0.0;
+            wr[q] = wext[q];
+        }
+        sshg::fir_window(xw.data(), wext.data(), r, acc, wr);
+        for (int q = 0; q < SR && base + q < n; ++q) out[base + q] = acc[q];
+    }
+    return 0;
+}

@@ -27,7 +27,8 @@ def harness():
     outdir = os.path.join(util.REPO, "tests", "_build")
     os.makedirs(outdir, exist_ok=True)
     so = os.path.join(outdir, "hostmath.so")
-    deps = [src, os.path.join(util.REPO, "shgyield_b200/csrc/sshg_math.cuh"), os.path.join(util.REPO, "include/sshg.h")]
+    deps = [src, os.path.join(util.REPO, "shgyield_b200/csrc/sshg_math.cuh"),
+            os.path.join(util.REPO, "shgyield_b200/csrc/sshg_fir.cuh"), os.path.join(util.REPO, "include/sshg.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
         subprocess.run([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-fPIC", "-shared",
@@ -115,3 +116,26 @@ def test_switches(harness):
         for i, pol in enumerate(cases.POLS):
             ok, msg = cases.parity_ok(out[i], want[pol], rtol=1e-10)
             assert ok, (sn, zq, mr, pol, msg)
+
+
+@pytest.mark.parametrize("sigma", [0.2, 0.6, 1.0, 2.0, 2.2, 2.3, 3.3, 4.4, 5.0, 5.6, 6.1, 7.7, 12.0, 50.0])
+def test_fir_window_arithmetic(harness, sigma):
+    """The register-window FIR of K1 (sshg_fir.cuh), run on the CPU, against SciPy -- every value of
+    (2 radius) mod 9 and the short-kernel path; a NaN sample must not spread beyond the radius."""
+    from scipy import ndimage
+    harness.hostmath_fir.restype = C.c_int
+    harness.hostmath_fir.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]
+    w = orc.gaussian_taps(sigma)
+    r = (len(w) - 1) // 2
+    taps = np.ascontiguousarray(w[r:])
+    for n in (1, 5, 64, 257):
+        x = np.random.default_rng(n).normal(size=n)
+        out = np.empty(n)
+        assert harness.hostmath_fir(x.ctypes.data, n, taps.ctypes.data, r, out.ctypes.data) == 0
+        np.testing.assert_allclose(out, ndimage.gaussian_filter(x, sigma), rtol=0, atol=4e-15 * max(1.0, np.abs(x).max()))
+    x = np.random.default_rng(1).normal(size=300)
+    x[150] = np.nan
+    out = np.empty(300)
+    harness.hostmath_fir(x.ctypes.data, 300, taps.ctypes.data, r, out.ctypes.data)
+    bad = np.isnan(out)
+    assert np.array_equal(bad, np.abs(np.arange(300) - 150) <= r)

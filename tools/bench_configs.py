@@ -52,6 +52,11 @@ def main():
              put(eps1w), put(eps2w), put(chi_rot)]
         T, D, P, E = axes["theta"].size, axes["thick"].size, axes["phi"].size, axes["energy"].size
         out = torch.empty((T, D, 4, P, E), dtype=torch.float64, device=dev)
+        for nt in ("128", "256"):
+            os.environ["SSHG_K2_NT"] = nt
+            med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
+            print(json.dumps({"case": tag, "k2_threads": nt, "k2_ms_median": med, "k2_ms_best": best}), flush=True)
+        os.environ.pop("SSHG_K2_NT", None)
         med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
         pts = out.numel()
         flops = 28.0 * pts + 1000.0 * E * T * D
@@ -60,9 +65,24 @@ def main():
                           "alg_fp64_tflops": flops / (med * 1e-3) / 1e12, "host_prep_ms": prep_ms}), flush=True)
         del out
 
-    # ---- K1 on a cube slab: 8 thetas of config 5, sigma = 5 samples along E ---------------------------
+    # ---- config-5 theta shards (what one of 8 / 4 ranks computes), both CTA sizes of K2 ----------------
     cfg = config5()
     dd = {k: put(v) for k, v in cfg.items()}
+    for nth in (23, 46):
+        out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
+        for nt in ("128", "256", None):
+            if nt is None:
+                os.environ.pop("SSHG_K2_NT", None)
+            else:
+                os.environ["SSHG_K2_NT"] = nt
+            med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"], dd["eps1w"],
+                                                            dd["eps2w"], dd["chi2"], out=out, consts=consts,
+                                                            t_range=(0, nth)), args.reps)
+            print(json.dumps({"case": "config5_shard_%dtheta" % nth, "k2_threads": nt or "auto", "ms_median": med,
+                              "ms_best": best, "store_gbs": 8e-9 * out.numel() / (med * 1e-3)}), flush=True)
+        del out
+
+    # ---- K1 on a cube slab: 8 thetas of config 5, sigma = 5 samples along E ---------------------------
     slab = grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"], dd["eps1w"], dd["eps2w"], dd["chi2"],
                                   consts=consts, t_range=(60, 68))
     for sigma in (2.0, 5.0, 12.0):
