@@ -62,7 +62,7 @@ SSHG_FIR_HD void fir_full(const double* __restrict__ xw, const double* __restric
 // The whole window: acc[] must be zero and wr[q] = wext[q] on entry.
 SSHG_FIR_HD void fir_window(const double* __restrict__ xw, const double* __restrict__ wext, int r, double (&acc)[SR],
                             double (&wr)[SR]) {
-    if (2 * r >= 2 * SR) {
+    if (2 * r >= SR - 1) {
         fir_head(xw, wext, acc, wr);               // t = 0 .. SR-1
         int t0 = SR;
         for (; t0 + SR - 1 <= 2 * r; t0 += SR) fir_full(xw, wext, t0, acc, wr);
@@ -78,7 +78,7 @@ SSHG_FIR_HD void fir_window(const double* __restrict__ xw, const double* __restr
             default: fir_tail<8>(xw, wext, t0, acc, wr); break;
         }
     } else {
-        // short kernels (sigma < 2.2 samples): both bounds checked at run time
+        // very short kernels (radius < 4, sigma < 0.9 samples): both bounds checked at run time
         const int steps = 2 * r + SR;
         for (int t0 = 0; t0 < steps; t0 += SR) {
 #pragma unroll
