@@ -102,7 +102,104 @@ __global__ void spline_factor_kernel(const double* __restrict__ x, double* __res
     }
 }
 
-// y, M: [rows][n]; dp: scratch [m][rows] (thread-contiguous).
+// One CTA per signal, everything in shared memory (3 m doubles: 48 KB for the 2001-sample spectra).
+// All threads form a_i = rhs_i * inv_i, b_i = low_i * inv_i in parallel; thread 0 then runs the two
+// first-order recurrences  d_i = a_i - b_i d_{i-1}  and  M_{i+1} = d_i - cp_i M_{i+2}  as dependent
+// FMAs fed from shared memory (global loads inside the chain cost ~500 cycles per step).
+// y, M: [rows][n].
+__global__ void __launch_bounds__(128) spline_solve_smem_kernel(const double* __restrict__ x,
+                                                                const double* __restrict__ y,
+                                                                const double* __restrict__ fac,
+                                                                double* __restrict__ M, long long n) {
+    extern __shared__ double sp[];
+    const int m = (int)(n - 2);
+    double* A = sp;
+    double* B = sp + m;
+    double* CP = sp + 2 * m;
+    const double* cp = fac;
+    const double* inv = fac + m;
+    const double* low = fac + 2 * m;
+    const double* ih = fac + 3 * m;
+    const double* yr = y + (long long)blockIdx.x * n;
+    double* Mr = M + (long long)blockIdx.x * n;
+    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const double y0 = yr[i], y1 = yr[i + 1], y2 = yr[i + 2];
+        const double rhs = 6.0 * ((y2 - y1) * ih[i + 1] - (y1 - y0) * ih[i]);
+        const double r = inv[i];
+        A[i] = rhs * r;
+        B[i] = low[i] * r;
+        CP[i] = cp[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // software-pipelined in batches of 8: the loads of the next batch are issued before the
+        // dependent FMA chain of the current one, so the chain never waits for shared memory
+        constexpr int W = 8;
+        double d = 0.0;
+        {
+            double a[W], b[W], an[W], bn[W];
+            int i = 0;
+            if (m >= W) {
+#pragma unroll
+                for (int k = 0; k < W; ++k) { a[k] = A[k]; b[k] = B[k]; }
+            }
+            for (; i + W <= m; i += W) {
+                const bool more = i + 2 * W <= m;
+                if (more) {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) { an[k] = A[i + W + k]; bn[k] = B[i + W + k]; }
+                }
+#pragma unroll
+                for (int k = 0; k < W; ++k) { d = fma(-b[k], d, a[k]); a[k] = d; }
+#pragma unroll
+                for (int k = 0; k < W; ++k) A[i + k] = a[k];
+#pragma unroll
+                for (int k = 0; k < W; ++k) { a[k] = an[k]; b[k] = bn[k]; }
+            }
+            for (; i < m; ++i) {
+                d = fma(-B[i], d, A[i]);
+                A[i] = d;
+            }
+        }
+        double next = d;                        // M_{n-2} = d_{m-1}; A[i] becomes M_{i+1}
+        {
+            double a[W], c[W], an[W], cn[W];
+            int i = m - 2;                      // next index to process, going down
+            if (i - (W - 1) >= 0) {
+#pragma unroll
+                for (int k = 0; k < W; ++k) { a[k] = A[i - k]; c[k] = CP[i - k]; }
+            }
+            for (; i - (W - 1) >= 0; i -= W) {
+                const bool more = i - (2 * W - 1) >= 0;
+                if (more) {
+#pragma unroll
+                    for (int k = 0; k < W; ++k) { an[k] = A[i - W - k]; cn[k] = CP[i - W - k]; }
+                }
+#pragma unroll
+                for (int k = 0; k < W; ++k) { next = fma(-c[k], next, a[k]); a[k] = next; }
+#pragma unroll
+                for (int k = 0; k < W; ++k) A[i - k] = a[k];
+#pragma unroll
+                for (int k = 0; k < W; ++k) { a[k] = an[k]; c[k] = cn[k]; }
+            }
+            for (; i >= 0; --i) {
+                next = fma(-CP[i], next, A[i]);
+                A[i] = next;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < m; i += blockDim.x) Mr[i + 1] = A[i];
+    if (threadIdx.x == 0) {
+        const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
+        const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
+        Mr[0] = (1.0 + q0) * A[0] - q0 * A[1];
+        Mr[n - 1] = (1.0 + q1) * A[m - 1] - q1 * A[m - 2];
+    }
+}
+
+// Fallback for axes too long for shared memory: one thread per signal, dp in global scratch
+// [m][rows] (thread-contiguous).
 __global__ void spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
                                     const double* __restrict__ fac, double* __restrict__ M, double* __restrict__ dp,
                                     long long rows, long long n) {
@@ -122,14 +219,15 @@ __global__ void spline_solve_kernel(const double* __restrict__ x, const double* 
         const double s_hi = (yr[i + 2] - yr[i + 1]) * ih[i + 1];
         const double rhs = 6.0 * (s_hi - s_lo);
         s_lo = s_hi;
-        dprev = (rhs - low[i] * dprev) * inv[i];
+        const double rr = inv[i];
+        dprev = fma(-(low[i] * rr), dprev, rhs * rr);
         dp[i * rows + r] = dprev;
     }
     double next = dprev;                        // M_{n-2}
     Mr[m] = next;
 #pragma unroll 8
     for (long long i = m - 2; i >= 0; --i) {
-        next = dp[i * rows + r] - cp[i] * next;
+        next = fma(-cp[i], next, dp[i * rows + r]);
         Mr[i + 1] = next;
     }
     const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
@@ -261,8 +359,14 @@ int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_
         ctx->spl_n = n;
         ctx->spl_ptr = dfac;
     }
-    spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM,
-                                                                            (double*)ddp, rows, n);
+    const size_t solve_smem = (size_t)3 * (n - 2) * 8;
+    if (solve_smem <= 200 * 1024 && rows < (1LL << 31)) {
+        SSHG_CUDA(cudaFuncSetAttribute(spline_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        spline_solve_smem_kernel<<<(unsigned)rows, 128, solve_smem, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM, n);
+    } else {
+        spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM,
+                                                                                (double*)ddp, rows, n);
+    }
     SSHG_CUDA(cudaGetLastError());
     const long long total = (long long)rows * nq;
     spline_eval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dx, dy, (const double*)dM, rows, n, dq,

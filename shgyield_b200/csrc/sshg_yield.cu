@@ -413,7 +413,7 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     {
         const int64_t ncol = (t1 - t0) * (d1 - d0);
         const int64_t ctas_big = ncol * ((p->nE + NT_BIG * EPT - 1) / (NT_BIG * EPT));
-        if (ctas_big < 6LL * 2 * ctx->num_sms) nt = NT_SMALL;
+        if (ctas_big < 10LL * 2 * ctx->num_sms) nt = NT_SMALL;
         if (const char* env = getenv("SSHG_K2_NT")) {
             if (atoi(env) == NT_SMALL) nt = NT_SMALL;
             else if (atoi(env) == NT_BIG) nt = NT_BIG;
