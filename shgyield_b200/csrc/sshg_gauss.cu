@@ -56,7 +56,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // (LDGSTS), so the FP64 pipe does not idle during the loads.  Taps that do not exist are skipped
 // rather than multiplied by zero, so that an Inf/NaN sample never reaches outputs beyond the true
 // radius (the reference's NaN pattern).
-__global__ void __launch_bounds__(ST, 8) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
+__global__ void __launch_bounds__(ST, 7) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                           const double* __restrict__ taps, long long n,
                                                           long long row_stride, int r, int tiles_per_row,
                                                           long long total_tiles) {
@@ -64,15 +64,14 @@ __global__ void __launch_bounds__(ST, 8) gauss_stream_kernel(const double* __res
     const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding)
     const int used = STILE + 2 * r;                // samples that feed an output of this tile
     const int ntap = 2 * r + 1 + 3 * SR;
-    double* bufs[2] = {sm, sm + span};
-    double* wext = sm + 2 * span;
+    double* wext = sm + 2 * span;                  // buffer b lives at sm + b * span
     const int tid = threadIdx.x;
 
     for (int k = tid; k < ntap; k += ST) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
         wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
-    for (int k = used + tid; k < span; k += ST) bufs[0][k] = bufs[1][k] = 0.0;   // padding, never overwritten
+    for (int k = used + tid; k < span; k += ST) sm[k] = sm[span + k] = 0.0;     // padding, never overwritten
 
     // queue the loads of one tile into xs (asynchronous for interior tiles)
     auto issue = [&](long long tile, double* xs) {
@@ -95,12 +94,12 @@ __global__ void __launch_bounds__(ST, 8) gauss_stream_kernel(const double* __res
 
     long long tile = blockIdx.x;
     int cur = 0;
-    if (tile < total_tiles) issue(tile, bufs[0]);
+    if (tile < total_tiles) issue(tile, sm);
     while (tile < total_tiles) {
         const long long next = tile + gridDim.x;
-        double* xs = bufs[cur];
+        double* xs = sm + cur * span;
         if (next < total_tiles) {
-            issue(next, bufs[cur ^ 1]);
+            issue(next, sm + (cur ^ 1) * span);
             cp_async_wait<1>();                    // everything but the newest group has landed
         } else {
             cp_async_wait<0>();
@@ -250,7 +249,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         const int tiles = (int)((n + STILE - 1) / STILE);
         SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
         const long long all_tiles = (long long)rows * tiles;
-        const long long resident = (long long)ctx->num_sms * 8;     // 8 CTAs of 128 threads per SM (64 registers)
+        const long long resident = (long long)ctx->num_sms * 7;     // 7 CTAs of 128 threads per SM (72 registers)
         const unsigned grid = (unsigned)(all_tiles < resident ? all_tiles : resident);
         gauss_stream_kernel<<<grid, ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n, row_stride, (int)r,
                                                                    tiles, all_tiles);

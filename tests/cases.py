@@ -117,9 +117,27 @@ API_CASES = [
                                  thick=np.arange(1.0, 31.0).reshape(30, 1), gamma=0, sigma_out=0.0)),
     ("selftest_shape", "selftest", dict(energy=np.linspace(0.01, 1.00, 100), theta=65, phi=30, thick=10, gamma=0,
                                         sigma_eps=0.0, sigma_chi=0.0, sigma_out=0.0)),
+    # edge shapes: empty energy axis, everything scalar (0-d result), a 2-D energy array blurred along both axes
+    ("empty", "si111", dict(energy=np.array([]), theta=65, phi=30, thick=10, gamma=0, sigma_out=5)),
+    ("scalar_all", "si111", dict(energy=1.5, theta=65, phi=30, thick=10, gamma=0, sigma_out=5)),
+    ("energy2d_blur", "full", dict(energy=np.array([[1.5, 1.6, 1.7], [1.8, 1.9, 2.0]]), theta=65, phi=30, thick=10,
+                                   gamma=10, sigma_out=0.7)),
+    # a NaN sample in one spectrum poisons the whole (global) spline -> every output is NaN, no exception
+    ("nan_sample", "si111_nan", dict(energy=E_C1, theta=65, phi=30, thick=10, gamma=0, sigma_out=0.0)),
+    ("negative_energy_sign", "full", dict(energy=np.linspace(0.5, 3.0, 20), theta=110.0, phi=-75.0, thick=10, gamma=-20,
+                                          sigma_out=0.0)),
 ]
 
-MATERIALS = {"si111": si111_material, "full": full_tensor_material, "selftest": selftest_material}
+
+def si111_nan_material(spectra=None):
+    m1, m2, m3, chi2 = si111_material(spectra)
+    m2 = {k: {"energy": v["energy"], "data": v["data"].copy()} for k, v in m2.items()}
+    m2["xx"]["data"][150] = np.nan
+    return m1, m2, m3, chi2
+
+
+MATERIALS = {"si111": si111_material, "full": full_tensor_material, "selftest": selftest_material,
+             "si111_nan": si111_nan_material}
 
 
 # ---- sampled points of the large grids (configs 3, 4, 5 of BASELINE.json) --------------------
