@@ -39,98 +39,68 @@ using sshg::fir_full;
 using sshg::fir_head;
 using sshg::fir_tail;
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// Persistent CTAs, grid-stride over the tiles (rows x tiles_per_row).
-// smem: two sample buffers xs[2][STILE + 2r + SR] (zero padded) and wext[2r + 1 + 3 SR] taps,
+// smem: xs[STILE + 2r + SR] samples (zero padded), then wext[2r + 1 + 3 SR] taps:
 // wext[k] = w_full[k - (SR-1)] for 0 <= k - (SR-1) <= 2r, else 0.
-// While a tile is filtered out of one buffer, the next tile streams into the other with cp.async
-// (LDGSTS), so the FP64 pipe does not idle during the loads.  Taps that do not exist are skipped
-// rather than multiplied by zero, so that an Inf/NaN sample never reaches outputs beyond the true
-// radius (the reference's NaN pattern).
-__global__ void __launch_bounds__(ST, 7) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
+// Taps that do not exist are skipped rather than multiplied by zero, so that an Inf/NaN sample
+// never reaches outputs beyond the true radius (the reference's NaN pattern).
+__global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                           const double* __restrict__ taps, long long n,
-                                                          long long row_stride, int r, int tiles_per_row,
-                                                          long long total_tiles) {
+                                                          long long row_stride, int r, int tiles_per_row) {
     extern __shared__ double sm[];
     const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding)
     const int used = STILE + 2 * r;                // samples that feed an output of this tile
     const int ntap = 2 * r + 1 + 3 * SR;
-    double* wext = sm + 2 * span;                  // buffer b lives at sm + b * span
+    double* xs = sm;
+    double* wext = sm + span;
     const int tid = threadIdx.x;
-
+    const long long row = blockIdx.x / tiles_per_row;
+    const long long i0 = (long long)(blockIdx.x % tiles_per_row) * STILE;
+    const double* src = in + row * row_stride;
+    double* dst = out + row * row_stride;
+    const bool interior = (i0 - r >= 0) && (i0 + STILE + r <= n);
+    constexpr int NB = 5;                          // loads in flight per thread
+    for (int k0 = 0; k0 < span; k0 += ST * NB) {
+        double v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * ST + tid;
+            v[b] = 0.0;
+            if (k < used) {
+                const long long i = i0 - r + k;
+                if (interior || (i >= 0 && i < n)) v[b] = src[i];
+                else if (i < n + r) v[b] = src[reflect(i, n)];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * ST + tid;
+            if (k < span) xs[k] = v[b];
+        }
+    }
     for (int k = tid; k < ntap; k += ST) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
         wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
-    for (int k = used + tid; k < span; k += ST) sm[k] = sm[span + k] = 0.0;     // padding, never overwritten
+    __syncthreads();
 
-    // queue the loads of one tile into xs (asynchronous for interior tiles)
-    auto issue = [&](long long tile, double* xs) {
-        const long long row = tile / tiles_per_row;
-        const long long i0 = (tile % tiles_per_row) * STILE;
-        const double* src = in + row * row_stride + (i0 - r);
-        if (i0 - r >= 0 && i0 + STILE + r <= n) {
-            for (int k = tid; k < used; k += ST) cp_async8(xs + k, src + k);
-        } else {
-            for (int k = tid; k < used; k += ST) {
-                const long long i = i0 - r + k;
-                double v = 0.0;                    // samples beyond n - 1 + r feed no valid output
-                if (i >= 0 && i < n) v = src[k];
-                else if (i < n + r) v = in[row * row_stride + reflect(i, n)];
-                xs[k] = v;
-            }
-        }
-        cp_async_commit();
-    };
-
-    long long tile = blockIdx.x;
-    int cur = 0;
-    if (tile < total_tiles) issue(tile, sm);
-    while (tile < total_tiles) {
-        const long long next = tile + gridDim.x;
-        double* xs = sm + cur * span;
-        if (next < total_tiles) {
-            issue(next, sm + (cur ^ 1) * span);
-            cp_async_wait<1>();                    // everything but the newest group has landed
-        } else {
-            cp_async_wait<0>();
-        }
-        __syncthreads();
-
-        const double* xw = xs + tid * SR;          // window of this thread: xw[t], t = 0 .. 2r + SR - 1
-        double acc[SR], wr[SR];
+    const double* xw = xs + tid * SR;              // window of this thread: xw[t], t = 0 .. 2r + SR - 1
+    double acc[SR], wr[SR];
 #pragma unroll
-        for (int q = 0; q < SR; ++q) {
-            acc[q] = 0.0;
-            wr[q] = wext[q];
-        }
-        sshg::fir_window(xw, wext, r, acc, wr);
-        __syncthreads();                           // every window read is done: reuse xs for the results
+    for (int q = 0; q < SR; ++q) {
+        acc[q] = 0.0;
+        wr[q] = wext[q];
+    }
+    sshg::fir_window(xw, wext, r, acc, wr);
+    __syncthreads();                               // every window read is done: reuse xs for the results
 #pragma unroll
-        for (int q = 0; q < SR; ++q) xs[tid * SR + q] = acc[q];
-        __syncthreads();
-        const long long row = tile / tiles_per_row;
-        const long long i0 = (tile % tiles_per_row) * STILE;
-        double* dst = out + row * row_stride;
-        if (i0 + STILE <= n) {
+    for (int q = 0; q < SR; ++q) xs[tid * SR + q] = acc[q];
+    __syncthreads();
+    if (i0 + STILE <= n) {
 #pragma unroll
-            for (int k = 0; k < SR; ++k) dst[i0 + k * ST + tid] = xs[k * ST + tid];
-        } else {
-            for (int k = tid; k < STILE; k += ST)
-                if (i0 + k < n) dst[i0 + k] = xs[k];
-        }
-        __syncthreads();                           // xs is the load target of the tile after next
-        cur ^= 1;
-        tile = next;
+        for (int k = 0; k < SR; ++k) dst[i0 + k * ST + tid] = xs[k * ST + tid];
+    } else {
+        for (int k = tid; k < STILE; k += ST)
+            if (i0 + k < n) dst[i0 + k] = xs[k];
     }
 }
 
@@ -243,16 +213,14 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         ctx->tap_sigma = sigma;
         ctx->tap_ptr = dw;
     }
-    const size_t smem_stream = (size_t)(2 * (STILE + 2 * r + SR) + 2 * r + 1 + 3 * SR) * 8;
+    const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;
     if (elem_stride == 1 && smem_stream <= SMEM_CAP) {
         const int tiles = (int)((n + STILE - 1) / STILE);
+        SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
         SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
-        const long long all_tiles = (long long)rows * tiles;
-        const long long resident = (long long)ctx->num_sms * 7;     // 7 CTAs of 128 threads per SM (72 registers)
-        const unsigned grid = (unsigned)(all_tiles < resident ? all_tiles : resident);
-        gauss_stream_kernel<<<grid, ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n, row_stride, (int)r,
-                                                                   tiles, all_tiles);
+        gauss_stream_kernel<<<(unsigned)(rows * tiles), ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n,
+                                                                                      row_stride, (int)r, tiles);
     } else if (smem_tiled <= SMEM_CAP) {
         const int tiles = (int)((n + GTILE - 1) / GTILE);
         SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");

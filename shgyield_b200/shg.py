@@ -76,10 +76,11 @@ def _gauss_axis(ctx, arr: np.ndarray, sigma: float, axis: int) -> np.ndarray:
 def broad(data, sigma):
     """Gaussian broadening of a real array (sigma in samples, every axis, like the reference's
     scipy.ndimage.gaussian_filter call, shg.py:26-28)."""
-    arr = np.ascontiguousarray(data, dtype=np.float64)
+    arr = np.asarray(data, dtype=np.float64)
     sigma = float(sigma)
     if arr.ndim == 0 or arr.size == 0 or not sigma > 1e-15:
-        return arr.copy()
+        return arr.copy()                       # a 0-d input stays 0-d, like scipy's gaussian_filter
+    arr = np.ascontiguousarray(arr)
     ctx = _lib.context()
     for ax in range(arr.ndim):
         arr = _gauss_axis(ctx, arr, sigma, ax)
