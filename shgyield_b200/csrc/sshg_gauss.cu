@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restri
     const double* src = in + row * row_stride;
     double* dst = out + row * row_stride;
     const bool interior = (i0 - r >= 0) && (i0 + STILE + r <= n);
-    constexpr int NB = 5;                          // loads in flight per thread
+    constexpr int NB = 10;                         // loads in flight per thread (one batch covers radius <= 59)
     for (int k0 = 0; k0 < span; k0 += ST * NB) {
         double v[NB];
 #pragma unroll
