@@ -32,34 +32,33 @@ __device__ __forceinline__ long long reflect(long long i, long long n) {
 }
 
 // ---- contiguous rows: register-window FIR (window arithmetic in sshg_fir.cuh) ------------------
+constexpr int ST = 128;             // threads per CTA
 constexpr int SR = sshg::SR;        // consecutive outputs per thread
-constexpr int ST_MAX = 256;         // threads per CTA: 64 .. 256, chosen per launch so that the tiles
-                                    // (threads x SR outputs) cover n with the smallest ragged remainder
+constexpr int STILE = ST * SR;      // outputs per CTA
+using sshg::fir_full;
+using sshg::fir_head;
+using sshg::fir_tail;
 
-__host__ __device__ inline int stream_span(int threads, int r) { return (threads * SR + 2 * r + SR + 1) & ~1; }
-__host__ __device__ inline int stream_ntap(int r) { return (sshg::fir_ntap(r) + 1) & ~1; }
-
-// smem: xs[span] samples (zero padded; span even so that what follows stays 16-byte aligned), then two
-// copies of the tap window wext[k] = w_full[k - (SR-1)] (0 outside 0..2r): wA aligned, wB 8 bytes further.
-__global__ void __launch_bounds__(ST_MAX) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
-                                                              const double* __restrict__ taps, long long n,
-                                                              long long row_stride, int r, int tiles_per_row) {
-    extern __shared__ __align__(16) double sm[];
-    const int ST = blockDim.x;
-    const int STILE = ST * SR;
-    const int span = stream_span(ST, r);
+// smem: xs[STILE + 2r + SR] samples (zero padded), then wext[2r + 1 + 3 SR] taps:
+// wext[k] = w_full[k - (SR-1)] for 0 <= k - (SR-1) <= 2r, else 0.
+// Taps that do not exist are skipped rather than multiplied by zero, so that an Inf/NaN sample
+// never reaches outputs beyond the true radius (the reference's NaN pattern).
+__global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                          const double* __restrict__ taps, long long n,
+                                                          long long row_stride, int r, int tiles_per_row) {
+    extern __shared__ double sm[];
+    const int span = STILE + 2 * r + SR;           // staged samples (incl. zero padding)
     const int used = STILE + 2 * r;                // samples that feed an output of this tile
-    const int ntap = stream_ntap(r);
+    const int ntap = 2 * r + 1 + 3 * SR;
     double* xs = sm;
-    double* wA = sm + span;
-    double* wB = wA + ntap + 1;
+    double* wext = sm + span;
     const int tid = threadIdx.x;
     const long long row = blockIdx.x / tiles_per_row;
     const long long i0 = (long long)(blockIdx.x % tiles_per_row) * STILE;
     const double* src = in + row * row_stride;
     double* dst = out + row * row_stride;
     const bool interior = (i0 - r >= 0) && (i0 + STILE + r <= n);
-    constexpr int NB = 8;                          // loads in flight per thread
+    constexpr int NB = 10;                         // loads in flight per thread (one batch covers radius <= 59)
     for (int k0 = 0; k0 < span; k0 += ST * NB) {
         double v[NB];
 #pragma unroll
@@ -80,14 +79,18 @@ __global__ void __launch_bounds__(ST_MAX) gauss_stream_kernel(const double* __re
     }
     for (int k = tid; k < ntap; k += ST) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
-        const double w = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
-        wA[k] = w;
-        wB[k] = w;
+        wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
     __syncthreads();
 
-    double acc[SR];
-    sshg::fir_window(xs + tid * SR, wA, wB, r, acc);
+    const double* xw = xs + tid * SR;              // window of this thread: xw[t], t = 0 .. 2r + SR - 1
+    double acc[SR], wr[SR];
+#pragma unroll
+    for (int q = 0; q < SR; ++q) {
+        acc[q] = 0.0;
+        wr[q] = wext[q];
+    }
+    sshg::fir_window(xw, wext, r, acc, wr);
     __syncthreads();                               // every window read is done: reuse xs for the results
 #pragma unroll
     for (int q = 0; q < SR; ++q) xs[tid * SR + q] = acc[q];
@@ -210,28 +213,13 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         ctx->tap_sigma = sigma;
         ctx->tap_ptr = dw;
     }
-    // CTA width for the streaming kernel: the multiple of 32 in [64, 256] that leaves the smallest ragged
-    // remainder in the last tile of a row (ties: the wider CTA, fewer halo re-reads)
-    int st = ST_MAX;
-    {
-        long long best = -1;
-        for (int t = 64; t <= ST_MAX; t += 32) {
-            const long long tile = (long long)t * SR;
-            const long long waste = (n + tile - 1) / tile * tile - n;
-            if (best < 0 || waste <= best) {
-                best = waste;
-                st = t;
-            }
-        }
-    }
-    const size_t smem_stream = (size_t)(stream_span(st, (int)r) + 2 * stream_ntap((int)r) + 2) * 8;
+    const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;
     if (elem_stride == 1 && smem_stream <= SMEM_CAP) {
-        const long long stile = (long long)st * SR;
-        const int tiles = (int)((n + stile - 1) / stile);
+        const int tiles = (int)((n + STILE - 1) / STILE);
         SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
         SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
-        gauss_stream_kernel<<<(unsigned)(rows * tiles), st, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n,
+        gauss_stream_kernel<<<(unsigned)(rows * tiles), ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n,
                                                                                       row_stride, (int)r, tiles);
     } else if (smem_tiled <= SMEM_CAP) {
         const int tiles = (int)((n + GTILE - 1) / GTILE);

@@ -61,7 +61,7 @@ extern "C" int hostmath_yield_points(const sshg_points* p, double* out) {
 // x: n samples, w: r + 1 taps (w[0] centre); out: n outputs with the 'reflect' boundary.
 extern "C" int hostmath_fir(const double* x, long long n, const double* w, int r, double* out) {
     const int SR = sshg::SR;
-    const int ntap = sshg::fir_ntap(r);
+    const int ntap = 2 * r + 1 + 3 * SR;
     std::vector<double> wext(ntap);
     for (int k = 0; k < ntap; ++k) {
         const int j = k - (SR - 1);
@@ -78,8 +78,12 @@ extern "C" int hostmath_fir(const double* x, long long n, const double* w, int r
             const long long i = base - r + t;
             xw[t] = (t < 2 * r + SR && i < n + r) ? x[reflect(i)] : 0.0;
         }
-        double acc[sshg::SR];
-        sshg::fir_window(xw.data(), wext.data(), wext.data(), r, acc);
+        double acc[sshg::SR], wr[sshg::SR];
+        for (int q = 0; q < SR; ++q) {
+            acc[q] = 0.0;
+            wr[q] = wext[q];
+        }
+        sshg::fir_window(xw.data(), wext.data(), r, acc, wr);
         for (int q = 0; q < SR && base + q < n; ++q) out[base + q] = acc[q];
     }
     return 0;

@@ -118,11 +118,10 @@ def test_switches(harness):
             assert ok, (sn, zq, mr, pol, msg)
 
 
-@pytest.mark.parametrize("sigma", [0.2, 0.6, 1.0, 1.4, 1.6, 1.9, 2.0, 2.2, 2.4, 2.7, 2.9, 3.2, 3.3, 3.6, 3.9, 4.1, 4.4, 5.0,
-                                   5.6, 6.1, 7.7, 12.0, 50.0])
+@pytest.mark.parametrize("sigma", [0.2, 0.6, 1.0, 2.0, 2.2, 2.3, 3.3, 4.4, 5.0, 5.6, 6.1, 7.7, 12.0, 50.0])
 def test_fir_window_arithmetic(harness, sigma):
     """The register-window FIR of K1 (sshg_fir.cuh), run on the CPU, against SciPy -- every value of
-    (2 radius) mod SR (radii 4 .. 18) and the short-kernel path; a NaN sample must not spread beyond the radius."""
+    (2 radius) mod 9 and the short-kernel path; a NaN sample must not spread beyond the radius."""
     from scipy import ndimage
     harness.hostmath_fir.restype = C.c_int
     harness.hostmath_fir.argtypes = [C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_void_p]

@@ -36,6 +36,7 @@ def timed(fn, reps, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--only-k1", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -43,7 +44,7 @@ def main():
     m1, m2, m3, chi2 = cases.si111_material()
 
     # ---- configs 3 and 4: Si(111) material, device resident; prep (K1, spline, rotate) timed apart -----
-    for tag, axes in (("config3", cases.config3_axes()), ("config4", cases.config4_axes())):
+    for tag, axes in (() if args.only_k1 else (("config3", cases.config3_axes()), ("config4", cases.config4_axes()))):
         t0 = time.perf_counter()
         eps1w, eps2w, chi_rot, thick = shg._prepare(axes["energy"], m1, m2, m3, chi2, axes["thick"], axes["gamma"], 0.0,
                                                     0.0, "3-layer")
@@ -68,7 +69,7 @@ def main():
     # ---- config-5 theta shards (what one of 8 / 4 ranks computes), both CTA sizes of K2 ----------------
     cfg = config5()
     dd = {k: put(v) for k, v in cfg.items()}
-    for nth in (23, 46):
+    for nth in (() if args.only_k1 else (23, 46)):
         out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
         for nt in ("128", "256", None):
             if nt is None:
@@ -93,6 +94,8 @@ def main():
                           "samples_per_s": n / (med * 1e-3), "rw_gbs": 16e-9 * n / (med * 1e-3),
                           "fp64_tflops": 2.0 * taps * n / (med * 1e-3) / 1e12}), flush=True)
     del slab
+    if args.only_k1:
+        return
 
     # ---- latency of the reference's own call shapes through the drop-in API (host in, host out) -------
     def wall(fn, reps=20):
