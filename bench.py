@@ -342,6 +342,19 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
     e2e_check = float(host_out[0, 0, :, 0, :].sum())
+    # the ceiling of the end-to-end leg: a plain device-to-pinned-host copy of the same bytes (PCIe)
+    probe = torch.empty(host_out.size, dtype=torch.float64, device=dev)
+    pin_t = torch.from_numpy(host_out.reshape(-1))
+    pcie_ms = []
+    for _ in range(3):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        pin_t.copy_(probe, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        pcie_ms.append(c0.elapsed_time(c1))
+    pcie_gbs = host_out.nbytes / (min(pcie_ms) * 1e-3) / 1e9
+    del probe
     h2d = sum(int(v.nbytes) for v in host_in.values())
     d2h = int(host_out.nbytes)
     e2e_pts = n_e2e * 4 * N_PHI * N_ENERGY
@@ -397,6 +410,9 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "sample": "sshg_yield with host buffers on the first %d thetas of each rank's shard "
                               "(%.3g points/step/GPU), pinned result buffer, %d steps" % (n_e2e, e2e_pts, e2e_steps),
+                    "d2h_gbs_achieved": d2h * e2e_steps / e2e_s / 1e9,
+                    "d2h_gbs_plain_copy": pcie_gbs,
+                    "bound": "PCIe device-to-host copy of the FP64 yields (rank 0's link; all ranks copy concurrently)",
                     "checksum": e2e_check},
             "gpu_launches": int(sum_launches),
             "clocks": clocks,

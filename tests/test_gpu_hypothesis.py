@@ -1,0 +1,74 @@
+"""Differential tests with generated inputs (hypothesis): random dielectric functions, chi2 tensors,
+angles and thicknesses through the CUDA kernels (C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import shg_oracle as orc
+from tests import cases, util
+
+pytestmark = pytest.mark.gpu
+CONSTS = util.load_consts()
+
+
+def _spectra(rng, nE):
+    energy = np.sort(rng.uniform(0.05, 9.0, nE))
+    eps1w = np.empty((3, nE), dtype=np.complex128)
+    eps2w = np.empty((3, nE), dtype=np.complex128)
+    eps1w[0] = eps2w[0] = 1.0
+    for m in (1, 2):
+        eps1w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(0.0, 25, nE)     # metals and dielectrics, Im >= 0
+        eps2w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(0.0, 25, nE)
+    chi = (rng.standard_normal((18, nE)) + 1j * rng.standard_normal((18, nE))) * 10.0 ** rng.uniform(-22, -17)
+    chi[rng.integers(0, 18, 4)] = 0.0                                             # some symmetry zeros
+    return energy, eps1w, eps2w, chi
+
+
+def _oracle(energy, eps1w, eps2w, chi, theta, phi, thick, **kw):
+    e1 = {"M%d" % (m + 1): eps1w[m] for m in range(3)}
+    e2 = {"M%d" % (m + 1): eps2w[m] for m in range(3)}
+    ch = {k: chi[i] for i, k in enumerate(cases.CHI2_KEYS)}
+    return orc.yield_points(energy, e1, e2, ch, theta, phi, thick, consts=CONSTS, **kw)
+
+
+@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 700), mref=st.booleans(), sn=st.booleans(), zq=st.booleans())
+def test_points_kernel_random(seed, n, mref, sn, zq):
+    from shgyield_b200 import shg
+    rng = np.random.default_rng(seed)
+    nE = int(rng.integers(1, 40))
+    energy, eps1w, eps2w, chi = _spectra(rng, nE)
+    eidx = rng.integers(0, nE, n)
+    theta, phi, thick = rng.uniform(0, 89.9, n), rng.uniform(-360, 720, n), rng.uniform(0, 120, n)
+    got = shg.yield_points(energy, eidx, theta, phi, thick, eps1w, eps2w, chi, mref=mref, consts=CONSTS,
+                           sinc_normalized=sn, zzz_phi_quirk=zq)
+    want = _oracle(energy[eidx], eps1w[:, eidx], eps2w[:, eidx], chi[:, eidx], theta, phi, thick, mref=mref,
+                   sinc_normalized=sn, zzz_phi_quirk=zq)
+    scale = max(np.max(np.abs(want[p])) for p in cases.POLS)
+    for k, pol in enumerate(cases.POLS):
+        ok, msg = cases.parity_ok(got[k], want[pol], rtol=1e-10, scale=scale)
+        assert ok, (seed, pol, msg)
+
+
+@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 1300), nT=st.integers(1, 5), nD=st.integers(1, 3),
+       grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]))
+def test_grid_kernel_random(seed, nE, nT, nD, grid_kind):
+    from shgyield_b200 import grid
+    rng = np.random.default_rng(seed)
+    energy, eps1w, eps2w, chi = _spectra(rng, nE)
+    theta = np.sort(rng.uniform(0, 90, nT))
+    thick = rng.uniform(0, 80, nD)
+    h = int(rng.integers(1, 9))
+    base = np.sort(rng.uniform(0, 180, h))
+    phi = {"paired": np.concatenate([base, base + 180.0]),
+           "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
+           "free": rng.uniform(0, 360, 2 * h + 1),
+           "single": np.array([rng.uniform(0, 360)])}[grid_kind]
+    got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS)
+    want = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
+    scale = max(np.max(np.abs(want[p])) for p in cases.POLS)
+    for k, pol in enumerate(cases.POLS):
+        w = np.broadcast_to(want[pol], (nT, nD, phi.size, nE))
+        ok, msg = cases.parity_ok(got[:, :, k], w, rtol=1e-10, scale=scale)
+        assert ok, (seed, grid_kind, pol, msg)
