@@ -135,7 +135,7 @@ def run_reference(args):
         return
     cores = cpu_cores()
     pool = CpuPool(cores)
-    tasks_per_step = cores
+    tasks_per_step = 4 * cores
     try:
         for w in range(args.warmup):
             pool.run(_cpu_tasks(tasks_per_step, w * tasks_per_step))

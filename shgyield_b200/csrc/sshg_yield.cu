@@ -21,11 +21,11 @@ using namespace sshg;
 
 namespace {
 
-constexpr int NT_BIG = 256;    // threads per CTA for large launches (512-energy tiles)
-constexpr int NT_SMALL = 128;  // ... and for launches of only a few waves (shorter tail)
+constexpr int NT_BIG = 256;    // threads per CTA when the column setup dominates (few phi rows per column)
+constexpr int NT_SMALL = 64;   // ... when the stores dominate: 128-energy tiles, up to 7 CTAs per SM
 constexpr int EPT = 2;         // energies per thread
 constexpr int CHUNK_BIG = 384;    // phi items per shared-memory table chunk (18 KB)
-constexpr int CHUNK_SMALL = 256;  // ... 12 KB, so that four 128-thread CTAs fit one SM
+constexpr int CHUNK_SMALL = 256;  // ... 12 KB for the 64-thread CTAs (32 KB of shared memory each)
 constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
 
 struct YieldArgs {
@@ -160,7 +160,7 @@ __device__ __forceinline__ cplx ldc(const double2* p) {
 }
 
 template <int NT, int CHUNK>
-__global__ void __launch_bounds__(NT, 512 / NT) yield_grid_kernel(const YieldArgs a) {
+__global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(const YieldArgs a) {
     extern __shared__ double smem[];
     double* tabs = smem;                        // [CHUNK][6]
     double* cols = smem + CHUNK * 6;            // [EPT][NCOL][NT]
@@ -407,17 +407,15 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     a.nDs = (int)(d1 - d0);
     a.t0 = (int)t0;
     a.d0 = (int)d0;
-    // CTA size: 256 threads unless the launch would be only a few waves, where 128-thread CTAs
-    // (half as long, twice as many) keep more SMs busy at the tail.  SSHG_K2_NT=128|256 overrides.
-    int nt = NT_BIG;
-    {
-        const int64_t ncol = (t1 - t0) * (d1 - d0);
-        const int64_t ctas_big = ncol * ((p->nE + NT_BIG * EPT - 1) / (NT_BIG * EPT));
-        if (ctas_big < 10LL * 2 * ctx->num_sms) nt = NT_SMALL;
-        if (const char* env = getenv("SSHG_K2_NT")) {
-            if (atoi(env) == NT_SMALL) nt = NT_SMALL;
-            else if (atoi(env) == NT_BIG) nt = NT_BIG;
-        }
+    // CTA size.  Store-dominated sweeps (many phi rows per column) run 64-thread CTAs: measured on
+    // config-5 shards they reach 0.95-0.97 of the HBM peak where 256-thread CTAs reach 0.89-0.92 (shorter
+    // tail, more CTAs to interleave), and they tie on the full cube.  Sweeps with few rows per column
+    // (config 4: P = 1) are bound by the column setup and run 256-thread CTAs (1.55 ms against 1.96 ms).
+    // SSHG_K2_NT=64|256 overrides (tuning).
+    int nt = (4 * p->nP >= 64) ? NT_SMALL : NT_BIG;
+    if (const char* env = getenv("SSHG_K2_NT")) {
+        if (atoi(env) == NT_SMALL) nt = NT_SMALL;
+        else if (atoi(env) == NT_BIG) nt = NT_BIG;
     }
     a.n_tiles = (int)((p->nE + nt * EPT - 1) / (nt * EPT));
     a.ph = make_physics(p->phys);
@@ -429,6 +427,7 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
                                    (int)grid_smem(NT_BIG, CHUNK_BIG)));
     SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
+
 
     auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
         YieldArgs b = a;

@@ -53,7 +53,7 @@ def main():
              put(eps1w), put(eps2w), put(chi_rot)]
         T, D, P, E = axes["theta"].size, axes["thick"].size, axes["phi"].size, axes["energy"].size
         out = torch.empty((T, D, 4, P, E), dtype=torch.float64, device=dev)
-        for nt in ("128", "256"):
+        for nt in ("64", "256"):
             os.environ["SSHG_K2_NT"] = nt
             med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
             print(json.dumps({"case": tag, "k2_threads": nt, "k2_ms_median": med, "k2_ms_best": best}), flush=True)
@@ -71,7 +71,7 @@ def main():
     dd = {k: put(v) for k, v in cfg.items()}
     for nth in (() if args.only_k1 else (23, 46)):
         out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
-        for nt in ("128", "256", None):
+        for nt in ("64", "256", None):
             if nt is None:
                 os.environ.pop("SSHG_K2_NT", None)
             else:
