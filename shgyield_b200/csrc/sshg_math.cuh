@@ -257,6 +257,119 @@ SSHG_HD void phi_basis_rad(double phi, double b[6]) {
 
 SSHG_HD void phi_basis(double phi_deg, double b[6]) { phi_basis_rad(phi_deg * (3.141592653589793 / 180.0), b); }
 
+// ---- sparse-phi form -------------------------------------------------------------------------
+// For sweeps with few azimuths per column (thickness / angle-of-incidence scans) the chi2 tensor is
+// contracted with the phi-dependent unit vectors FIRST, once per (energy, phi):
+//   r_pP = G_pP ( -A (a2 X0 + 2 ab X1 + b2 X2) + Bz (a2 X3 + 2 ab X4) + Q X5 )
+//   r_pS = G_pS (  a2 X6 + 2 ab X7 + b2 X8 )
+//   r_sP = G_sP ( -A X9 + Bz X10 )
+//   r_sS = G_sS X11
+// (the same 18/12/9/6 terms of shg.py:218-269, 290-313, 334-351, 372-377, grouped by their
+// theta/thickness-dependent factor), so a column costs 12 complex multiplies instead of the
+// 7-coefficient assembly per polarisation.
+constexpr int NX = 12;
+
+template <typename ChiFn>
+SSHG_HD void contract_phi(ChiFn chi, double s, double c, int zzz_phi_quirk, cplx X[NX]) {
+    const double c2 = c * c, sc = s * c, s2 = s * s;
+    const double c3 = c2 * c, sc2 = sc * c, s2c = sc * s, s3 = s2 * s;
+    X[0] = c3 * chi(XXX) + sc2 * (2.0 * chi(XXY) + chi(YXX)) + s2c * (chi(XYY) + 2.0 * chi(YXY)) + s3 * chi(YYY);
+    X[1] = c2 * chi(XXZ) + sc * (chi(XYZ) + chi(YXZ)) + s2 * chi(YYZ);
+    X[2] = c * chi(XZZ) + s * chi(YZZ);
+    X[3] = c2 * chi(ZXX) + (2.0 * sc) * chi(ZXY) + s2 * chi(ZYY);
+    X[4] = c * chi(ZXZ) + s * chi(ZYZ);
+    X[5] = zzz_phi_quirk ? s3 * chi(ZZZ) : chi(ZZZ);          // shg.py:269
+    X[6] = c3 * chi(YXX) + sc2 * (2.0 * chi(YXY) - chi(XXX)) + s2c * (chi(YYY) - 2.0 * chi(XXY)) - s3 * chi(XYY);
+    X[7] = c2 * chi(YXZ) + sc * (chi(YYZ) - chi(XXZ)) - s2 * chi(XYZ);
+    X[8] = c * chi(YZZ) - s * chi(XZZ);
+    X[9] = c3 * chi(XYY) + sc2 * (chi(YYY) - 2.0 * chi(XXY)) + s2c * (chi(XXX) - 2.0 * chi(YXY)) + s3 * chi(YXX);
+    X[10] = c2 * chi(ZYY) - (2.0 * sc) * chi(ZXY) + s2 * chi(ZXX);
+    X[11] = c3 * chi(YYY) - sc2 * (chi(XYY) + 2.0 * chi(YXY)) + s2c * (2.0 * chi(XXY) + chi(YXX)) - s3 * chi(XXX);
+}
+
+// The part of the column setup that does not depend on the thickness (shg.py:137-171 and the
+// prefactor): kept per (energy, theta) while a thread walks the thickness axis.
+struct ColumnStatic {
+    cplx R_p, R_s, P2p, P2s, W;        // 2w: r^{lb}, r^{vl} r^{lb} (p, s), wave vector in the layer
+    cplx r_p, r_s, P1p, P1s, w;        // 1w
+    cplx out_p, T_s, in_p, t_s, q;     // T_p / N_l, T_s, (t_p / n_l)^2, t_s, sqrt(prefactor) / n_l
+    double sin_t, s3;                  // sin(theta), sin^3(theta)
+};
+
+SSHG_HD ColumnStatic column_static(const cplx e1[3], const cplx e2[3], double energy, double sin_t, double cos_t,
+                                   const Physics& ph) {
+    const double s2 = sin_t * sin_t;
+    const Fresnel f1 = fresnel_set(e1[0], e1[1], e1[2], s2);
+    const Fresnel f2 = fresnel_set(e2[0], e2[1], e2[2], s2);
+    const cplx inl = crecip(csqrt_(e1[1]));
+    const cplx iNl = crecip(csqrt_(e2[1]));
+    ColumnStatic c;
+    c.R_p = f2.r_p_lb; c.R_s = f2.r_s_lb; c.P2p = f2.r_p_vl * f2.r_p_lb; c.P2s = f2.r_s_vl * f2.r_s_lb; c.W = f2.w_l;
+    c.r_p = f1.r_p_lb; c.r_s = f1.r_s_lb; c.P1p = f1.r_p_vl * f1.r_p_lb; c.P1s = f1.r_s_vl * f1.r_s_lb; c.w = f1.w_l;
+    c.out_p = f2.t_p * iNl;
+    c.T_s = f2.t_s;
+    c.in_p = csq(f1.t_p * inl);
+    c.t_s = f1.t_s;
+    c.q = ph.raw ? mk(1.0, 0.0) : (ph.pref * energy / fabs(cos_t)) * inl;
+    c.sin_t = sin_t;
+    c.s3 = sin_t * s2;
+    return c;
+}
+
+// The thickness-dependent part (shg.py:174-198) and the four yields of one azimuth from the
+// phi-contracted chi2.
+struct ColumnDynamic {
+    cplx Gpp, Gps, Gsp, Gss, A, Bz, Q, a2, ab2, b2;     // ab2 = 2 a b
+};
+
+SSHG_HD ColumnDynamic column_dynamic(const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+    cplx Rp = c.R_p, Rs = c.R_s, rp = c.r_p, rs = c.r_s;
+    if (ph.mref) {
+        const double PI = 3.141592653589793;
+        const double x = energy * thick * ph.kd;
+        const cplx hd = (4.0 * PI * x) * c.W;
+        const cplx eh = cexp_i(hd);
+        const cplx ed = csq(eh);
+        cplx arg = hd;
+        if (arg.re == 0.0 && arg.im == 0.0) arg = mk(1.0e-20, 0.0);
+        if (ph.sinc_normalized) arg = PI * arg;
+        const cplx snc = csin_(arg) / arg;
+        Rp = ((c.R_p * eh) / (1.0 + c.P2p * ed)) * snc;
+        Rs = ((c.R_s * eh) / (1.0 + c.P2s * ed)) * snc;
+        const cplx ev = cexp_i((4.0 * PI * x) * c.w);
+        rp = (c.r_p * ev) / (1.0 + c.P1p * ev);
+        rs = (c.r_s * ev) / (1.0 + c.P1s * ev);
+    }
+    const cplx out_s = c.T_s * (1.0 + Rs);
+    const cplx in_s = csq(c.t_s * (1.0 + rs));
+    ColumnDynamic d;
+    d.Gpp = c.q * (c.out_p * c.in_p);
+    d.Gps = c.q * (out_s * c.in_p);
+    d.Gsp = c.q * (c.out_p * in_s);
+    d.Gss = c.q * (out_s * in_s);
+    const cplx onepR = 1.0 + Rp, onepr = 1.0 + rp;
+    d.A = (1.0 - Rp) * c.W;
+    d.Bz = c.sin_t * onepR;
+    d.Q = ph.zzz_phi_quirk ? onepR * csq(onepr) : c.s3 * (onepR * csq(onepr));
+    const cplx a = (1.0 - rp) * c.w;
+    const cplx b = c.sin_t * onepr;
+    d.a2 = csq(a);
+    d.ab2 = 2.0 * (a * b);
+    d.b2 = csq(b);
+    return d;
+}
+
+SSHG_HD void sparse_yields(const ColumnDynamic& d, const cplx X[NX], double y[4]) {
+    const cplx pp = d.Gpp * (d.Bz * (d.a2 * X[3] + d.ab2 * X[4]) + d.Q * X[5] - d.A * (d.a2 * X[0] + d.ab2 * X[1] + d.b2 * X[2]));
+    const cplx ps = d.Gps * (d.a2 * X[6] + d.ab2 * X[7] + d.b2 * X[8]);
+    const cplx sp = d.Gsp * (d.Bz * X[10] - d.A * X[9]);
+    const cplx ss = d.Gss * X[11];
+    y[0] = fma(pp.re, pp.re, pp.im * pp.im);
+    y[1] = fma(ps.re, ps.re, ps.im * ps.im);
+    y[2] = fma(sp.re, sp.re, sp.im * sp.im);
+    y[3] = fma(ss.re, ss.re, ss.im * ss.im);
+}
+
 // ---- the reference's small helpers, one formula each (shg.py:137-198) -----------------------
 SSHG_HD cplx wvec_(cplx eps, double sin_t) { return csqrt_(mk(eps.re - sin_t * sin_t, eps.im)); }
 SSHG_HD cplx frefs_(cplx ei, cplx ej, double st) {

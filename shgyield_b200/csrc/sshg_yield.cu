@@ -269,6 +269,84 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
     }
 }
 
+// ---- sparse-phi sweeps (few azimuths per column: thickness / incidence-angle scans) ---------------
+// chi2 is contracted with the phi-dependent unit vectors once per (energy, phi) (`phi_contract_kernel`,
+// X[p][12][nE]); `yield_sparse_kernel` then gives one thread one energy and a run of consecutive
+// columns (theta-major, thickness fastest): the thickness-independent Fresnel factors are computed once
+// per (energy, theta) and only the exponentials / multiple-reflection coefficients per thickness.
+struct SparseArgs {
+    const double2* eps1w;
+    const double2* eps2w;
+    const double2* chi;
+    const double2* X;          // [nP][NX][nE]
+    const double* energy;
+    const double* theta_deg;
+    const double* thick_nm;
+    const double* phi_deg;
+    double* out;               // column col0 of the shard is at out[0]
+    long long nE, nP;
+    long long col0, ncols;     // columns of this launch (col = tl * nDs + dl)
+    int nDs, t0, d0;
+    int n_tiles, chunk;        // energies tiles of SNT threads; columns per CTA
+    Physics ph;
+};
+
+constexpr int SNT = 128;
+
+__global__ void phi_contract_kernel(const double2* __restrict__ chi, const double* __restrict__ phi_deg,
+                                    double2* __restrict__ X, long long nE, long long nP, int zzz_phi_quirk) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nE * nP) return;
+    const long long e = g % nE, p = g / nE;
+    double s, c;
+    sincos(phi_deg[p] * (3.141592653589793 / 180.0), &s, &c);
+    cplx x[NX];
+    contract_phi([&](int r) { return ldc(chi + r * nE + e); }, s, c, zzz_phi_quirk, x);
+#pragma unroll
+    for (int k = 0; k < NX; ++k) X[(p * NX + k) * nE + e] = make_double2(x[k].re, x[k].im);
+}
+
+__global__ void __launch_bounds__(SNT, 3) yield_sparse_kernel(const SparseArgs a) {
+    const long long blk = blockIdx.x;
+    const int tile = (int)(blk % a.n_tiles);
+    const long long chunk_id = blk / a.n_tiles;
+    const long long e = (long long)tile * SNT + threadIdx.x;
+    if (e >= a.nE) return;
+    const long long nE = a.nE;
+    const long long c_lo = a.col0 + chunk_id * a.chunk;
+    const long long c_hi = min(c_lo + a.chunk, a.col0 + a.ncols);
+    cplx e1[3], e2[3];
+#pragma unroll
+    for (int m = 0; m < 3; ++m) {
+        e1[m] = ldc(a.eps1w + m * nE + e);
+        e2[m] = ldc(a.eps2w + m * nE + e);
+    }
+    const double energy = a.energy[e];
+    const long long rows = 4 * a.nP * nE;                  // doubles per column
+    ColumnStatic cs;
+    int tl_cur = -1;
+    for (long long col = c_lo; col < c_hi; ++col) {
+        const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+        if (tl != tl_cur) {                                // new angle of incidence
+            double st, ct;
+            sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
+            cs = column_static(e1, e2, energy, st, ct, a.ph);
+            tl_cur = tl;
+        }
+        const ColumnDynamic cd = column_dynamic(cs, energy, a.thick_nm[a.d0 + dl], a.ph);
+        double* o = a.out + (col - a.col0) * rows + e;
+        for (long long p = 0; p < a.nP; ++p) {
+            cplx x[NX];
+#pragma unroll
+            for (int k = 0; k < NX; ++k) x[k] = ldc(a.X + (p * NX + k) * nE + e);
+            double y[4];
+            sparse_yields(cd, x, y);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) __stcs(o + (k * a.nP + p) * nE, y[k]);
+        }
+    }
+}
+
 // General NumPy-broadcast shape: one thread per point, all four polarisations.
 struct PointArgs {
     const double2* eps1w;
@@ -429,7 +507,43 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
                                    (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
 
 
+    // Sweeps with few azimuths per column go through the sparse-phi kernel (phi-contracted chi2,
+    // thickness loop inside the thread).  SSHG_K2_SPARSE=0|1 overrides (tests run both kernels).
+    bool sparse = 4 * p->nP < 64;
+    if (const char* env = getenv("SSHG_K2_SPARSE")) sparse = atoi(env) != 0;
+    SparseArgs sa{};
+    if (sparse) {
+        void* dX;
+        if (int rc = sshg_scratch(ctx, SCR_XPHI, (size_t)p->nP * NX * nE * 16, &dX)) return rc;
+        const long long tot = (long long)p->nP * p->nE;
+        phi_contract_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(a.chi, (const double*)dphi, (double2*)dX,
+                                                                                  p->nE, p->nP, a.ph.zzz_phi_quirk);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        sa.eps1w = a.eps1w; sa.eps2w = a.eps2w; sa.chi = a.chi; sa.X = (const double2*)dX;
+        sa.energy = a.energy; sa.theta_deg = a.theta_deg; sa.thick_nm = a.thick_nm; sa.phi_deg = (const double*)dphi;
+        sa.nE = p->nE; sa.nP = p->nP; sa.nDs = a.nDs; sa.t0 = a.t0; sa.d0 = a.d0;
+        sa.n_tiles = (int)((p->nE + SNT - 1) / SNT);
+        sa.ph = a.ph;
+    }
+
     auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
+        if (sparse) {
+            SparseArgs b = sa;
+            b.col0 = c0;
+            b.ncols = nc;
+            b.out = dst;
+            // columns per CTA: enough CTAs for ~8 waves of 3 CTAs per SM, at most 32 columns each
+            const long long want = 8LL * 3 * ctx->num_sms;
+            long long chunk = nc * b.n_tiles / want;
+            b.chunk = (int)(chunk < 1 ? 1 : (chunk > 32 ? 32 : chunk));
+            const long long n_chunks = (nc + b.chunk - 1) / b.chunk;
+            SSHG_REQUIRE(n_chunks * b.n_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
+            yield_sparse_kernel<<<(unsigned)(n_chunks * b.n_tiles), SNT, 0, st>>>(b);
+            SSHG_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return SSHG_OK;
+        }
         YieldArgs b = a;
         b.col0 = c0;
         b.out = dst;

@@ -88,3 +88,36 @@ extern "C" int hostmath_fir(const double* x, long long n, const double* w, int r
     }
     return 0;
 }
+
+// ---- sparse-phi form (contract_phi, column_static / column_dynamic, sparse_yields) on the CPU --------
+extern "C" int hostmath_sparse_points(const sshg_points* p, double* out) {
+    Physics ph;
+    ph.kd = 1e-9 / (p->phys.h_eVs * p->phys.c);
+    ph.pref = 100.0 / (p->phys.hbar_eVs * sqrt(2.0 * p->phys.eps0 * p->phys.c * p->phys.c * p->phys.c));
+    ph.mref = p->phys.mref;
+    ph.sinc_normalized = p->phys.sinc_normalized;
+    ph.zzz_phi_quirk = p->phys.zzz_phi_quirk;
+    ph.raw = 0;
+    ph.radians = 0;
+    const long long nE = p->nE, n = p->n;
+    for (long long i = 0; i < n; ++i) {
+        const long long e = p->eidx[i];
+        double st, ct, s, c;
+        sincos(p->theta_deg[i] * (3.141592653589793 / 180.0), &st, &ct);
+        sincos(p->phi_deg[i] * (3.141592653589793 / 180.0), &s, &c);
+        cplx e1[3], e2[3];
+        for (int m = 0; m < 3; ++m) {
+            e1[m] = mk(p->eps1w[2 * (m * nE + e)], p->eps1w[2 * (m * nE + e) + 1]);
+            e2[m] = mk(p->eps2w[2 * (m * nE + e)], p->eps2w[2 * (m * nE + e) + 1]);
+        }
+        auto chi = [&](int r) { return mk(p->chi2[2 * (r * nE + e)], p->chi2[2 * (r * nE + e) + 1]); };
+        cplx X[NX];
+        contract_phi(chi, s, c, ph.zzz_phi_quirk, X);
+        const ColumnStatic cs = column_static(e1, e2, p->energy_eV[e], st, ct, ph);
+        const ColumnDynamic cd = column_dynamic(cs, p->energy_eV[e], p->thick_nm[i], ph);
+        double y[4];
+        sparse_yields(cd, X, y);
+        for (int k = 0; k < 4; ++k) out[k * n + i] = y[k];
+    }
+    return 0;
+}

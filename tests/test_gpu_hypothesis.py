@@ -1,5 +1,7 @@
 """Differential tests with generated inputs (hypothesis): random dielectric functions, chi2 tensors,
 angles and thicknesses through the CUDA kernels (C ABI) against the CPU oracle."""
+import os
+
 import numpy as np
 import pytest
 from hypothesis import HealthCheck, given, settings, strategies as st
@@ -52,9 +54,19 @@ def test_points_kernel_random(seed, n, mref, sn, zq):
 
 @settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 1300), nT=st.integers(1, 5), nD=st.integers(1, 3),
-       grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]))
-def test_grid_kernel_random(seed, nE, nT, nD, grid_kind):
+       grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]),
+       kernel=st.sampled_from(["dense", "sparse"]))
+def test_grid_kernel_random(seed, nE, nT, nD, grid_kind, kernel):
+    import os
     from shgyield_b200 import grid
+    os.environ["SSHG_K2_SPARSE"] = "1" if kernel == "sparse" else "0"
+    try:
+        _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind)
+    finally:
+        os.environ.pop("SSHG_K2_SPARSE", None)
+
+
+def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind):
     rng = np.random.default_rng(seed)
     energy, eps1w, eps2w, chi = _spectra(rng, nE)
     theta = np.sort(rng.uniform(0, 90, nT))
@@ -71,4 +83,4 @@ def test_grid_kernel_random(seed, nE, nT, nD, grid_kind):
     for k, pol in enumerate(cases.POLS):
         w = np.broadcast_to(want[pol], (nT, nD, phi.size, nE))
         ok, msg = cases.parity_ok(got[:, :, k], w, rtol=1e-10, scale=scale)
-        assert ok, (seed, grid_kind, pol, msg)
+        assert ok, (seed, grid_kind, os.environ.get("SSHG_K2_SPARSE"), pol, msg)

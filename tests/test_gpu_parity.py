@@ -174,8 +174,12 @@ GRID_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", ["auto", "dense", "sparse"])
 @pytest.mark.parametrize("nE,theta,phi,thick", GRID_SHAPES, ids=[str(i) for i in range(len(GRID_SHAPES))])
-def test_grid_kernel_matches_oracle(grid, consts, nE, theta, phi, thick):
+def test_grid_kernel_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, thick, kernel):
+    """Every shape through the dense (harmonic, phi-pair) kernel and the sparse-phi kernel."""
+    if kernel != "auto":
+        monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
     cfg = _small_cfg(nE, theta, phi, thick)
     got = grid.yield_grid_host(**cfg, consts=consts)
     want = _oracle_cube(cfg, consts)
@@ -185,8 +189,10 @@ def test_grid_kernel_matches_oracle(grid, consts, nE, theta, phi, thick):
         assert ok, (pol, msg)
 
 
+@pytest.mark.parametrize("kernel", ["dense", "sparse"])
 @pytest.mark.parametrize("kw", [dict(mref=False), dict(sinc_normalized=False), dict(zzz_phi_quirk=False)])
-def test_grid_kernel_switches(grid, consts, kw):
+def test_grid_kernel_switches(grid, consts, monkeypatch, kw, kernel):
+    monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
     cfg = _small_cfg(200, [15.0, 70.0], np.arange(0, 360, 20.0), [10.0, 55.0], seed=4)
     got = grid.yield_grid_host(**cfg, consts=consts, **kw)
     want = _oracle_cube(cfg, consts, **kw)
@@ -195,8 +201,10 @@ def test_grid_kernel_switches(grid, consts, kw):
         assert ok, (kw, pol, msg)
 
 
-def test_grid_shards_are_bitwise_slices(grid, consts):
+@pytest.mark.parametrize("kernel", ["dense", "sparse"])
+def test_grid_shards_are_bitwise_slices(grid, consts, monkeypatch, kernel):
     """Sharding changes no arithmetic: every shard equals the slice of the full cube bit for bit."""
+    monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
     cfg = _small_cfg(300, np.linspace(0, 90, 11), np.arange(0, 360, 10.0), [4.0, 9.0, 14.0], seed=2)
     full = grid.yield_grid_host(**cfg, consts=consts)
     for world in (2, 4, 8):

@@ -34,13 +34,14 @@ def harness():
         subprocess.run([nvcc, "-O2", "-std=c++17", "-w", "-Xcompiler", "-fPIC", "-shared",
                         "-I", os.path.join(util.REPO, "include"), "-o", so, src], check=True)
     lib = C.CDLL(so)
-    lib.hostmath_yield_points.restype = C.c_int
-    lib.hostmath_yield_points.argtypes = [C.POINTER(_lib.Points), C.c_void_p]
+    for fn in (lib.hostmath_yield_points, lib.hostmath_sparse_points):
+        fn.restype = C.c_int
+        fn.argtypes = [C.POINTER(_lib.Points), C.c_void_p]
     return lib
 
 
 def run_points(lib, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, mref=True,
-               sinc_normalized=True, zzz_phi_quirk=True):
+               sinc_normalized=True, zzz_phi_quirk=True, sparse=False):
     n = eidx.size
     arrs = dict(energy=np.ascontiguousarray(energy, dtype=np.float64),
                 eidx=np.ascontiguousarray(eidx, dtype=np.int64),
@@ -57,17 +58,20 @@ def run_points(lib, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, 
                     phys=_lib.Physics(consts["h_eVs"], consts["hbar_eVs"], consts["eps0"], consts["c"],
                                       int(mref), int(sinc_normalized), int(zzz_phi_quirk), 0))
     out = np.empty((4, n))
-    assert lib.hostmath_yield_points(C.byref(p), out.ctypes.data) == 0
+    fn = lib.hostmath_sparse_points if sparse else lib.hostmath_yield_points
+    assert fn(C.byref(p), out.ctypes.data) == 0
     return out
 
 
-def test_config5_samples(harness):
+@pytest.mark.parametrize("sparse", [False, True], ids=["harmonic", "sparse"])
+def test_config5_samples(harness, sparse):
     consts = util.load_consts()
     z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_grid_samples.npz"))
     idx = z["c5_idx"]
     energy, eps1w, eps2w, chi = synthetic_spectra(20000)
     theta, phi = np.linspace(0.0, 90.0, 181), np.linspace(0.0, 360.0, 721)
-    out = run_points(harness, energy, idx[:, 3], theta[idx[:, 0]], phi[idx[:, 2]], 10.0, eps1w, eps2w, chi, consts)
+    out = run_points(harness, energy, idx[:, 3], theta[idx[:, 0]], phi[idx[:, 2]], 10.0, eps1w, eps2w, chi, consts,
+                     sparse=sparse)
     sc = cases.case_scale(z, "c5_")
     for i, pol in enumerate(cases.POLS):
         ok, msg = cases.parity_ok(out[i], z["c5_" + pol], rtol=1e-10, scale=sc)
@@ -112,10 +116,11 @@ def test_switches(harness):
     ch = {k: chi[i][eidx] for i, k in enumerate(cases.CHI2_KEYS)}
     for sn, zq, mr in ((False, True, True), (True, False, True), (True, True, False), (False, False, False)):
         want = orc.yield_points(energy[eidx], e1, e2, ch, theta, phi, thick, mr, consts, sn, zq)
-        out = run_points(harness, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, mr, sn, zq)
-        for i, pol in enumerate(cases.POLS):
-            ok, msg = cases.parity_ok(out[i], want[pol], rtol=1e-10)
-            assert ok, (sn, zq, mr, pol, msg)
+        for sparse in (False, True):
+            out = run_points(harness, energy, eidx, theta, phi, thick, eps1w, eps2w, chi, consts, mr, sn, zq, sparse)
+            for i, pol in enumerate(cases.POLS):
+                ok, msg = cases.parity_ok(out[i], want[pol], rtol=1e-10)
+                assert ok, (sn, zq, mr, sparse, pol, msg)
 
 
 @pytest.mark.parametrize("sigma", [0.2, 0.6, 1.0, 2.0, 2.2, 2.3, 3.3, 4.4, 5.0, 5.6, 6.1, 7.7, 12.0, 50.0])
