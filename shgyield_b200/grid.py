@@ -158,7 +158,7 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
             cube = _gauss_axis(_lib.context(), cube, sigma_out, cube.ndim - 1)
     res = {"energy": energy, "theta": theta, "phi": phi, "thick": thick, "cube": cube}
     for k, pol in enumerate(POLS):
-        res[pol] = cube[:, :, k]
+        res[pol] = cube[:, :, k] if cube is not None else None     # gather: only rank 0 holds the cube
     return res
 
 

@@ -34,6 +34,34 @@ def main():
         ok = ok and gathered is None
     everywhere = grid.gather_slabs(slab, 11, 1, (rank, world, "theta"), all_ranks=True)
     ok = ok and bool(torch.equal(everywhere, full_local))
+    # thickness sharding (fewer thetas than ranks): slabs are strided slices of the cube
+    cfg2 = config5(n_energy=200, n_theta=1, n_phi=5)
+    thick = np.linspace(1.0, 40.0, 9)
+    d2 = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg2.items()}
+    d2["thick"] = torch.from_numpy(thick).to(dev)
+    args2 = (d2["energy"], d2["theta"], d2["phi"], d2["thick"], d2["eps1w"], d2["eps2w"], d2["chi2"])
+    assert grid.choose_shard_axis(1, 9, world) == "thick"
+    lo2, hi2 = grid.shard_bounds(9, world, rank)
+    slab2 = grid.yield_grid_device(*args2, consts=consts, d_range=(lo2, hi2))
+    full2 = grid.yield_grid_device(*args2, consts=consts)
+    torch.cuda.synchronize()
+    ok = ok and bool(torch.equal(slab2, full2[:, lo2:hi2]))
+    g2 = grid.gather_slabs(slab2, 1, 9, (rank, world, "thick"), all_ranks=True)
+    ok = ok and bool(torch.equal(g2, full2))
+
+    # the public sweep entry point with the reference's material arguments, sharded + gathered
+    from tests import cases
+    m1, m2, m3, chi2 = cases.si111_material()
+    kw = dict(energy=np.linspace(0.5, 5.0, 300), eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2,
+              theta=np.linspace(10, 80, 9), phi=np.arange(0, 360, 30.0), thick=[10.0], gamma=0, sigma_out=2.0)
+    whole = grid.shgyield_grid(**kw)["cube"]
+    part = grid.shgyield_grid(shard=(rank, world), gather=True, **kw)["cube"]
+    torch.cuda.synchronize()
+    if rank == 0:
+        ok = ok and bool(torch.equal(part, whole))
+    else:
+        ok = ok and part is None
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
