@@ -19,8 +19,11 @@ def _spectra(rng, nE):
     eps2w = np.empty((3, nE), dtype=np.complex128)
     eps1w[0] = eps2w[0] = 1.0
     for m in (1, 2):
-        eps1w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(0.0, 25, nE)     # metals and dielectrics, Im >= 0
-        eps2w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(0.0, 25, nE)
+        # metals and dielectrics; a slightly negative Im (what broadening / splines can produce) exercises
+        # the other side of the square-root branch cut
+        eps1w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(-0.3, 25, nE)
+        eps2w[m] = rng.uniform(-20, 30, nE) + 1j * rng.uniform(-0.3, 25, nE)
+        eps1w[m][rng.integers(0, nE)] = rng.uniform(-20, 30) + 0j              # purely real (signed zero)
     chi = (rng.standard_normal((18, nE)) + 1j * rng.standard_normal((18, nE))) * 10.0 ** rng.uniform(-22, -17)
     chi[rng.integers(0, 18, 4)] = 0.0                                             # some symmetry zeros
     return energy, eps1w, eps2w, chi

@@ -377,3 +377,11 @@ def test_config5_full_size_in_slabs(grid, consts):
         assert bool(torch.isfinite(view).all())
     assert seen == idx_all.shape[0]
     assert float(out[180 - 176].abs().max()) == 0.0          # theta = 90 deg: exactly zero (w_v = 0)
+    # linearity: r is linear in chi2, so doubling chi2 (exact in binary FP) quadruples every yield bit for bit
+    grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                           out=out, consts=consts, t_range=(40, 40 + step))
+    out2 = torch.empty_like(out)
+    grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], 2.0 * d["chi2"],
+                           out=out2, consts=consts, t_range=(40, 40 + step))
+    torch.cuda.synchronize()
+    assert bool(torch.equal(out2, 4.0 * out))
