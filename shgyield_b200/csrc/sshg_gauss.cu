@@ -104,6 +104,111 @@ __global__ void __launch_bounds__(ST) gauss_stream_kernel(const double* __restri
     }
 }
 
+// ---- contiguous rows, common radii: taps as kernel parameters ----------------------------------
+// For the radii that sigma = 1, 1.5, 2, ... produce (even radii 4 .. 24, 28, 32, 40; the reference's
+// default sigma_out = 5 gives 20) the radius is a template parameter and the RAD + 1 distinct taps
+// travel as a by-value kernel argument, i.e. in the constant bank: every tap is an immediate
+// constant-bank operand of its DFMA, no tap is loaded or held in a register, and the whole window
+// (2 RAD + FR steps x up to FR outputs) is straight-line code.  That removes a quarter of the
+// shared-memory wavefronts of the generic kernel and frees the registers for FR = 13 outputs per
+// thread, which moves the kernel from shared-memory bound to FP64 bound.
+constexpr int FR = 13;              // outputs per thread (odd: conflict-free stride)
+constexpr int FT_MAX = 256;         // threads per CTA: 64 .. 256, chosen per launch (smallest ragged remainder)
+
+template <int RAD>
+struct FixedTaps {
+    double w[RAD + 1];              // w[0] centre
+};
+
+template <int RAD>
+__global__ void __launch_bounds__(FT_MAX) gauss_fixed_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                             const FixedTaps<RAD> taps, long long n,
+                                                             long long row_stride, int tiles_per_row) {
+    extern __shared__ double sm[];
+    const int FTN = blockDim.x;
+    const int tile_n = FTN * FR;
+    const int used = tile_n + 2 * RAD;             // samples that feed an output of this tile
+    double* xs = sm;
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.x / tiles_per_row;
+    const long long i0 = (long long)(blockIdx.x % tiles_per_row) * tile_n;
+    const double* src = in + row * row_stride;
+    double* dst = out + row * row_stride;
+    const bool interior = (i0 - RAD >= 0) && (i0 + tile_n + RAD <= n);
+    constexpr int NB = 8;                          // loads in flight per thread
+    for (int k0 = 0; k0 < used; k0 += FTN * NB) {
+        double v[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * FTN + tid;
+            v[b] = 0.0;
+            if (k < used) {
+                const long long i = i0 - RAD + k;
+                if (interior || (i >= 0 && i < n)) v[b] = src[i];
+                else if (i < n + RAD) v[b] = src[reflect(i, n)];
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int k = k0 + b * FTN + tid;
+            if (k < used) xs[k] = v[b];
+        }
+    }
+    __syncthreads();
+
+    const double* xw = xs + tid * FR;              // xw[t] = x[o0 - RAD + t], o0 = first output of this thread
+    double acc[FR];
+#pragma unroll
+    for (int q = 0; q < FR; ++q) acc[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 2 * RAD + FR; ++t) {
+        const double v = xw[t];
+#pragma unroll
+        for (int q = 0; q < FR; ++q) {
+            const int j = t - q;                   // tap index 0 .. 2 RAD of the full kernel; absent taps are skipped
+            if (j >= 0 && j <= 2 * RAD) acc[q] = fma(taps.w[j <= RAD ? RAD - j : j - RAD], v, acc[q]);
+        }
+    }
+    __syncthreads();                               // every window read is done: reuse xs for the results
+#pragma unroll
+    for (int q = 0; q < FR; ++q) xs[tid * FR + q] = acc[q];
+    __syncthreads();
+    if (i0 + tile_n <= n) {
+#pragma unroll
+        for (int k = 0; k < FR; ++k) dst[i0 + k * FTN + tid] = xs[k * FTN + tid];
+    } else {
+        for (int k = tid; k < tile_n; k += FTN)
+            if (i0 + k < n) dst[i0 + k] = xs[k];
+    }
+}
+
+template <int RAD>
+int launch_fixed(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
+                 const double* w_host) {
+    FixedTaps<RAD> taps;
+    for (int k = 0; k <= RAD; ++k) taps.w[k] = w_host[k];
+    // CTA width: the multiple of 32 in [64, 256] that leaves the smallest ragged remainder in the last tile
+    int ft = FT_MAX;
+    long long best = -1;
+    for (int t = 64; t <= FT_MAX; t += 32) {
+        const long long tile = (long long)t * FR;
+        const long long waste = (n + tile - 1) / tile * tile - n;
+        if (best < 0 || waste <= best) {
+            best = waste;
+            ft = t;
+        }
+    }
+    const long long tile = (long long)ft * FR;
+    const long long tiles = (n + tile - 1) / tile;
+    SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
+    const size_t smem = (size_t)(tile + 2 * RAD) * 8;
+    SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    gauss_fixed_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return SSHG_OK;
+}
+
 // ---- strided rows: SciPy-order tiled kernel -------------------------------------------------------
 constexpr int GT = 256;          // threads per CTA
 constexpr int GPT = 4;           // outputs per thread
@@ -206,12 +311,22 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         w[0] = 1.0;
         sum += 1.0;
         for (long long k = 0; k <= r; ++k) w[k] /= sum;
+        for (long long k = 0; k <= r && k < SSHG_TAP_HOST; ++k) ctx->tap_host[k] = w[k];
         // pageable source: the runtime copies it to a staging buffer before returning
         cudaError_t e = cudaMemcpyAsync(dw, w, (size_t)(r + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);
         free(w);
         if (e != cudaSuccess) return sshg_cuda_fail(e, "tap upload", __FILE__, __LINE__);
         ctx->tap_sigma = sigma;
         ctx->tap_ptr = dw;
+    }
+    if (elem_stride == 1 && !getenv("SSHG_K1_GENERIC")) {
+        switch (r) {                               // radii with a compile-time specialisation
+#define SSHG_FIXED(R_) case R_: return launch_fixed<R_>(ctx, din, dout, rows, n, row_stride, ctx->tap_host);
+            SSHG_FIXED(4) SSHG_FIXED(6) SSHG_FIXED(8) SSHG_FIXED(10) SSHG_FIXED(12) SSHG_FIXED(14) SSHG_FIXED(16)
+            SSHG_FIXED(18) SSHG_FIXED(20) SSHG_FIXED(22) SSHG_FIXED(24) SSHG_FIXED(28) SSHG_FIXED(32) SSHG_FIXED(40)
+#undef SSHG_FIXED
+            default: break;
+        }
     }
     const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;

@@ -6,6 +6,7 @@
 #include "../../include/sshg.h"
 
 #define SSHG_NSCRATCH 24
+#define SSHG_TAP_HOST 64
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
 #define SCR_SPLFAC 17    // spline elimination coefficients of the last axis (cached)
 #define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel
@@ -22,6 +23,7 @@ struct sshg_ctx {
     int64_t launches;
     double tap_sigma;           // sigma whose taps are in scratch[SCR_TAPS] (tap_ptr guards reallocation)
     void* tap_ptr;
+    double tap_host[SSHG_TAP_HOST];   // host copy of the first taps (kernel arguments of the fixed-radius K1)
     uint64_t spl_hash;          // axis whose spline factorisation is in scratch[SCR_SPLFAC] (0: none)
     int64_t spl_n;
     void* spl_ptr;

@@ -45,8 +45,10 @@ def test_scipy_constants_match_fixture(shg, consts):
 
 # ---- K1: Gaussian broadening vs the live SciPy ---------------------------------------------------
 @pytest.mark.parametrize("n", [1, 2, 7, 126, 1024, 1025, 2001, 20000])
-@pytest.mark.parametrize("sigma", [0.0, 0.2, 3.3, 5.0, 50.0])
+@pytest.mark.parametrize("sigma", [0.0, 0.2, 1.0, 2.0, 3.3, 3.5, 5.0, 6.0, 7.0, 8.0, 10.0, 50.0])
 def test_gauss_matches_scipy(shg, n, sigma):
+    """radius = int(4 sigma + 0.5): even radii 4..24, 28, 32, 40 take the fixed-radius kernel (taps in the
+    constant bank), the others the generic register-window kernel."""
     from scipy import ndimage
     x = np.random.default_rng(n).normal(size=n)
     got = shg.broad(x, sigma)
@@ -65,6 +67,23 @@ def test_gauss_huge_radius_and_nd(shg):
     z = np.random.default_rng(3).normal(size=40) + 1j * np.random.default_rng(4).normal(size=40)
     want = ndimage.gaussian_filter(z.real, 2.5) + 1j * ndimage.gaussian_filter(z.imag, 2.5)
     np.testing.assert_allclose(shg.broadC(z, 2.5), want, rtol=0, atol=1e-14)
+
+
+@pytest.mark.parametrize("sigma", [2.0, 3.3, 5.0, 10.0])
+def test_gauss_nan_stays_within_the_radius(shg, sigma):
+    """An Inf/NaN sample poisons exactly the outputs within the radius, as in SciPy (taps that do not
+    exist are skipped, not multiplied by zero); rows are independent."""
+    from scipy import ndimage
+    r = int(4 * sigma + 0.5)
+    x = np.random.default_rng(3).normal(size=(3, 4000))
+    x[1, 1700] = np.nan
+    x[2, 5] = np.inf
+    got, want = shg.broad(x, sigma), np.stack([ndimage.gaussian_filter(row, sigma) for row in x])
+    got1 = np.stack([shg.broad(row, sigma) for row in x])           # 1-D calls: the energy axis only
+    assert np.array_equal(np.isnan(got1[1]), np.abs(np.arange(4000) - 1700) <= r)
+    assert np.array_equal(np.isfinite(got1), np.isfinite(want))
+    np.testing.assert_allclose(got1[0], want[0], rtol=0, atol=1e-14)
+    assert got.shape == x.shape
 
 
 def test_gauss_matches_oracle_restatement(shg):
