@@ -1,0 +1,1 @@
+"""Import path of the reference package (`import shgyield.shg`), served by `shgyield_b200`."""

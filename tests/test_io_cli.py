@@ -85,3 +85,26 @@ def test_cli_reproduces_reference_golden(example_dir):
     np.testing.assert_allclose(got[0], gold["energy"], atol=5e-5)
     for col, pol in zip(got[1:], ("pp", "sp", "ps", "ss")):
         np.testing.assert_allclose(col, gold[pol], rtol=1e-5)        # text inputs carry 7 digits
+
+
+@pytest.mark.gpu
+def test_cli_sweep_writes_cube(example_dir):
+    """theta / phi given as lists -> a sweep on the GPU, written as .npz; one column must equal the
+    scalar run of the same input (sigma_out broadens along the energy axis only)."""
+    import subprocess
+    import yaml
+    src = os.path.join(example_dir, "si111-input.yml")
+    doc = yaml.safe_load(open(src))
+    doc["parameters"]["theta"] = [55, 65]
+    doc["parameters"]["phi"] = [0, 30, 90]
+    swp = os.path.join(example_dir, "sweep.yml")
+    yaml.safe_dump(doc, open(swp, "w"))
+    out = os.path.join(example_dir, "sweep.npz")
+    subprocess.run([sys.executable, os.path.join(util.REPO, "shgyield.py"), swp, "-o", out], check=True)
+    z = np.load(out)
+    assert z["pp"].shape == (2, 1, 3, 126)
+    one = os.path.join(example_dir, "one.dat")
+    subprocess.run([sys.executable, os.path.join(util.REPO, "shgyield.py"), src, "-o", one], check=True)
+    col = np.loadtxt(one, unpack=True)
+    for k, pol in zip((1, 2, 3, 4), ("pp", "sp", "ps", "ss")):
+        np.testing.assert_allclose(z[pol][1, 0, 1], col[k], rtol=2e-8)       # text output keeps 9 digits
