@@ -326,9 +326,16 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
         else:
             y = np.empty((4, 0))
         res = [y[k].reshape(shape) for k in range(4)]
+    # output broadening (reference shg.py:433-436): the four arrays are filtered together, one K1 launch
+    # per axis of the result (scalar sigma blurs every axis, like scipy's gaussian_filter)
+    stack = np.ascontiguousarray(np.stack([np.asarray(r, dtype=np.float64) for r in res]))       # [4, *shape]
+    if float(sigma_out) > 1e-15 and stack.ndim > 1 and stack.size:
+        ctx = _lib.context()
+        for ax in range(1, stack.ndim):
+            stack = _gauss_axis(ctx, stack, float(sigma_out), ax)
     out = {"energy": energy, "phi": phi}
     for k, pol in enumerate(POLS):
-        out[pol] = broad(res[k], sigma_out)
+        out[pol] = np.array(stack[k])             # own array per polarisation (0-d stays a 0-d ndarray)
     return out
 
 
