@@ -9,7 +9,7 @@
 #define SSHG_TAP_HOST 64
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
 #define SCR_SPLFAC 17    // spline elimination coefficients of the last axis (cached)
-#define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel
+#define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel (slot 19: thickness-axis info)
 #define SCR_BROAD 16     // broadened rows handed from K1 to the spline kernels
 
 struct sshg_ctx {

@@ -322,23 +322,81 @@ struct ColumnDynamic {
     cplx Gpp, Gps, Gsp, Gss, A, Bz, Q, a2, ab2, b2;     // ab2 = 2 a b
 };
 
-SSHG_HD ColumnDynamic column_dynamic(const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+// The three thickness-dependent phase factors of a column (shg.py:180-183, 193-195):
+//   eh = e^{i delta/2}, ev = e^{i varphi}, snc = sinc(delta/2) in the reference's (np.sinc) convention.
+struct Phases {
+    cplx eh, ev, snc;
+};
+
+SSHG_HD cplx sinc_arg(const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+    const double PI = 3.141592653589793;
+    cplx arg = (4.0 * PI * (energy * thick * ph.kd)) * c.W;      // delta / 2
+    if (arg.re == 0.0 && arg.im == 0.0) arg = mk(1.0e-20, 0.0);  // np.sinc: 0 -> 1e-20
+    return ph.sinc_normalized ? PI * arg : arg;
+}
+
+SSHG_HD Phases phases_exact(const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+    const double PI = 3.141592653589793;
+    const double x = energy * thick * ph.kd;
+    Phases p;
+    p.eh = cexp_i((4.0 * PI * x) * c.W);
+    p.ev = cexp_i((4.0 * PI * x) * c.w);
+    const cplx arg = sinc_arg(c, energy, thick, ph);
+    p.snc = csin_(arg) / arg;
+    return p;
+}
+
+// Uniform thickness grids: the three exponentials e^{i delta/2}, e^{i varphi}, e^{i arg} advance by a
+// constant complex factor per step, so a run of columns needs one complex multiply each instead of
+// sincos + exp; sin(arg) = (e^{i arg} - e^{-i arg}) / 2i.  The run is re-seeded exactly at its first
+// column (<= 32 steps: accumulated error ~1e-14), and |arg| < 0.5, where that difference cancels,
+// takes the direct complex sine.
+struct PhaseWalk {
+    cplx eh, ev, ep;      // current exponentials
+    cplx sh, sv, sp;      // per-step factors
+};
+
+SSHG_HD void walk_seed(PhaseWalk& w, const ColumnStatic& c, double energy, double thick, double dstep, const Physics& ph) {
+    const double PI = 3.141592653589793;
+    const double k = 4.0 * PI * energy * ph.kd;
+    const double ks = ph.sinc_normalized ? PI * k : k;
+    w.eh = cexp_i((k * thick) * c.W);
+    w.ev = cexp_i((k * thick) * c.w);
+    w.ep = cexp_i((ks * thick) * c.W);
+    w.sh = cexp_i((k * dstep) * c.W);
+    w.sv = cexp_i((k * dstep) * c.w);
+    w.sp = cexp_i((ks * dstep) * c.W);
+}
+
+SSHG_HD void walk_advance(PhaseWalk& w) {
+    w.eh = w.eh * w.sh;
+    w.ev = w.ev * w.sv;
+    w.ep = w.ep * w.sp;
+}
+
+SSHG_HD Phases walk_phases(const PhaseWalk& w, const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+    Phases p;
+    p.eh = w.eh;
+    p.ev = w.ev;
+    const cplx arg = sinc_arg(c, energy, thick, ph);
+    if (arg.re * arg.re + arg.im * arg.im < 0.25) {
+        p.snc = csin_(arg) / arg;
+    } else {
+        const cplx em = crecip(w.ep);
+        const cplx diff = w.ep - em;                             // 2i sin(arg)
+        p.snc = mk(0.5 * diff.im, -0.5 * diff.re) / arg;
+    }
+    return p;
+}
+
+SSHG_HD ColumnDynamic column_from_phases(const ColumnStatic& c, const Phases& f, const Physics& ph) {
     cplx Rp = c.R_p, Rs = c.R_s, rp = c.r_p, rs = c.r_s;
     if (ph.mref) {
-        const double PI = 3.141592653589793;
-        const double x = energy * thick * ph.kd;
-        const cplx hd = (4.0 * PI * x) * c.W;
-        const cplx eh = cexp_i(hd);
-        const cplx ed = csq(eh);
-        cplx arg = hd;
-        if (arg.re == 0.0 && arg.im == 0.0) arg = mk(1.0e-20, 0.0);
-        if (ph.sinc_normalized) arg = PI * arg;
-        const cplx snc = csin_(arg) / arg;
-        Rp = ((c.R_p * eh) / (1.0 + c.P2p * ed)) * snc;
-        Rs = ((c.R_s * eh) / (1.0 + c.P2s * ed)) * snc;
-        const cplx ev = cexp_i((4.0 * PI * x) * c.w);
-        rp = (c.r_p * ev) / (1.0 + c.P1p * ev);
-        rs = (c.r_s * ev) / (1.0 + c.P1s * ev);
+        const cplx ed = csq(f.eh);
+        Rp = ((c.R_p * f.eh) / (1.0 + c.P2p * ed)) * f.snc;
+        Rs = ((c.R_s * f.eh) / (1.0 + c.P2s * ed)) * f.snc;
+        rp = (c.r_p * f.ev) / (1.0 + c.P1p * f.ev);
+        rs = (c.r_s * f.ev) / (1.0 + c.P1s * f.ev);
     }
     const cplx out_s = c.T_s * (1.0 + Rs);
     const cplx in_s = csq(c.t_s * (1.0 + rs));
@@ -357,6 +415,12 @@ SSHG_HD ColumnDynamic column_dynamic(const ColumnStatic& c, double energy, doubl
     d.ab2 = 2.0 * (a * b);
     d.b2 = csq(b);
     return d;
+}
+
+SSHG_HD ColumnDynamic column_dynamic(const ColumnStatic& c, double energy, double thick, const Physics& ph) {
+    Phases f{};
+    if (ph.mref) f = phases_exact(c, energy, thick, ph);
+    return column_from_phases(c, f, ph);
 }
 
 SSHG_HD void sparse_yields(const ColumnDynamic& d, const cplx X[NX], double y[4]) {

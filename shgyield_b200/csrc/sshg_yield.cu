@@ -288,10 +288,39 @@ struct SparseArgs {
     long long col0, ncols;     // columns of this launch (col = tl * nDs + dl)
     int nDs, t0, d0;
     int n_tiles, chunk;        // energies tiles of SNT threads; columns per CTA
+    const double* dinfo;       // [2]: {1.0 if thick_nm is uniformly spaced, its step} (thick_uniform_kernel)
     Physics ph;
 };
 
 constexpr int SNT = 128;
+
+// Is the thickness axis uniformly spaced?  (Decided on the device so that device-resident inputs need
+// no host round trip.)  info[0] = 1.0 / 0.0, info[1] = step.
+__global__ void thick_uniform_kernel(const double* __restrict__ thick, long long nD, double* __restrict__ info,
+                                     int allow) {
+    __shared__ int bad;
+    __shared__ double scale_s;
+    if (threadIdx.x == 0) {
+        bad = (allow && nD >= 3) ? 0 : 1;
+        double sc = 0.0;
+        for (long long k = 0; k < nD; ++k) sc = fmax(sc, fabs(thick[k]));
+        scale_s = sc;
+    }
+    __syncthreads();
+    const double d0 = thick[0];
+    const double step = nD > 1 ? (thick[nD - 1] - d0) / (double)(nD - 1) : 0.0;
+    if (!bad) {
+        int mybad = (step == 0.0 || !isfinite(step)) ? 1 : 0;
+        for (long long k = threadIdx.x; k < nD; k += blockDim.x)
+            if (!(fabs(thick[k] - (d0 + step * (double)k)) <= 1e-13 * scale_s)) mybad = 1;
+        if (mybad) bad = 1;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        info[0] = bad ? 0.0 : 1.0;
+        info[1] = step;
+    }
+}
 
 __global__ void phi_contract_kernel(const double2* __restrict__ chi, const double* __restrict__ phi_deg,
                                     double2* __restrict__ X, long long nE, long long nP, int zzz_phi_quirk) {
@@ -324,16 +353,28 @@ __global__ void __launch_bounds__(SNT, 3) yield_sparse_kernel(const SparseArgs a
     const double energy = a.energy[e];
     const long long rows = 4 * a.nP * nE;                  // doubles per column
     ColumnStatic cs;
+    PhaseWalk walk;
+    const bool recur = a.dinfo[0] != 0.0 && a.ph.mref;
+    const double d_step = a.dinfo[1];
     int tl_cur = -1;
     for (long long col = c_lo; col < c_hi; ++col) {
         const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
-        if (tl != tl_cur) {                                // new angle of incidence
+        const double thick = a.thick_nm[a.d0 + dl];
+        const bool fresh = tl != tl_cur;
+        if (fresh) {                                       // new angle of incidence
             double st, ct;
             sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
             cs = column_static(e1, e2, energy, st, ct, a.ph);
             tl_cur = tl;
         }
-        const ColumnDynamic cd = column_dynamic(cs, energy, a.thick_nm[a.d0 + dl], a.ph);
+        ColumnDynamic cd;
+        if (recur) {
+            if (fresh) walk_seed(walk, cs, energy, thick, d_step, a.ph);     // exact at the first column of a run
+            else walk_advance(walk);
+            cd = column_from_phases(cs, walk_phases(walk, cs, energy, thick, a.ph), a.ph);
+        } else {
+            cd = column_dynamic(cs, energy, thick, a.ph);
+        }
         double* o = a.out + (col - a.col0) * rows + e;
         for (long long p = 0; p < a.nP; ++p) {
             cplx x[NX];
@@ -525,6 +566,14 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
         sa.nE = p->nE; sa.nP = p->nP; sa.nDs = a.nDs; sa.t0 = a.t0; sa.d0 = a.d0;
         sa.n_tiles = (int)((p->nE + SNT - 1) / SNT);
         sa.ph = a.ph;
+        // uniformly spaced thicknesses -> phase factors by recurrence (SSHG_K2_NO_RECURRENCE disables)
+        void* dinfo;
+        if (int rc = sshg_scratch(ctx, SCR_XPHI + 1, 16, &dinfo)) return rc;
+        thick_uniform_kernel<<<1, 256, 0, ctx->stream>>>(a.thick_nm, p->nD, (double*)dinfo,
+                                                       getenv("SSHG_K2_NO_RECURRENCE") ? 0 : 1);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        sa.dinfo = (const double*)dinfo;
     }
 
     auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {

@@ -121,3 +121,42 @@ extern "C" int hostmath_sparse_points(const sshg_points* p, double* out) {
     }
     return 0;
 }
+
+// ---- uniform thickness grids: phase factors by recurrence (PhaseWalk) on the CPU ---------------------
+// One (energy column e, theta, phi); thick = d0 + k * dstep, k < nd; out[pol][k].
+extern "C" int hostmath_sparse_walk(const sshg_points* p, long long e, double theta_deg, double phi_deg, double d0,
+                                    double dstep, long long nd, double* out) {
+    Physics ph;
+    ph.kd = 1e-9 / (p->phys.h_eVs * p->phys.c);
+    ph.pref = 100.0 / (p->phys.hbar_eVs * sqrt(2.0 * p->phys.eps0 * p->phys.c * p->phys.c * p->phys.c));
+    ph.mref = p->phys.mref;
+    ph.sinc_normalized = p->phys.sinc_normalized;
+    ph.zzz_phi_quirk = p->phys.zzz_phi_quirk;
+    ph.raw = 0;
+    ph.radians = 0;
+    const long long nE = p->nE;
+    double st, ct, s, c;
+    sincos(theta_deg * (3.141592653589793 / 180.0), &st, &ct);
+    sincos(phi_deg * (3.141592653589793 / 180.0), &s, &c);
+    cplx e1[3], e2[3];
+    for (int m = 0; m < 3; ++m) {
+        e1[m] = mk(p->eps1w[2 * (m * nE + e)], p->eps1w[2 * (m * nE + e) + 1]);
+        e2[m] = mk(p->eps2w[2 * (m * nE + e)], p->eps2w[2 * (m * nE + e) + 1]);
+    }
+    auto chi = [&](int r) { return mk(p->chi2[2 * (r * nE + e)], p->chi2[2 * (r * nE + e) + 1]); };
+    cplx X[NX];
+    contract_phi(chi, s, c, ph.zzz_phi_quirk, X);
+    const double energy = p->energy_eV[e];
+    const ColumnStatic cs = column_static(e1, e2, energy, st, ct, ph);
+    PhaseWalk w;
+    for (long long k = 0; k < nd; ++k) {
+        const double thick = d0 + dstep * (double)k;
+        if (k % 32 == 0) walk_seed(w, cs, energy, thick, dstep, ph);     // a run of the kernel is at most 32 columns
+        else walk_advance(w);
+        const ColumnDynamic cd = column_from_phases(cs, walk_phases(w, cs, energy, thick, ph), ph);
+        double y[4];
+        sparse_yields(cd, X, y);
+        for (int q = 0; q < 4; ++q) out[q * nd + k] = y[q];
+    }
+    return 0;
+}

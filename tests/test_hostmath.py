@@ -144,3 +144,29 @@ def test_fir_window_arithmetic(harness, sigma):
     harness.hostmath_fir(x.ctypes.data, 300, taps.ctypes.data, r, out.ctypes.data)
     bad = np.isnan(out)
     assert np.array_equal(bad, np.abs(np.arange(300) - 150) <= r)
+
+
+@pytest.mark.parametrize("sn", [True, False])
+def test_phase_recurrence_on_uniform_thickness_grids(harness, sn):
+    """PhaseWalk (exponentials advanced by a constant factor, sin from their difference, direct sine for
+    small arguments) against the oracle on thickness grids from 0 / 1e-6 nm upwards."""
+    consts = util.load_consts()
+    harness.hostmath_sparse_walk.restype = C.c_int
+    harness.hostmath_sparse_walk.argtypes = [C.POINTER(_lib.Points), C.c_longlong, C.c_double, C.c_double, C.c_double,
+                                             C.c_double, C.c_longlong, C.c_void_p]
+    energy, eps1w, eps2w, chi = synthetic_spectra(12, seed=5)
+    arrs = [np.ascontiguousarray(a) for a in (energy, eps1w, eps2w, chi)]
+    p = _lib.Points(n=1, nE=12, energy_eV=arrs[0].ctypes.data, eidx=0, theta_deg=0, phi_deg=0, thick_nm=0,
+                    eps1w=arrs[1].ctypes.data, eps2w=arrs[2].ctypes.data, chi2=arrs[3].ctypes.data,
+                    phys=_lib.Physics(consts["h_eVs"], consts["hbar_eVs"], consts["eps0"], consts["c"], 1, int(sn), 1, 0))
+    for e, theta, phi, d0, step, nd in ((0, 65.0, 30.0, 1.0, 1.0, 100), (5, 20.0, 200.0, 0.0, 0.37, 257),
+                                        (11, 80.0, 10.0, 1e-6, 2.5e-3, 64), (3, 45.0, 123.0, 500.0, -4.0, 100)):
+        out = np.empty((4, nd))
+        assert harness.hostmath_sparse_walk(C.byref(p), e, theta, phi, d0, step, nd, out.ctypes.data) == 0
+        thick = d0 + step * np.arange(nd)
+        e1 = {"M%d" % (m + 1): eps1w[m][e] for m in range(3)}
+        e2 = {"M%d" % (m + 1): eps2w[m][e] for m in range(3)}
+        ch = {k: chi[i][e] for i, k in enumerate(cases.CHI2_KEYS)}
+        want = orc.yield_points(energy[e], e1, e2, ch, theta, phi, thick, True, consts, sn, True)
+        for i, pol in enumerate(cases.POLS):
+            np.testing.assert_allclose(out[i], want[pol], rtol=2e-12, atol=0, err_msg="%s e=%d" % (pol, e))
