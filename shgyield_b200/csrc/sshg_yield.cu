@@ -335,7 +335,10 @@ __global__ void phi_contract_kernel(const double2* __restrict__ chi, const doubl
     for (int k = 0; k < NX; ++k) X[(p * NX + k) * nE + e] = make_double2(x[k].re, x[k].im);
 }
 
-__global__ void __launch_bounds__(SNT, 3) yield_sparse_kernel(const SparseArgs a) {
+#ifndef SSHG_SPARSE_MINB
+#define SSHG_SPARSE_MINB 3
+#endif
+__global__ void __launch_bounds__(SNT, SSHG_SPARSE_MINB) yield_sparse_kernel(const SparseArgs a) {
     const long long blk = blockIdx.x;
     const int tile = (int)(blk % a.n_tiles);
     const long long chunk_id = blk / a.n_tiles;
