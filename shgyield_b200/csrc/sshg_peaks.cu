@@ -5,10 +5,19 @@
 
 namespace {
 
+// Each warp writes 4 consecutive 512-byte runs per iteration (the access pattern of the yield kernel:
+// st.global.cs.v2.f64, a warp covers 512 contiguous bytes per store).
 __global__ void __launch_bounds__(256) store_kernel(double2* __restrict__ p, long long n2, double v) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride)
-        __stcs(p + i, make_double2(v, v + (double)(i & 7)));
+    const long long stride = (long long)gridDim.x * blockDim.x * 4;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    for (long long i = warp * 128 + lane; i < n2; i += stride) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long j = i + 32 * k;
+            if (j < n2) __stcs(p + j, make_double2(v, v + (double)k));
+        }
+    }
 }
 
 constexpr int DFMA_ILP = 8;
@@ -45,7 +54,7 @@ extern "C" int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* 
     cudaEventCreate(&t0);
     cudaEventCreate(&t1);
     const long long n2 = bytes / 16;
-    const int grid = ctx->num_sms * 8;
+    const int grid = ctx->num_sms * 16;
     float best = 1e30f;
     for (int it = 0; it < iters + 2; ++it) {
         cudaEventRecord(t0, ctx->stream);
