@@ -22,7 +22,6 @@ ABI_VERSION = 1
 FLAG_RADIANS = 1
 
 c_double_p = C.POINTER(C.c_double)
-c_int64_p = C.POINTER(C.c_int64)
 
 
 class Physics(C.Structure):
@@ -113,21 +112,6 @@ def check(rc: int, lib=None):
     if rc == SSHG_ENOMEM:
         raise MemoryError(msg)
     raise RuntimeError(msg)
-
-
-def ptr(a) -> int:
-    """Address of a C-contiguous NumPy array, a torch tensor, or an int (device pointer)."""
-    if a is None:
-        return 0
-    if isinstance(a, int):
-        return a
-    if isinstance(a, np.ndarray):
-        if not a.flags["C_CONTIGUOUS"]:
-            raise ValueError("array must be C-contiguous")
-        return a.ctypes.data
-    if hasattr(a, "data_ptr"):
-        return a.data_ptr()
-    raise TypeError("cannot take the address of %r" % type(a))
 
 
 class Context:
