@@ -404,3 +404,27 @@ def test_config5_full_size_in_slabs(grid, consts):
                            out=out2, consts=consts, t_range=(40, 40 + step))
     torch.cuda.synchronize()
     assert bool(torch.equal(out2, 4.0 * out))
+
+
+def test_config5_full_theta_rows_vs_oracle(grid, consts):
+    """Two complete theta rows of the 20k x 181 x 721 cube (2 x 57.7 M points, every phi and energy)
+    against the CPU oracle, not just sampled points."""
+    import torch
+    from shgyield_b200.synthetic import config5
+    cfg = config5()
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg.items()}
+    e1 = {"M%d" % (m + 1): cfg["eps1w"][m] for m in range(3)}
+    e2 = {"M%d" % (m + 1): cfg["eps2w"][m] for m in range(3)}
+    ch = {k: cfg["chi2"][i] for i, k in enumerate(cases.CHI2_KEYS)}
+    for it in (65, 179):                                     # 32.5 deg and 89.5 deg (grazing: huge prefactor)
+        got = grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                                     consts=consts, t_range=(it, it + 1)).cpu().numpy()[0, 0]      # [4, P, E]
+        worst = 0.0
+        for p0 in range(0, 721, 103):
+            phi = cfg["phi"][p0:p0 + 103]
+            want = orc.yield_points(cfg["energy"], e1, e2, ch, cfg["theta"][it], phi[:, None], 10.0, True, consts)
+            for k, pol in enumerate(cases.POLS):
+                a, b = got[k, p0:p0 + 103], want[pol]
+                worst = max(worst, float(np.max(np.abs(a - b)) / np.max(b)))
+        assert worst < 1e-12, (it, worst)
