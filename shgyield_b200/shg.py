@@ -280,6 +280,52 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
     return eps1w, eps2w, chi_rot, thick
 
 
+# ---------------------------------------------------------------------------------------------
+# Optional reuse of the prepared spectra between calls.  The reference re-runs broadening, splines and
+# the rotation on every call and lists "avoid running unless changed" as a to-do (shg.py:11-12); its GUI
+# calls shgyield() twice per slider tick with the same material.  Opt-in, because a cache keyed on object
+# identity cannot see arrays that are modified in place.
+# ---------------------------------------------------------------------------------------------
+_PREPARE_CACHE = None           # None: off; else an OrderedDict
+_PREPARE_CACHE_SIZE = 8
+
+
+def cache_prepared(enable: bool = True, size: int = 8):
+    """Keep the broadened / resampled / averaged / rotated spectra of the last `size` distinct
+    (material objects, energy values, gamma, sigma_eps, sigma_chi, mode) combinations, so that calls
+    that only change theta / phi / thick / sigma_out / mref skip K1, the splines and the rotation.
+    The material dicts are held (by reference) while cached; arrays modified IN PLACE are not noticed
+    -- call cache_prepared(False) or pass new objects."""
+    global _PREPARE_CACHE, _PREPARE_CACHE_SIZE
+    from collections import OrderedDict
+    _PREPARE_CACHE = OrderedDict() if enable else None
+    _PREPARE_CACHE_SIZE = max(1, int(size))
+
+
+def _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode):
+    if _PREPARE_CACHE is None:
+        return _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode)
+    try:
+        key = (id(eps_m1), id(eps_m2), id(eps_m3), id(chi2), e_arr.shape, e_arr.tobytes(), float(gamma),
+               float(sigma_eps), float(sigma_chi), str(mode))
+    except (TypeError, ValueError):
+        return _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode)
+    hit = _PREPARE_CACHE.get(key)
+    if hit is None:
+        eps1w, eps2w, chi_rot, thick_eff = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
+                                                    sigma_chi, mode)
+        # the references keep the ids in the key alive and unique
+        _PREPARE_CACHE[key] = (eps1w, eps2w, chi_rot, (eps_m1, eps_m2, eps_m3, chi2))
+        while len(_PREPARE_CACHE) > _PREPARE_CACHE_SIZE:
+            _PREPARE_CACHE.popitem(last=False)
+        return eps1w, eps2w, chi_rot, thick_eff
+    _PREPARE_CACHE.move_to_end(key)
+    eps1w, eps2w, chi_rot, _ = hit
+    if mode in ("fresnel", "2-layer"):
+        thick = 0                                   # reference shg.py:414
+    return eps1w, eps2w, chi_rot, thick
+
+
 def _axes_of(shape, ndim):
     """Axes (in the ndim-dimensional broadcast result) along which an operand of `shape` varies."""
     pad = (1,) * (ndim - len(shape)) + tuple(shape)
@@ -296,8 +342,8 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     """
     consts = physical_constants()
     e_arr = np.asarray(energy, dtype=np.float64)
-    eps1w, eps2w, chi_rot, thick = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
-                                            sigma_chi, mode)
+    eps1w, eps2w, chi_rot, thick = _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
+                                                   sigma_chi, mode)
     t_arr, p_arr, d_arr = (np.asarray(v, dtype=np.float64) for v in (theta, phi, thick))
     shape = np.broadcast_shapes(e_arr.shape, t_arr.shape, p_arr.shape, d_arr.shape)
     ndim = len(shape)

@@ -428,3 +428,39 @@ def test_config5_full_theta_rows_vs_oracle(grid, consts):
                 a, b = got[k, p0:p0 + 103], want[pol]
                 worst = max(worst, float(np.max(np.abs(a - b)) / np.max(b)))
         assert worst < 1e-12, (it, worst)
+
+
+def test_prepared_cache_is_transparent(shg, spectra):
+    """cache_prepared(): same results bit for bit, a hit when only angles / thickness / sigma_out change,
+    a miss when sigma_eps, gamma, the energies or the material objects change."""
+    m1, m2, m3, chi2 = cases.full_tensor_material(spectra)
+    kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, thick=10, gamma=25, sigma_eps=2.0, sigma_chi=1.0)
+    base = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)
+    other = shg.shgyield(cases.E_C1, theta=40, phi=np.arange(0.0, 360.0, 45.0).reshape(8, 1), sigma_out=0.0, **kw)
+    ctx_launches = lambda: __import__("shgyield_b200._lib", fromlist=["x"]).context().launches
+    shg.cache_prepared(True)
+    try:
+        a = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)            # miss: fills the cache
+        n0 = ctx_launches()
+        b = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)            # hit
+        n1 = ctx_launches()
+        c = shg.shgyield(cases.E_C1, theta=40, phi=np.arange(0.0, 360.0, 45.0).reshape(8, 1), sigma_out=0.0, **kw)
+        assert n1 - n0 == 2                                                          # yield kernel + output FIR only
+        for pol in cases.POLS:
+            assert np.array_equal(a[pol], base[pol]) and np.array_equal(b[pol], base[pol])
+            assert np.array_equal(c[pol], other[pol])
+        assert len(shg._PREPARE_CACHE) == 1
+        shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, sigma_eps=3.0))
+        shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, gamma=26))
+        shg.shgyield(cases.E_C1[:-1], theta=65, phi=30, sigma_out=5, **kw)
+        shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, chi2=dict(chi2)))
+        assert len(shg._PREPARE_CACHE) == 5
+        f = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
+        g = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
+        for pol in cases.POLS:
+            assert np.array_equal(f[pol], g[pol])
+    finally:
+        shg.cache_prepared(False)
+    f0 = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
+    for pol in cases.POLS:
+        assert np.array_equal(f[pol], f0[pol])
