@@ -153,6 +153,13 @@ SSHG_API int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const double*
  * contraction + |Gamma r|^2 (shg.py:137-378, 428-436).  */
 SSHG_API int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where);
 SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
+/* The same sweep with the output broadening of shgyield() (broad(., sigma_out) on every yield spectrum,
+ * shg.py:26-28, 433-436; sigma_out in SAMPLES of the energy axis, 5.0 is the reference's default):
+ * out[t][d][pol][p][:] = gaussian_filter(yield[t][d][pol][p][:], sigma_out) with scipy.ndimage's taps,
+ * radius int(4 sigma + 0.5) and 'reflect' boundary.  Dense sweeps are broadened inside the yield kernel
+ * (the FIR is applied to the 13 azimuthal harmonics of a column before the phi sweep), so the
+ * cube is written once; sigma_out = 0 is sshg_yield. */
+SSHG_API int sshg_yield_broadened(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where);
 
 /* ---- the reference's public helper functions, element-wise over n values ------------------
  * kind: wvec (shg.py:137-141, epsj unused), frefs / frefp (144-156), ftrans / ftranp (159-171);

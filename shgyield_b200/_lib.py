@@ -67,6 +67,7 @@ SYMBOLS = {
     "sshg_broaden_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double,
                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "sshg_yield": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_void_p, C.c_int]),
+    "sshg_yield_broadened": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_double, C.c_void_p, C.c_int]),
     "sshg_yield_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
     "sshg_fresnel": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "sshg_multiref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

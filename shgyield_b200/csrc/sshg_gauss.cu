@@ -280,6 +280,19 @@ constexpr size_t SMEM_CAP = 200 * 1024;
 
 }  // namespace
 
+// scipy _gaussian_kernel1d: exp(-0.5 / sigma^2 * x^2), normalised by the sum over -r..r
+void sshg_gaussian_taps(double sigma, long long r, double* w) {
+    const double f = -0.5 / (sigma * sigma);
+    double sum = 0.0;
+    for (long long k = r; k >= 1; --k) {
+        w[k] = exp(f * (double)(k * k));
+        sum += 2.0 * w[k];
+    }
+    w[0] = 1.0;
+    sum += 1.0;
+    for (long long k = 0; k <= r; ++k) w[k] /= sum;
+}
+
 // Device-level filter: din / dout are device pointers; queued on ctx->stream.
 int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                       int64_t elem_stride, double sigma) {
@@ -301,16 +314,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
             sshg_set_error("out of host memory");
             return SSHG_ENOMEM;
         }
-        // scipy _gaussian_kernel1d: exp(-0.5 / sigma^2 * x^2), normalised by the sum over -r..r
-        const double f = -0.5 / (sigma * sigma);
-        double sum = 0.0;
-        for (long long k = r; k >= 1; --k) {
-            w[k] = exp(f * (double)(k * k));
-            sum += 2.0 * w[k];
-        }
-        w[0] = 1.0;
-        sum += 1.0;
-        for (long long k = 0; k <= r; ++k) w[k] /= sum;
+        sshg_gaussian_taps(sigma, r, w);
         for (long long k = 0; k <= r && k < SSHG_TAP_HOST; ++k) ctx->tap_host[k] = w[k];
         // pageable source: the runtime copies it to a staging buffer before returning
         cudaError_t e = cudaMemcpyAsync(dw, w, (size_t)(r + 1) * 8, cudaMemcpyHostToDevice, ctx->stream);

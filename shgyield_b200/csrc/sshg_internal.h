@@ -56,6 +56,9 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
 int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
                        int64_t nq, double* dout, int* dflag, uint64_t axis_hash);
 
+// scipy _gaussian_kernel1d on the host: w[k] = exp(-k^2 / (2 sigma^2)) / sum over -r..r, k = 0..r (w[0] centre)
+void sshg_gaussian_taps(double sigma, long long r, double* w);
+
 // Copies a host array to a scratch slot (or passes a device pointer through).
 int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device,
                   const void** dev);

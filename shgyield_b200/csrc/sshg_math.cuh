@@ -257,6 +257,97 @@ SSHG_HD void phi_basis_rad(double phi, double b[6]) {
 
 SSHG_HD void phi_basis(double phi_deg, double b[6]) { phi_basis_rad(phi_deg * (3.141592653589793 / 180.0), b); }
 
+// ---- harmonic form of the yield (fused output broadening, K3) --------------------------------------
+// |r(phi)|^2 of a 7-term r is a real trigonometric polynomial of degree 6:
+//   y(phi) = C0 + sum_{q=1..6} (C_q cos(q phi) + S_q sin(q phi)).
+// The Gaussian broadening of the yields along the energy axis (broad(., sigma_out), shg.py:26-28,
+// 433-436) is linear, so it commutes with this expansion: broadening the 13 coefficient spectra of a
+// (theta, thickness) column once replaces broadening every one of its phi rows.
+//
+// With r = sum_{n=-3..3} rho_n e^{i n phi}:  y = sum_q Y_q e^{i q phi},  Y_q = sum_n rho_n conj(rho_{n-q}),
+// Y_{-q} = conj(Y_q), hence C0 = Y_0, C_q = 2 Re Y_q, S_q = -2 Im Y_q.
+//
+// Layout of H[13] (and of a phi-table item, without the leading 1):
+//   H[0] = C0 | H[1..6] = C2 S2 C4 S4 C6 S6 (even under phi -> phi + 180 deg) | H[7..12] = C1 S1 C3 S3 C5 S5 (odd).
+constexpr int NH = 13;
+constexpr int NH_SS = 7;      // sS has odd rho only: q = 0, 2, 4, 6
+
+// F-basis coefficients k[7] (see `fold`) -> rho[n + 3], n = -3..3:
+//   c^2 = (1 + cos 2phi)/2, s c = sin 2phi / 2, c^3 = (3 cos phi + cos 3phi)/4, s c^2 = (sin phi + sin 3phi)/4,
+//   s^2 c = (cos phi - cos 3phi)/4, s^3 = (3 sin phi - sin 3phi)/4.
+SSHG_HD void rho_from_coeffs(const cplx k[7], cplx rho[7]) {
+    const cplx a0 = k[0] + 0.5 * k[1];
+    const cplx a2 = 0.5 * k[1], b2 = 0.5 * k[2];
+    const cplx a1 = 0.25 * (3.0 * k[3] + k[5]), b1 = 0.25 * (k[4] + 3.0 * k[6]);
+    const cplx a3 = 0.25 * (k[3] - k[5]), b3 = 0.25 * (k[4] - k[6]);
+    // alpha cos + beta sin = (alpha - i beta)/2 e^{+i n phi} + (alpha + i beta)/2 e^{-i n phi}
+    rho[3] = a0;
+    rho[4] = mk(0.5 * (a1.re + b1.im), 0.5 * (a1.im - b1.re));
+    rho[2] = mk(0.5 * (a1.re - b1.im), 0.5 * (a1.im + b1.re));
+    rho[5] = mk(0.5 * (a2.re + b2.im), 0.5 * (a2.im - b2.re));
+    rho[1] = mk(0.5 * (a2.re - b2.im), 0.5 * (a2.im + b2.re));
+    rho[6] = mk(0.5 * (a3.re + b3.im), 0.5 * (a3.im - b3.re));
+    rho[0] = mk(0.5 * (a3.re - b3.im), 0.5 * (a3.im + b3.re));
+}
+
+// ODD_ONLY: rho_0 = rho_{+-2} = 0 (sS); only H[0..6] are written.
+template <bool ODD_ONLY>
+SSHG_HD void harmonics_from_rho(const cplx rho[7], double* H) {
+#pragma unroll
+    for (int q = 0; q <= 6; ++q) {
+        if (ODD_ONLY && (q & 1)) continue;
+        double re = 0.0, im = 0.0;
+#pragma unroll
+        for (int n = q - 3; n <= 3; ++n) {
+            if (ODD_ONLY && !(n & 1)) continue;
+            const cplx a = rho[n + 3], b = rho[n - q + 3];
+            re = fma(a.re, b.re, fma(a.im, b.im, re));
+            if (q) im = fma(a.im, b.re, fma(-a.re, b.im, im));
+        }
+        if (q == 0) H[0] = re;
+        else if (q & 1) { H[q + 6] = 2.0 * re; H[q + 7] = -2.0 * im; }
+        else { H[q - 1] = 2.0 * re; H[q] = -2.0 * im; }
+    }
+}
+
+SSHG_HD void harmonics7(const cplx k[7], double H[NH]) {
+    cplx rho[7];
+    rho_from_coeffs(k, rho);
+    harmonics_from_rho<false>(rho, H);
+}
+
+// sS: k[0..3] multiply {c^3, s c^2, s^2 c, s^3}
+SSHG_HD void harmonics4(const cplx k[4], double H[NH_SS]) {
+    const cplx zero = mk(0.0, 0.0);
+    const cplx k7[7] = {zero, zero, zero, k[0], k[1], k[2], k[3]};
+    cplx rho[7];
+    rho_from_coeffs(k7, rho);
+    harmonics_from_rho<true>(rho, H);
+}
+
+// phi-table item of the harmonic form: t[0..5] = cos/sin of 2, 4, 6 phi; t[6..11] = cos/sin of 1, 3, 5 phi.
+SSHG_HD void phi_harmonics(double phi_deg, double t[12]) {
+#pragma unroll
+    for (int q = 1; q <= 6; ++q) {
+        double s, c;
+        sincospi(fmod((double)q * phi_deg, 360.0) / 180.0, &s, &c);
+        const int j = (q & 1) ? q + 5 : q - 2;
+        t[j] = c;
+        t[j + 1] = s;
+    }
+}
+
+SSHG_HD double harmonic_yield(const double* H, const double t[12], bool odd_only) {
+    double ye = H[0];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) ye = fma(H[1 + j], t[j], ye);
+    if (odd_only) return ye;
+    double yo = H[7] * t[6];
+#pragma unroll
+    for (int j = 1; j < 6; ++j) yo = fma(H[7 + j], t[6 + j], yo);
+    return ye + yo;
+}
+
 // ---- sparse-phi form -------------------------------------------------------------------------
 // For sweeps with few azimuths per column (thickness / angle-of-incidence scans) the chi2 tensor is
 // contracted with the phi-dependent unit vectors FIRST, once per (energy, phi):

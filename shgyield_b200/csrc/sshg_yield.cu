@@ -15,6 +15,7 @@
 #include "sshg_internal.h"
 #include "sshg_math.cuh"
 
+#include <math.h>
 #include <stdlib.h>
 
 using namespace sshg;
@@ -269,6 +270,251 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
     }
 }
 
+// ---- K3: the yield cube broadened along the energy axis (sigma_out > 0), in ONE pass --------------------
+// The reference broadens every yield spectrum after the fact (broad(., sigma_out), shg.py:26-28, 433-436;
+// sigma_out = 5 is the API default).  Done literally on a cube that is a second pass over HBM (read 8 B +
+// write 8 B per point) and 2 radius + 1 FMAs per point -- 3.7x the cost of K2.  Here the broadening is
+// moved in front of the azimuthal sweep instead: |r(phi)|^2 is a trigonometric polynomial of degree 6 in
+// phi (sshg_math.cuh::harmonics7), the Gaussian FIR along E is linear, so it is applied to the 13 (sS: 7)
+// harmonic spectra of a column -- 46 FIRs per (theta, d) column instead of 4 nP -- and each point is then
+// a 13-term real sum.  Per point that is 7 FP64 instructions (sS: 3) against 10 (5) in K2, so the broadened
+// cube is again bound by its 8 B/point store stream.
+//
+// A CTA of NT threads owns 2 NT consecutive energies of a column.  (A) it evaluates column setup +
+// coefficients + harmonics for those energies plus a halo of `radius` on each side ('reflect' boundary of
+// scipy.ndimage at the ends of the axis) into shared memory, raw[46][S]; (B) per polarisation every
+// thread filters the harmonic spectra for its two energies into registers (one LDS.128 feeds 4 FMAs) and
+// (C) sweeps the azimuth, phi / phi + 180 deg pairs sharing the even and odd harmonic sums.
+// Accuracy: the sum of harmonics cancels where the yield has a node in phi, so the error is absolute --
+// a few 1e-15 of the column's azimuthal mean -- instead of relative (tests/test_hostmath.py).
+constexpr int NT_BLUR = 64;
+constexpr int BLUR_CHUNK = 128;                 // phi items per table chunk (12 doubles each: 12 KB)
+constexpr int NA = 3 * NH + NH_SS;              // harmonic spectra per column (46)
+constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
+
+struct BlurArgs {
+    YieldArgs y;                                // y.tab: harmonic table, 12 doubles per item
+    int radius;
+    int S;                                      // staged energies per CTA = 2 NT + 2 radius
+    double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
+};
+
+__global__ void phi_harm_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
+                                      int allow_pairs) {
+    __shared__ int bad;
+    const long long H = nP / 2;
+    if (threadIdx.x == 0) bad = (allow_pairs && H > 0) ? 0 : 1;
+    __syncthreads();
+    if (allow_pairs && H > 0) {
+        int mybad = 0;
+        for (long long j = threadIdx.x; j < H; j += blockDim.x)
+            if (phi[j + H] != phi[j] + 180.0) mybad = 1;
+        if (mybad) bad = 1;
+    }
+    __syncthreads();
+    const long long h = bad ? 0 : H;
+    if (threadIdx.x == 0) tab[0] = (double)h;
+    const long long items = nP - h;
+    for (long long i = threadIdx.x; i < items; i += blockDim.x) {
+        double t[12];
+        phi_harmonics(phi[i < h ? i : i + h], t);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) tab[2 + i * 12 + k] = t[k];     // items start 16-byte aligned
+    }
+}
+
+__device__ __forceinline__ long long reflect_index(long long i, long long n) {
+    if (i >= 0 && i < n) return i;
+    long long m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m >= n ? 2 * n - 1 - m : m;
+}
+
+// (B) Gaussian FIR of NHH harmonic spectra for two adjacent energies: x points at this thread's window
+// x[0 .. 2 R + 1] of the first spectrum (spectra are S doubles apart), wf[0 .. 2 R] are the full taps.
+// out0 = sum_t wf[t] x[t], out1 = sum_t wf[t] x[t + 1].  Absent taps at the two ends are skipped, not
+// multiplied by zero (a NaN sample must not spread beyond the radius).
+template <int NHH>
+__device__ __forceinline__ void fir_pair(const double* __restrict__ x, int S, int R, const double* __restrict__ wf,
+                                         double* A0, double* A1) {
+    {
+        const double w0 = wf[0], w1 = wf[1];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S);
+            A0[m] = fma(v.y, w1, v.x * w0);
+            A1[m] = v.y * w0;
+        }
+    }
+#pragma unroll 1
+    for (int j = 1; j < R; ++j) {
+        const double wa = wf[2 * j - 1], wb = wf[2 * j], wc = wf[2 * j + 1];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S + 2 * j);
+            A0[m] = fma(v.y, wc, fma(v.x, wb, A0[m]));
+            A1[m] = fma(v.y, wb, fma(v.x, wa, A1[m]));
+        }
+    }
+    {
+        const double wa = wf[2 * R - 1], wb = wf[2 * R];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S + 2 * R);
+            A0[m] = fma(v.x, wb, A0[m]);
+            A1[m] = fma(v.y, wb, fma(v.x, wa, A1[m]));
+        }
+    }
+}
+
+// (C) azimuthal sweep of the harmonic form, two energies per thread.  tb: items of 12 doubles
+// {cos, sin of 2, 4, 6 phi | cos, sin of 1, 3, 5 phi}.
+template <bool SS>
+__device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
+                                           int n_pair, int n_single, double* plo, double* phi_, double* psg,
+                                           long long stride, bool vec, bool valid1) {
+#pragma unroll 2
+    for (int i = 0; i < n_pair + n_single; ++i) {
+        double t[12];
+#pragma unroll
+        for (int j = 0; j < (SS ? 3 : 6); ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
+            t[2 * j] = v.x;
+            t[2 * j + 1] = v.y;
+        }
+        tb += 12;
+        double ye0 = A0[0], ye1 = A1[0];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            ye0 = fma(A0[1 + j], t[j], ye0);
+            ye1 = fma(A1[1 + j], t[j], ye1);
+        }
+        double yo0 = 0.0, yo1 = 0.0;
+        if (!SS) {
+            yo0 = A0[7] * t[6];
+            yo1 = A1[7] * t[6];
+#pragma unroll
+            for (int j = 1; j < 6; ++j) {
+                yo0 = fma(A0[7 + j], t[6 + j], yo0);
+                yo1 = fma(A1[7 + j], t[6 + j], yo1);
+            }
+        }
+        if (i < n_pair) {
+            if (SS) {
+                store2(plo, ye0, ye1, vec, valid1);
+                store2(phi_, ye0, ye1, vec, valid1);
+            } else {
+                store2(plo, ye0 + yo0, ye1 + yo1, vec, valid1);
+                store2(phi_, ye0 - yo0, ye1 - yo1, vec, valid1);
+            }
+            plo += stride;
+            phi_ += stride;
+        } else {
+            if (SS) store2(psg, ye0, ye1, vec, valid1);
+            else store2(psg, ye0 + yo0, ye1 + yo1, vec, valid1);
+            psg += stride;
+        }
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(NT, 3) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
+    extern __shared__ double smem[];
+    const YieldArgs& a = b.y;
+    const int R = b.radius, S = b.S;
+    double* tabs = smem;                        // [BLUR_CHUNK][12]
+    double* wf = tabs + BLUR_CHUNK * 12;        // [2 R + 2] full taps (padded to an even count)
+    double* raw = wf + 2 * R + 2;               // [NA][S]
+
+    const long long blk = blockIdx.x;
+    const int tile = (int)(blk % a.n_tiles);
+    const long long lcol = blk / a.n_tiles;
+    const long long col = a.col0 + lcol;
+    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+    const int tid = threadIdx.x;
+    const long long nE = a.nE;
+    const long long tile_e0 = (long long)tile * NT * EPT;
+
+    for (int t = tid; t <= 2 * R; t += NT) wf[t] = b.w[t < R ? R - t : t - R];
+
+    // ---- (A) harmonic spectra of the staged energies (tile + halo) --------------------------------------
+    {
+        double st, ct;
+        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
+        const double thick = a.thick_nm[a.d0 + dl];
+#pragma unroll 1
+        for (int i = tid; i < S; i += NT) {
+            const long long g = tile_e0 - R + i;
+            if (g >= nE + R) break;             // no output of this axis reaches that far
+            const long long e = reflect_index(g, nE);
+            cplx e1[3], e2[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                e1[m] = ldc(a.eps1w + m * nE + e);
+                e2[m] = ldc(a.eps2w + m * nE + e);
+            }
+            const Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
+            auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+            double* dst = raw + i;
+#pragma unroll 1
+            for (int pol = 0; pol < 4; ++pol) {
+                if (pol == 3) {
+                    cplx kk[4];
+                    coeffs_ss(c, chi, kk);
+                    double H[NH_SS];
+                    harmonics4(kk, H);
+#pragma unroll
+                    for (int m = 0; m < NH_SS; ++m) dst[(3 * NH + m) * S] = H[m];
+                } else {
+                    cplx kk[7];
+                    if (pol == 0) coeffs_pp(c, chi, a.ph, kk);
+                    else if (pol == 1) coeffs_ps(c, chi, kk);
+                    else coeffs_sp(c, chi, kk);
+                    double H[NH];
+                    harmonics7(kk, H);
+#pragma unroll
+                    for (int m = 0; m < NH; ++m) dst[(pol * NH + m) * S] = H[m];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const long long e0 = tile_e0 + (long long)tid * EPT;
+    const bool active = e0 < nE;
+    const bool valid1 = e0 + 1 < nE;
+    const long long H = (long long)a.tab[0];
+    const long long items = a.nP - H;
+    const bool vec = a.vec_ok != 0;
+    const long long rows_per_pol = a.nP * nE;
+    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+
+#pragma unroll 1
+    for (int pol = 0; pol < 4; ++pol) {
+        // ---- (B) broadened harmonics of this thread's two energies ---------------------------------------
+        double A0[NH], A1[NH];
+        const double* x = raw + (pol * NH) * S + tid * EPT;
+        if (pol == 3) fir_pair<NH_SS>(x, S, R, wf, A0, A1);
+        else fir_pair<NH>(x, S, R, wf, A0, A1);
+        double* prow = out_col + pol * rows_per_pol;
+        // ---- (C) azimuthal sweep, table chunk by chunk ---------------------------------------------------
+        for (long long base = 0; base < items; base += BLUR_CHUNK) {
+            const int n_items = (int)min((long long)BLUR_CHUNK, items - base);
+            __syncthreads();                    // previous chunk fully consumed
+            for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
+            __syncthreads();
+            if (!active) continue;
+            const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
+            const int n_single = n_items - n_pair;
+            double* plo = prow + base * nE;
+            double* phi_ = prow + (base + H) * nE;
+            double* psg = prow + (base + n_pair + H) * nE;
+            if (pol == 3) sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+            else sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+        }
+    }
+}
+
 // ---- sparse-phi sweeps (few azimuths per column: thickness / incidence-angle scans) ---------------
 // chi2 is contracted with the phi-dependent unit vectors once per (energy, phi) (`phi_contract_kernel`,
 // X[p][12][nE]); `yield_sparse_kernel` then gives one thread one energy and a run of consecutive
@@ -479,8 +725,10 @@ constexpr size_t grid_smem(int nt, int chunk) { return (size_t)(chunk * 6 + EPT 
 
 }  // namespace
 
-extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where) {
+static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where) {
     SSHG_REQUIRE(ctx && p && out, "sshg_yield: null argument");
+    SSHG_REQUIRE(sigma_out >= 0.0 && isfinite(sigma_out), "sshg_yield: sigma_out must be finite and >= 0 (got %g)",
+                 sigma_out);
     SSHG_REQUIRE(p->nE > 0 && p->nT > 0 && p->nP > 0 && p->nD > 0,
                  "sshg_yield: nE, nT, nP, nD must be positive (got %lld %lld %lld %lld)",
                  (long long)p->nE, (long long)p->nT, (long long)p->nP, (long long)p->nD);
@@ -516,10 +764,22 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     SSHG_REQUIRE(((uintptr_t)a.eps1w | (uintptr_t)a.eps2w | (uintptr_t)a.chi) % 16 == 0,
                  "sshg_yield: complex device arrays must be 16-byte aligned");
 
+    // Output broadening (shg.py:433-436): radius as scipy.ndimage (int(4 sigma + 0.5)); a radius of 0 is the
+    // identity.  Dense sweeps with radius <= 64 take the fused kernel K3, everything else K2 -> K1 slab by slab.
+    // SSHG_K3=0 forces the two-pass path (tests compare both).
+    bool sparse = 4 * p->nP < 64;
+    if (const char* env = getenv("SSHG_K2_SPARSE")) sparse = atoi(env) != 0;
+    const long long radius = sigma_out > 1e-15 ? (long long)(4.0 * sigma_out + 0.5) : 0;
+    SSHG_REQUIRE(radius < (1LL << 28), "sshg_yield: sigma_out %g is too large", sigma_out);
+    bool fused = radius >= 1 && radius <= BLUR_RMAX && !sparse;
+    if (const char* env = getenv("SSHG_K3")) fused = fused && atoi(env) != 0;
+    const bool two_pass = radius >= 1 && !fused;
+
     void* tab;
-    if (int rc = sshg_scratch(ctx, 7, (size_t)(1 + 6 * p->nP) * 8, &tab)) return rc;
+    if (int rc = sshg_scratch(ctx, 7, (size_t)(2 + 12 * p->nP) * 8, &tab)) return rc;
     a.tab = (const double*)tab;
-    phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
+    if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
+    else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
 
@@ -553,8 +813,6 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
 
     // Sweeps with few azimuths per column go through the sparse-phi kernel (phi-contracted chi2,
     // thickness loop inside the thread).  SSHG_K2_SPARSE=0|1 overrides (tests run both kernels).
-    bool sparse = 4 * p->nP < 64;
-    if (const char* env = getenv("SSHG_K2_SPARSE")) sparse = atoi(env) != 0;
     SparseArgs sa{};
     if (sparse) {
         void* dX;
@@ -579,7 +837,21 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
         sa.dinfo = (const double*)dinfo;
     }
 
-    auto launch = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
+    BlurArgs ba{};
+    size_t blur_smem = 0;
+    if (fused) {
+        ba.radius = (int)radius;
+        ba.S = NT_BLUR * EPT + 2 * (int)radius;
+        sshg_gaussian_taps(sigma_out, radius, ba.w);
+        blur_smem = (size_t)(BLUR_CHUNK * 12 + 2 * radius + 2 + (size_t)NA * ba.S) * sizeof(double);
+        SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)blur_smem));
+    }
+    const int blur_tiles = (int)((p->nE + NT_BLUR * EPT - 1) / (NT_BLUR * EPT));
+    SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
+
+    // un-broadened yields of columns [c0, c0 + nc) of the shard -> dst
+    auto launch_raw = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
         if (sparse) {
             SparseArgs b = sa;
             b.col0 = c0;
@@ -609,16 +881,49 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
         ctx->launches++;
         return SSHG_OK;
     };
+    // K3: the same columns, broadened along the energy axis, in one pass
+    auto launch_blur = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
+        BlurArgs b = ba;
+        b.y = a;
+        b.y.col0 = c0;
+        b.y.out = dst;
+        b.y.n_tiles = blur_tiles;
+        b.y.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
+        yield_blur_kernel<NT_BLUR><<<(unsigned)(nc * blur_tiles), NT_BLUR, blur_smem, st>>>(b);
+        SSHG_CUDA(cudaGetLastError());
+        ctx->launches++;
+        return SSHG_OK;
+    };
 
-    if (out_dev) return launch(0, cols, out, ctx->stream);
-
-    // Host output: compute slabs of columns into two device buffers and copy slab k back on the
-    // copy stream while slab k+1 is computed.
+    // slabs of columns: the host-output pipeline and the two-pass broadening work slab by slab
     const size_t slab_target = (size_t)256 << 20;
     int64_t cols_per_slab = (int64_t)(slab_target / ((size_t)per_col * 8));
     if (cols_per_slab < 1) cols_per_slab = 1;
     if (cols_per_slab > cols) cols_per_slab = cols;
     const size_t slab_bytes = (size_t)cols_per_slab * per_col * 8;
+    void* tmp = nullptr;                        // K2 output of a slab, input of K1 (two-pass only)
+    if (two_pass) {
+        if (int rc = sshg_scratch(ctx, 12, slab_bytes, &tmp)) return rc;
+    }
+    // yields of columns [c0, c0 + nc), broadened if asked, -> dst (device), queued on ctx->stream
+    auto produce = [&](int64_t c0, int64_t nc, double* dst) -> int {
+        if (fused) return launch_blur(c0, nc, dst, ctx->stream);
+        if (!two_pass) return launch_raw(c0, nc, dst, ctx->stream);
+        if (int rc = launch_raw(c0, nc, (double*)tmp, ctx->stream)) return rc;
+        return sshg_gauss_device(ctx, (const double*)tmp, dst, nc * 4 * p->nP, p->nE, p->nE, 1, sigma_out);
+    };
+
+    if (out_dev) {
+        if (!two_pass) return produce(0, cols, out);
+        for (int64_t c0 = 0; c0 < cols; c0 += cols_per_slab) {
+            const int64_t nc = (cols - c0 < cols_per_slab) ? cols - c0 : cols_per_slab;
+            if (int rc = produce(c0, nc, out + c0 * per_col)) return rc;
+        }
+        return SSHG_OK;
+    }
+
+    // Host output: compute slabs of columns into two device buffers and copy slab k back on the
+    // copy stream while slab k+1 is computed.
     void* buf[2];
     if (int rc = sshg_scratch(ctx, 8, slab_bytes, &buf[0])) return rc;
     if (cols_per_slab < cols) {
@@ -631,7 +936,7 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     for (int64_t c0 = 0; c0 < cols; c0 += cols_per_slab, k ^= 1) {
         const int64_t nc = (cols - c0 < cols_per_slab) ? cols - c0 : cols_per_slab;
         if (used[k]) SSHG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));   // buffer drained
-        if (int rc = launch(c0, nc, (double*)buf[k], ctx->stream)) return rc;
+        if (int rc = produce(c0, nc, (double*)buf[k])) return rc;
         SSHG_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
         SSHG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
         SSHG_CUDA(cudaMemcpyAsync(out + c0 * per_col, buf[k], (size_t)nc * per_col * 8, cudaMemcpyDeviceToHost,
@@ -642,6 +947,14 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
     SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
     return SSHG_OK;
+}
+
+extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where) {
+    return yield_impl(ctx, p, 0.0, out, where);
+}
+
+extern "C" int sshg_yield_broadened(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where) {
+    return yield_impl(ctx, p, sigma_out, out, where);
 }
 
 static int points_impl(sshg_ctx* ctx, const sshg_points* p, double* out, int where, bool amp) {

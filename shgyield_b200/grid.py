@@ -67,9 +67,10 @@ def _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, phys, t_range=None, 
 
 
 def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, consts=None, sinc_normalized=True,
-                    zzz_phi_quirk=True, t_range=None, d_range=None, out=None, pinned=False):
+                    zzz_phi_quirk=True, t_range=None, d_range=None, out=None, pinned=False, sigma_out=0.0):
     """Host arrays in, host cube out: float64 [T_shard, D_shard, 4, P, E].  The library computes
-    slabs on the device and copies slab k back while slab k+1 is computed."""
+    slabs on the device and copies slab k back while slab k+1 is computed.  sigma_out > 0 broadens
+    every yield spectrum along the energy axis (shg.py:433-436) inside the yield kernel."""
     ctx = _lib.context()
     keep = []
     p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, _physics(consts, mref, sinc_normalized, zzz_phi_quirk),
@@ -81,15 +82,18 @@ def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, co
         out = _lib.pinned_empty(shape) if pinned else np.empty(shape)
     elif out.shape != shape or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
         raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
-    _lib.check(ctx.lib.sshg_yield(ctx.handle, C.byref(p), out.ctypes.data, _lib.HOST), ctx.lib)
+    _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), out.ctypes.data, _lib.HOST),
+               ctx.lib)
     return out
 
 
 def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, mref=True, consts=None,
-                      sinc_normalized=True, zzz_phi_quirk=True, t_range=None, d_range=None, stream=None):
+                      sinc_normalized=True, zzz_phi_quirk=True, t_range=None, d_range=None, stream=None,
+                      sigma_out=0.0):
     """Device-resident sweep: every array is a CUDA torch tensor (float64 / complex128), `out` a
     float64 CUDA tensor [T_shard, D_shard, 4, P, E] (allocated if None).  Asynchronous: the kernels
-    are queued on torch's current stream (or `stream`)."""
+    are queued on torch's current stream (or `stream`).  sigma_out > 0: yields broadened along the
+    energy axis in the same pass (K3)."""
     import torch
     ctx = _lib.context(energy.device.index)
     s = stream if stream is not None else torch.cuda.current_stream(energy.device)
@@ -108,7 +112,8 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
         out = torch.empty(shape, dtype=torch.float64, device=energy.device)
     elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
         raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
-    _lib.check(ctx.lib.sshg_yield(ctx.handle, C.byref(p), out.data_ptr(), _lib.DEVICE), ctx.lib)
+    _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), out.data_ptr(), _lib.DEVICE),
+               ctx.lib)
     return out
 
 
@@ -122,7 +127,8 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
 
     shard=(rank, world[, 'theta'|'thick']) computes only that rank's slab; with gather=True and an
     initialised torch.distributed process group the slabs are gathered onto rank 0 (`gather_slabs`).
-    sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles).
+    sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles); it is
+    done inside the yield kernel (K3: the cube is written once).
     """
     energy = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
     theta = np.atleast_1d(np.asarray(theta, dtype=np.float64)).ravel()
@@ -145,17 +151,12 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
         dev = torch.device("cuda", _lib.context().device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
         cube = yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
-                                 mref=mref, consts=consts, t_range=t_range, d_range=d_range)
-        if sigma_out > 1e-15:
-            cube = broaden_energy_device(cube, sigma_out)
+                                 mref=mref, consts=consts, t_range=t_range, d_range=d_range, sigma_out=sigma_out)
         if gather and shard is not None:
             cube = gather_slabs(cube, theta.size, thick.size, shard)
     else:
         cube = yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi_rot, mref=mref, consts=consts,
-                               t_range=t_range, d_range=d_range)
-        if sigma_out > 1e-15:
-            from .shg import _gauss_axis
-            cube = _gauss_axis(_lib.context(), cube, sigma_out, cube.ndim - 1)
+                               t_range=t_range, d_range=d_range, sigma_out=sigma_out)
     res = {"energy": energy, "theta": theta, "phi": phi, "thick": thick, "cube": cube}
     for k, pol in enumerate(POLS):
         res[pol] = cube[:, :, k] if cube is not None else None     # gather: only rank 0 holds the cube

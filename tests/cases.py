@@ -159,9 +159,11 @@ def sample_indices(shape, n, seed):
     return np.unique(np.concatenate([idx, corners]), axis=0)
 
 
-def parity_ok(a, b, rtol=1e-10, scale=None):
+def parity_ok(a, b, rtol=1e-10, scale=None, rel_floor=1e-6):
     """SURVEY.md section 8c metric, per polarisation: |a-b| <= rtol*max|b| everywhere AND
-    |a-b| <= rtol*|b| wherever |b| >= 1e-6*max|b|.  NaN/Inf must coincide.
+    |a-b| <= rtol*|b| wherever |b| >= rel_floor*max|b| (1e-6; the fused output broadening K3, whose
+    error is absolute -- a few 1e-15 of the column's azimuthal mean -- is held to 1e-4 and to that
+    absolute bound).  NaN/Inf must coincide.
     `scale` (optional) = max |yield| over ALL four polarisations of the case: a polarisation
     that is a symmetry node over the whole array (e.g. R_pS of Si(111) at gamma=90, phi=30 is
     1e-52 against 1e-22) is pure rounding noise of an amplitude that cancels to 1e-16, i.e.
@@ -184,7 +186,7 @@ def parity_ok(a, b, rtol=1e-10, scale=None):
     err = np.abs(af - bf)
     if np.max(err) > rtol * big:
         return False, "abs err %.3e > %.1e * max %.3e" % (np.max(err), rtol, big)
-    sel = np.abs(bf) >= 1e-6 * big
+    sel = np.abs(bf) >= rel_floor * big
     if sel.any():
         rel = np.max(err[sel] / np.abs(bf[sel]))
         if rel > rtol:

@@ -160,3 +160,70 @@ extern "C" int hostmath_sparse_walk(const sshg_points* p, long long e, double th
     }
     return 0;
 }
+
+// ---- K3 on the CPU: harmonic form of one (theta, thickness) column, broadened along the energy axis ----
+// p: a point list whose spectra columns are the energy axis (eidx unused); theta / thickness scalars;
+// phi: nP azimuths; w: r + 1 Gaussian taps (w[0] centre); out[pol][nP][nE].
+extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, double thick_nm, const double* phi_deg,
+                                    long long nP, const double* w, int r, double* out) {
+    Physics ph;
+    ph.kd = 1e-9 / (p->phys.h_eVs * p->phys.c);
+    ph.pref = 100.0 / (p->phys.hbar_eVs * sqrt(2.0 * p->phys.eps0 * p->phys.c * p->phys.c * p->phys.c));
+    ph.mref = p->phys.mref;
+    ph.sinc_normalized = p->phys.sinc_normalized;
+    ph.zzz_phi_quirk = p->phys.zzz_phi_quirk;
+    ph.raw = 0;
+    ph.radians = 0;
+    const long long nE = p->nE;
+    double st, ct;
+    sincos(theta_deg * (3.141592653589793 / 180.0), &st, &ct);
+    const int off[5] = {0, NH, 2 * NH, 3 * NH, 3 * NH + NH_SS};
+    const int NA = off[4];
+    std::vector<double> raw((size_t)NA * nE), blur((size_t)NA * nE);
+    for (long long e = 0; e < nE; ++e) {
+        cplx e1[3], e2[3];
+        for (int m = 0; m < 3; ++m) {
+            e1[m] = mk(p->eps1w[2 * (m * nE + e)], p->eps1w[2 * (m * nE + e) + 1]);
+            e2[m] = mk(p->eps2w[2 * (m * nE + e)], p->eps2w[2 * (m * nE + e) + 1]);
+        }
+        const Column c = column_setup(e1, e2, p->energy_eV[e], st, ct, thick_nm, ph);
+        auto chi = [&](int q) { return mk(p->chi2[2 * (q * nE + e)], p->chi2[2 * (q * nE + e) + 1]); };
+        for (int pol = 0; pol < 3; ++pol) {
+            cplx k[7];
+            if (pol == 0) coeffs_pp(c, chi, ph, k);
+            else if (pol == 1) coeffs_ps(c, chi, k);
+            else coeffs_sp(c, chi, k);
+            double H[NH];
+            harmonics7(k, H);
+            for (int m = 0; m < NH; ++m) raw[(size_t)(off[pol] + m) * nE + e] = H[m];
+        }
+        cplx k[4];
+        coeffs_ss(c, chi, k);
+        double H[NH_SS];
+        harmonics4(k, H);
+        for (int m = 0; m < NH_SS; ++m) raw[(size_t)(off[3] + m) * nE + e] = H[m];
+    }
+    auto reflect = [&](long long i) {
+        long long m = i % (2 * nE);
+        if (m < 0) m += 2 * nE;
+        return m >= nE ? 2 * nE - 1 - m : m;
+    };
+    for (int a = 0; a < NA; ++a)
+        for (long long e = 0; e < nE; ++e) {
+            double acc = 0.0;
+            for (int j = -r; j <= r; ++j) acc = fma(raw[(size_t)a * nE + reflect(e + j)], w[j < 0 ? -j : j], acc);
+            blur[(size_t)a * nE + e] = acc;
+        }
+    for (long long ip = 0; ip < nP; ++ip) {
+        double t[12];
+        phi_harmonics(phi_deg[ip], t);
+        for (int pol = 0; pol < 4; ++pol)
+            for (long long e = 0; e < nE; ++e) {
+                double H[NH];
+                const int nh = pol == 3 ? NH_SS : NH;
+                for (int m = 0; m < nh; ++m) H[m] = blur[(size_t)(off[pol] + m) * nE + e];
+                out[((size_t)pol * nP + ip) * nE + e] = harmonic_yield(H, t, pol == 3);
+            }
+    }
+    return 0;
+}

@@ -1,0 +1,176 @@
+"""
+GPU parity tests of the broadened sweep (sshg_yield_broadened, K3): the yield cube with the output
+broadening of shgyield() (broad(., sigma_out) along the energy axis, reference shg.py:26-28, 433-436)
+computed in one pass, against the CPU oracle (un-broadened yields -> scipy-style gaussian filter row by
+row) and against the two-pass device path (K2 -> K1, SSHG_K3=0).
+
+Tolerance: tests/cases.py::parity_ok with rtol 1e-10; K3's error is absolute (a few 1e-15 of the column's
+maximum over phi, checked here as < 5e-14), so the element-wise relative part of the metric starts at
+1e-4 of the maximum for it (1e-6 for the two-pass path).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import shg_oracle as orc
+from tests import cases, util
+from tests.test_gpu_parity import _oracle_cube, _small_cfg
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def grid():
+    from shgyield_b200 import grid as mod
+    return mod
+
+
+@pytest.fixture(scope="module")
+def consts():
+    return util.load_consts()
+
+
+def _blurred_oracle(cfg, consts, sigma, **kw):
+    return orc.gaussian_filter1d(_oracle_cube(cfg, consts, **kw), sigma, axis=-1)
+
+
+def _check(got, want, fused, what):
+    assert got.shape == want.shape
+    top = np.max(want)
+    for k, pol in enumerate(cases.POLS):
+        a, b = got[:, :, k], want[:, :, k]
+        ok, msg = cases.parity_ok(a, b, rtol=RTOL, scale=top, rel_floor=1e-4 if fused else 1e-6)
+        assert ok, (what, pol, msg)
+        colmax = np.maximum(np.max(b, axis=2, keepdims=True), 1e-12 * top)       # max over phi of every column
+        assert np.max(np.abs(a - b) / colmax) < 5e-14, (what, pol)
+
+
+BLUR_SHAPES = [
+    # nE, theta, phi, thick
+    (1, [65.0], np.arange(0, 360, 20.0), [10.0]),                 # one energy: every reflection lands on it
+    (126, [65.0], np.arange(0, 360, 20.0), [10.0]),               # one tile, ragged
+    (513, [0.0, 33.0, 90.0], np.arange(0, 360, 15.0), [10.0]),    # odd nE (64-bit stores), pairs, 5 tiles
+    (600, [10.0, 80.0], np.linspace(0, 360, 41), [0.0, 7.5]),     # pairs + one un-paired row, two thicknesses
+    (64, [45.0], np.linspace(0, 350, 17), [3.0]),                 # no pairing possible
+    (30, [55.0], np.linspace(0, 360, 1001), [12.0]),              # several phi chunks, nE < radius
+    (1030, [20.0, 40.0], np.arange(0, 360, 22.5), [5.0]),         # tile boundaries inside the axis
+]
+
+
+@pytest.mark.parametrize("path", ["fused", "two_pass"])
+@pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0])
+@pytest.mark.parametrize("nE,theta,phi,thick", BLUR_SHAPES, ids=[str(i) for i in range(len(BLUR_SHAPES))])
+def test_broadened_sweep_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, thick, sigma, path):
+    """radius 1, 5, 20 (the default sigma_out = 5) and 64 (the largest fused radius)."""
+    monkeypatch.setenv("SSHG_K3", "1" if path == "fused" else "0")
+    cfg = _small_cfg(nE, theta, phi, thick, seed=3)
+    got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
+    _check(got, _blurred_oracle(cfg, consts, sigma), path == "fused", (nE, sigma, path))
+
+
+def test_sparse_phi_sweeps_and_large_radii_take_the_two_pass_path(grid, consts, monkeypatch):
+    """P = 1 (config-4 shape) and sigma_out > 16: K2 / K2s -> K1 slab by slab; P = 1 forced through K3."""
+    cfg = _small_cfg(300, np.arange(0, 90, 9.0), [30.0], np.arange(1.0, 31.0), seed=5)
+    want = _blurred_oracle(cfg, consts, 5.0)
+    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, False, "sparse")
+    monkeypatch.setenv("SSHG_K2_SPARSE", "0")
+    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, True, "P=1 through K3")
+    monkeypatch.delenv("SSHG_K2_SPARSE")
+    cfg = _small_cfg(400, [30.0, 60.0], np.arange(0, 360, 30.0), [10.0], seed=6)
+    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=20.0), _blurred_oracle(cfg, consts, 20.0), False, "r=80")
+    # a radius of 0 (sigma_out < 0.125) is the identity
+    assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, sigma_out=0.1), grid.yield_grid_host(**cfg, consts=consts))
+
+
+@pytest.mark.parametrize("kw", [dict(mref=False), dict(sinc_normalized=False), dict(zzz_phi_quirk=False)])
+def test_broadened_sweep_switches(grid, consts, kw):
+    cfg = _small_cfg(200, [15.0, 70.0], np.arange(0, 360, 20.0), [10.0, 55.0], seed=4)
+    got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=2.0, **kw)
+    _check(got, _blurred_oracle(cfg, consts, 2.0, **kw), True, kw)
+
+
+def test_broadened_shards_are_bitwise_slices(grid, consts):
+    cfg = _small_cfg(300, np.linspace(0, 90, 11), np.arange(0, 360, 10.0), [4.0, 9.0, 14.0], seed=2)
+    full = grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0)
+    for world in (2, 8):
+        for rank in range(world):
+            lo, hi = grid.shard_bounds(11, world, rank)
+            assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0, t_range=(lo, hi)), full[lo:hi])
+    lo, hi = grid.shard_bounds(3, 2, 1)
+    assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0, d_range=(lo, hi)), full[:, lo:hi])
+
+
+def test_nan_sample_stays_within_the_radius(grid, consts):
+    """A NaN in one spectrum sample: the reference's broadened yields are NaN exactly within the radius
+    of that energy, for every angle and polarisation that uses the sample."""
+    cfg = _small_cfg(400, [30.0], np.arange(0, 360, 30.0), [10.0], seed=8)
+    cfg["chi2"] = cfg["chi2"].copy()
+    cfg["chi2"][:, 200] = np.nan
+    got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=2.0)          # radius 8
+    want = _blurred_oracle(cfg, consts, 2.0)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.isnan(got[0, 0, 0, 0, 192:209]).all() and not np.isnan(got[0, 0, 0, 0, :192]).any()
+
+
+def test_broadened_device_host_and_two_pass_paths_agree(grid, consts, monkeypatch):
+    """Device-resident output, the host slab pipeline (several slabs) and the two-pass path on a 472 MB cube."""
+    import torch
+    cfg = _small_cfg(4096, np.linspace(5, 85, 20), np.arange(0, 360, 2.0), [10.0], seed=6)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg.items()}
+    run = lambda: grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                                         consts=consts, sigma_out=5.0)
+    fused = run()
+    host = grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0)
+    assert np.array_equal(fused.cpu().numpy(), host)
+    monkeypatch.setenv("SSHG_K3", "0")
+    two = run()
+    torch.cuda.synchronize()
+    top = float(two.max())
+    colmax = two.amax(dim=3, keepdim=True).clamp_min(1e-12 * top)
+    assert float(((fused - two).abs() / colmax).max()) < 5e-14
+    assert float((fused - two).abs().max()) < 1e-13 * top
+
+
+def test_api_sweep_with_output_broadening_matches_the_reference_loop(grid):
+    """shgyield_grid(sigma_out=5) against the oracle's shgyield() called angle by angle (the only way the
+    reference can broaden a sweep along the energy axis alone)."""
+    m1, m2, m3, chi2 = cases.full_tensor_material(cases.load_spectra())
+    energy = np.linspace(1.0, 3.0, 201)
+    theta, phi = np.array([25.0, 65.0]), np.arange(0.0, 360.0, 40.0)
+    res = grid.shgyield_grid(energy, m1, m2, m3, chi2, theta, phi, 10.0, gamma=35, sigma_out=5.0, device=False)
+    for it, th in enumerate(theta):
+        for ip, ph in enumerate(phi):
+            ref = orc.shgyield(energy, m1, m2, m3, chi2, th, ph, 10.0, gamma=35, sigma_out=5.0)
+            sc = max(np.max(ref[p]) for p in cases.POLS)
+            for pol in cases.POLS:
+                ok, msg = cases.parity_ok(res[pol][it, 0, ip], ref[pol], rtol=RTOL, scale=sc, rel_floor=1e-4)
+                assert ok, (th, ph, pol, msg)
+
+
+def test_config5_shard_broadened_full_rows_vs_oracle(grid, consts):
+    """A theta shard of the 20k x 181 x 721 cube with sigma_out = 5, complete (theta, phi) rows against the oracle."""
+    import torch
+    from shgyield_b200.synthetic import config5
+    cfg = config5()
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg.items()}
+    t0, t1 = 60, 68
+    cube = grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                                  consts=consts, t_range=(t0, t1), sigma_out=5.0)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(cube).all())
+    top = float(cube.max())
+    assert float((cube[:, :, :, 0] - cube[:, :, :, 720]).abs().max()) <= 1e-12 * top      # phi = 0 == phi = 360
+    e1 = {"M%d" % (m + 1): cfg["eps1w"][m] for m in range(3)}
+    e2 = {"M%d" % (m + 1): cfg["eps2w"][m] for m in range(3)}
+    ch = {k: cfg["chi2"][i] for i, k in enumerate(cases.CHI2_KEYS)}
+    ips = np.array([0, 1, 77, 360, 361, 500, 719, 720])
+    for it in (t0, t0 + 5, t1 - 1):
+        raw = orc.yield_points(cfg["energy"], e1, e2, ch, cfg["theta"][it], cfg["phi"][ips][:, None], 10.0, True, consts)
+        got = cube[it - t0, 0][:, torch.from_numpy(ips).to(dev)].cpu().numpy()            # [4, len(ips), E]
+        for k, pol in enumerate(cases.POLS):
+            want = orc.gaussian_filter1d(raw[pol], 5.0, axis=-1)
+            assert np.max(np.abs(got[k] - want)) < 1e-13 * np.max(want), (it, pol)

@@ -170,3 +170,53 @@ def test_phase_recurrence_on_uniform_thickness_grids(harness, sn):
         want = orc.yield_points(energy[e], e1, e2, ch, theta, phi, thick, True, consts, sn, True)
         for i, pol in enumerate(cases.POLS):
             np.testing.assert_allclose(out[i], want[pol], rtol=2e-12, atol=0, err_msg="%s e=%d" % (pol, e))
+
+
+def _blur_column(harness, energy, eps1w, eps2w, chi, theta, thick, phi, sigma, consts):
+    harness.hostmath_blur_column.restype = C.c_int
+    harness.hostmath_blur_column.argtypes = [C.POINTER(_lib.Points), C.c_double, C.c_double, C.c_void_p, C.c_longlong,
+                                             C.c_void_p, C.c_int, C.c_void_p]
+    arrs = [np.ascontiguousarray(a) for a in (energy, eps1w, eps2w, chi)]
+    nE = energy.size
+    p = _lib.Points(n=1, nE=nE, energy_eV=arrs[0].ctypes.data, eidx=0, theta_deg=0, phi_deg=0, thick_nm=0,
+                    eps1w=arrs[1].ctypes.data, eps2w=arrs[2].ctypes.data, chi2=arrs[3].ctypes.data,
+                    phys=_lib.Physics(consts["h_eVs"], consts["hbar_eVs"], consts["eps0"], consts["c"], 1, 1, 1, 0))
+    w = orc.gaussian_taps(sigma)
+    r = (len(w) - 1) // 2
+    taps = np.ascontiguousarray(w[r:])
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    out = np.empty((4, phi.size, nE))
+    assert harness.hostmath_blur_column(C.byref(p), float(theta), float(thick), phi.ctypes.data, phi.size,
+                                        taps.ctypes.data, r, out.ctypes.data) == 0
+    return out
+
+
+@pytest.mark.parametrize("sigma", [0.3, 2.0, 5.0])
+@pytest.mark.parametrize("material", ["synthetic", "si111"])
+def test_harmonic_form_commutes_with_output_broadening(harness, material, sigma):
+    """K3's algorithm on the CPU: |r(phi)|^2 expanded in 13 azimuthal harmonics per energy, the harmonic
+    spectra broadened along the energy axis, then evaluated per phi -- against the oracle's
+    broad(yield, sigma_out) row by row (shg.py:433-436).  Si(111) has exact symmetry nodes in phi."""
+    consts = util.load_consts()
+    if material == "synthetic":
+        energy, eps1w, eps2w, chi = synthetic_spectra(90, seed=11)
+    else:
+        m1, m2, m3, chi2 = cases.si111_material(cases.load_spectra())
+        energy = np.linspace(0.5, 5.0, 90)
+        e1, e2, ch, _ = orc.prepare(energy, m1, m2, m3, chi2, 10.0, 0, 0.0, 0.0, "3-layer")
+        eps1w, eps2w, chi = util.pack_eps(e1, 90), util.pack_eps(e2, 90), util.pack_chi(ch, 90)
+    phi = np.concatenate([np.arange(0.0, 360.0, 7.5), [29.98, 30.0, 30.05, 123.456]])
+    for theta, thick in ((65.0, 10.0), (0.0, 3.0), (89.0, 55.0)):
+        got = _blur_column(harness, energy, eps1w, eps2w, chi, theta, thick, phi, sigma, consts)
+        d1 = {"M%d" % (m + 1): eps1w[m] for m in range(3)}
+        d2 = {"M%d" % (m + 1): eps2w[m] for m in range(3)}
+        ch = {k: chi[i] for i, k in enumerate(cases.CHI2_KEYS)}
+        raw = orc.yield_points(energy, d1, d2, ch, theta, phi[:, None], thick, True, consts)
+        want = {pol: orc.gaussian_filter1d(raw[pol], sigma, axis=-1) for pol in cases.POLS}
+        sc = max(np.max(np.abs(v)) for v in want.values())
+        for i, pol in enumerate(cases.POLS):
+            ok, msg = cases.parity_ok(got[i], want[pol], rtol=1e-10, scale=sc, rel_floor=1e-4)
+            assert ok, (material, sigma, theta, pol, msg)
+            # the error of the harmonic form is absolute: a few 1e-15 of the column's maximum over phi
+            colmax = np.maximum(want[pol].max(axis=0, keepdims=True), 1e-12 * sc)
+            assert np.max(np.abs(got[i] - want[pol]) / colmax) < 5e-14, (material, sigma, theta, pol)

@@ -37,6 +37,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only-k1", action="store_true")
+    ap.add_argument("--only-k3", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -44,7 +45,7 @@ def main():
     m1, m2, m3, chi2 = cases.si111_material()
 
     # ---- configs 3 and 4: Si(111) material, device resident; prep (K1, spline, rotate) timed apart -----
-    for tag, axes in (() if args.only_k1 else (("config3", cases.config3_axes()), ("config4", cases.config4_axes()))):
+    for tag, axes in (() if (args.only_k1 or args.only_k3) else (("config3", cases.config3_axes()), ("config4", cases.config4_axes()))):
         t0 = time.perf_counter()
         eps1w, eps2w, chi_rot, thick = shg._prepare(axes["energy"], m1, m2, m3, chi2, axes["thick"], axes["gamma"], 0.0,
                                                     0.0, "3-layer")
@@ -69,7 +70,7 @@ def main():
     # ---- config-5 theta shards (what one of 8 / 4 ranks computes), both CTA sizes of K2 ----------------
     cfg = config5()
     dd = {k: put(v) for k, v in cfg.items()}
-    for nth in (() if args.only_k1 else (23, 46)):
+    for nth in (() if (args.only_k1 or args.only_k3) else (23, 46)):
         out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
         for nt in ("64", "256", None):
             if nt is None:
@@ -82,6 +83,25 @@ def main():
             print(json.dumps({"case": "config5_shard_%dtheta" % nth, "k2_threads": nt or "auto", "ms_median": med,
                               "ms_best": best, "store_gbs": 8e-9 * out.numel() / (med * 1e-3)}), flush=True)
         del out
+
+    # ---- K3: config-5 theta shards with the output broadening (sigma_out samples along E) -------------
+    # fused (one pass, FIR on the 13 azimuthal harmonics of a column) against two-pass (K2 -> K1 by slabs)
+    for nth in (() if args.only_k1 else (23, 46)):
+        out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
+        for sigma in (2.0, 5.0, 12.0):
+            for k3 in ("1", "0"):
+                os.environ["SSHG_K3"] = k3
+                med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"],
+                                                                dd["eps1w"], dd["eps2w"], dd["chi2"], out=out, consts=consts,
+                                                                t_range=(0, nth), sigma_out=sigma), args.reps)
+                print(json.dumps({"case": "config5_shard_%dtheta_sigma_out%g" % (nth, sigma),
+                                  "path": "K3 fused" if k3 == "1" else "K2 -> K1 two-pass", "ms_median": med, "ms_best": best,
+                                  "points_per_s": out.numel() / (med * 1e-3),
+                                  "store_gbs": 8e-9 * out.numel() / (med * 1e-3)}), flush=True)
+        os.environ.pop("SSHG_K3", None)
+        del out
+    if args.only_k3:
+        return
 
     # ---- K1 on a cube slab: 8 thetas of config 5, sigma = 5 samples along E ---------------------------
     slab = grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"], dd["eps1w"], dd["eps2w"], dd["chi2"],
