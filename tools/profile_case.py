@@ -2,6 +2,7 @@
 """Profiling driver for ncu: runs a few launches of one kernel on a representative workload.
 
     python tools/profile_case.py k2 [n_theta]    fused yield kernel, config-5 theta shard
+    python tools/profile_case.py k3 [n_theta] [sigma_out]   broadened sweep (fused K3), config-5 theta shard
     python tools/profile_case.py k1 [sigma]      Gaussian FIR along E of a 4-theta config-5 slab
     python tools/profile_case.py c4              config 4 (thickness sweep, P = 1)
     python tools/profile_case.py c3              config 3 (angular map)
@@ -24,14 +25,15 @@ dev = torch.device("cuda", 0)
 put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 consts = shg.physical_constants()
 
-if case in ("k2", "k1"):
+if case in ("k2", "k1", "k3"):
     cfg = config5()
     d = {k: put(v) for k, v in cfg.items()}
-    nth = int(sys.argv[2]) if case == "k2" and len(sys.argv) > 2 else (37 if case == "k2" else 4)
+    nth = int(sys.argv[2]) if case in ("k2", "k3") and len(sys.argv) > 2 else (37 if case == "k2" else 4)
+    sigma_out = (float(sys.argv[3]) if len(sys.argv) > 3 else 5.0) if case == "k3" else 0.0
     out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
-    for _ in range(3 if case == "k2" else 1):
+    for _ in range(1 if case == "k1" else 3):
         grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"], out=out,
-                               consts=consts, t_range=(60, 60 + nth))
+                               consts=consts, t_range=(60, 60 + nth), sigma_out=sigma_out)
     if case == "k1":
         sigma = float(sys.argv[2]) if len(sys.argv) > 2 else 5.0
         for _ in range(3):
