@@ -382,6 +382,45 @@ def run_ours(args):
                       "how": "grouped ncclSend/ncclRecv of the true shard sizes into the cube on rank 0 (NVLink)",
                       "own_slab_intact": ok}
         del full
+        torch.cuda.empty_cache()
+        # the same gather WITHOUT a collective: every rank's K2 stores its slab straight into rank 0's cube
+        # over NVLink (CUDA IPC mapping, grid.PeerCube) -- compute and gather are one kernel per rank
+        try:
+            if args.no_peer_gather:
+                raise RuntimeError("skipped (--no-peer-gather)")
+            pc = grid.PeerCube((N_THETA, 1, 4, N_PHI, N_ENERGY), dst=0)      # raises on EVERY rank or on none
+            p_ms = []
+            for it in range(3):
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                                       consts=consts, t_range=(t_lo, t_hi), out_ptr=pc.slab_ptr(t_lo))
+                g1.record()
+                barrier()
+                if it:
+                    p_ms.append(g0.elapsed_time(g1))
+            pt = torch.tensor([min(p_ms)], dtype=torch.float64, device=dev)
+            dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+            if rank == 0:
+                cube = pc.tensor()
+                lo_l, hi_l = grid.shard_bounds(N_THETA, world, world - 1)          # re-compute the last rank's slab here
+                chk = grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"],
+                                             d["chi2"], consts=consts, t_range=(lo_l, hi_l))
+                same = bool(torch.equal(cube[lo_l:hi_l], chk)) and bool(torch.equal(cube[t_lo:t_hi], out))
+                gather["peer_store"] = {
+                    "ms_compute_and_gather": float(pt.item()), "gbs_into_rank0": recv_bytes / (pt.item() * 1e-3) / 1e9,
+                    "vs_compute_then_nccl_gather_ms": total_ms / args.steps + gather["ms"],
+                    "how": "every rank's yield_grid_kernel stores its theta slab directly into rank 0's cube (cudaIpc "
+                           "mapping over NVLink/NVSwitch): no slab buffer, no send/recv; max over ranks of the kernel time",
+                    "bitwise_equal_to_local": same}
+                del cube, chk
+            pc.close()
+            del pc
+        except Exception as e:                                   # IPC not permitted on this box: report, keep the line
+            if rank == 0 and gather is not None:
+                gather["peer_store"] = {"unavailable": repr(e)[:200]}
+        torch.cuda.empty_cache()
 
     # ---- secondary: the same shard with the reference's default output broadening (sigma_out = 5), K3 ---
     ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
@@ -464,6 +503,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gather", action="store_true", help="skip timing the NCCL gather of the slabs (N > 1)")
+    ap.add_argument("--no-peer-gather", action="store_true", help="skip the gather by peer stores (N > 1)")
     args = ap.parse_args()
     if args.steps < 1:
         raise SystemExit("--steps must be >= 1")

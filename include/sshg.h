@@ -123,6 +123,21 @@ SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by
 SSHG_API int sshg_host_alloc(void** ptr, int64_t bytes);  /* page-locked host memory for fast D2H    */
 SSHG_API int sshg_host_free(void* ptr);
 
+/* ---- the gather of the yield cube without a collective: peer memory over NVLink ----------------
+ * north_star's one exchange step is the gather of the theta slabs onto one GPU.  Instead of computing a
+ * slab locally and sending it (ncclSend/ncclRecv), the destination rank allocates the whole cube with
+ * sshg_device_alloc, exports it (sshg_ipc_export: 64 opaque bytes that travel to the other ranks of the
+ * node by any means), every other rank maps it (sshg_ipc_open) and passes `mapped + slab offset` as the
+ * device `out` of sshg_yield / sshg_yield_broadened: the yield kernel's 128-bit stores then go straight
+ * over NVLink / NVSwitch into the destination's HBM and the gather disappears into the kernel.
+ * (SURVEY.md 8e "B200-native alternative"; the reference itself is single-process NumPy.) */
+#define SSHG_IPC_HANDLE_BYTES 64
+SSHG_API int sshg_device_alloc(sshg_ctx* ctx, void** ptr, int64_t bytes);   /* cudaMalloc on the context's device */
+SSHG_API int sshg_device_free(sshg_ctx* ctx, void* ptr);
+SSHG_API int sshg_ipc_export(sshg_ctx* ctx, const void* dev_ptr, unsigned char handle[SSHG_IPC_HANDLE_BYTES]);
+SSHG_API int sshg_ipc_open(sshg_ctx* ctx, const unsigned char handle[SSHG_IPC_HANDLE_BYTES], void** dev_ptr);
+SSHG_API int sshg_ipc_close(sshg_ctx* ctx, void* dev_ptr);
+
 /* ---- Gaussian broadening: replaces broad / broadC (shg.py:26-35), i.e.
  * scipy.ndimage.gaussian_filter along one axis: taps exp(-k^2/(2 sigma^2))/sum,
  * radius int(4 sigma + 0.5), 'reflect' boundary; sigma <= 1e-15 copies.

@@ -20,6 +20,7 @@ SSHG_OK, SSHG_EINVAL, SSHG_ECUDA, SSHG_ENOMEM = 0, -1, -2, -3
 HOST, IN_DEVICE, OUT_DEVICE, DEVICE = 0, 1, 2, 3
 ABI_VERSION = 1
 FLAG_RADIANS = 1
+IPC_HANDLE_BYTES = 64
 
 c_double_p = C.POINTER(C.c_double)
 
@@ -59,6 +60,11 @@ SYMBOLS = {
     "sshg_ctx_launches": (C.c_int64, [C.c_void_p]),
     "sshg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "sshg_host_free": (C.c_int, [C.c_void_p]),
+    "sshg_device_alloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]),
+    "sshg_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "sshg_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
+    "sshg_ipc_open": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
+    "sshg_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sshg_gauss1d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                C.c_double, C.c_int]),
     "sshg_rotate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int]),

@@ -182,4 +182,56 @@ int sshg_host_free(void* ptr) {
     return SSHG_OK;
 }
 
+// ---- peer memory for the store-through gather (include/sshg.h) ---------------------------------------
+int sshg_device_alloc(sshg_ctx* ctx, void** ptr, int64_t bytes) {
+    SSHG_REQUIRE(ctx && ptr && bytes > 0, "sshg_device_alloc: bad argument");
+    *ptr = nullptr;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        sshg_set_error("device allocation of %lld bytes failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return SSHG_ENOMEM;
+    }
+    return SSHG_OK;
+}
+
+int sshg_device_free(sshg_ctx* ctx, void* ptr) {
+    SSHG_REQUIRE(ctx, "sshg_device_free: null context");
+    if (!ptr) return SSHG_OK;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    SSHG_CUDA(cudaFree(ptr));
+    return SSHG_OK;
+}
+
+static_assert(sizeof(cudaIpcMemHandle_t) == SSHG_IPC_HANDLE_BYTES, "IPC handle size");
+
+int sshg_ipc_export(sshg_ctx* ctx, const void* dev_ptr, unsigned char handle[SSHG_IPC_HANDLE_BYTES]) {
+    SSHG_REQUIRE(ctx && dev_ptr && handle, "sshg_ipc_export: null argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    SSHG_CUDA(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return SSHG_OK;
+}
+
+int sshg_ipc_open(sshg_ctx* ctx, const unsigned char handle[SSHG_IPC_HANDLE_BYTES], void** dev_ptr) {
+    SSHG_REQUIRE(ctx && handle && dev_ptr, "sshg_ipc_open: null argument");
+    *dev_ptr = nullptr;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    SSHG_CUDA(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return SSHG_OK;
+}
+
+int sshg_ipc_close(sshg_ctx* ctx, void* dev_ptr) {
+    SSHG_REQUIRE(ctx, "sshg_ipc_close: null context");
+    if (!dev_ptr) return SSHG_OK;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));     // stores of queued kernels have left this GPU
+    SSHG_CUDA(cudaIpcCloseMemHandle(dev_ptr));
+    return SSHG_OK;
+}
+
 }  // extern "C"

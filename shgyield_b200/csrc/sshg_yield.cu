@@ -287,8 +287,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 // (C) sweeps the azimuth, phi / phi + 180 deg pairs sharing the even and odd harmonic sums.
 // Accuracy: the sum of harmonics cancels where the yield has a node in phi, so the error is absolute --
 // a few 1e-15 of the column's azimuthal mean -- instead of relative (tests/test_hostmath.py).
-constexpr int NT_BLUR = 64;
+constexpr int NT_BLUR = 64;                     // 128-energy tiles, 3 CTAs/SM at radius 20
 constexpr int BLUR_CHUNK = 128;                 // phi items per table chunk (12 doubles each: 12 KB)
+constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM
+constexpr int BLUR_CHUNK_WIDE = 16;
 constexpr int NA = 3 * NH + NH_SS;              // harmonic spectra per column (46)
 constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
 
@@ -417,8 +419,8 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
     }
 }
 
-template <int NT>
-__global__ void __launch_bounds__(NT, 3) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
+template <int NT, int BLUR_CHUNK>
+__global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
     extern __shared__ double smem[];
     const YieldArgs& a = b.y;
     const int R = b.radius, S = b.S;
@@ -839,15 +841,39 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     BlurArgs ba{};
     size_t blur_smem = 0;
+    // Tile width: 256-energy tiles (128 threads) halve the halo overhead and measured 0.94 of the HBM peak
+    // against 0.89 on a 46-theta shard of config 5 -- as long as two of them fit on an SM (radius <= 22);
+    // beyond that 128-energy tiles (3 .. 2 CTAs/SM) win.  SSHG_K3_NT=64|128 overrides (tuning).
+    int blur_nt = NT_BLUR;
+    auto smem_for = [&](int nt, int chunk) {
+        return (size_t)(chunk * 12 + 2 * radius + 2 + (size_t)NA * (nt * EPT + 2 * radius)) * sizeof(double);
+    };
     if (fused) {
+        const size_t wide = smem_for(NT_BLUR_WIDE, BLUR_CHUNK_WIDE);
+        int per_sm = 0;
+        if (wide <= (size_t)227 * 1024) {
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide));
+            SSHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
+                                                                    NT_BLUR_WIDE, wide));
+        }
+        if (per_sm >= 2 && p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
+        if (const char* env = getenv("SSHG_K3_NT")) {
+            if (atoi(env) == NT_BLUR) blur_nt = NT_BLUR;
+            else if (atoi(env) == NT_BLUR_WIDE && per_sm >= 1) blur_nt = NT_BLUR_WIDE;
+        }
         ba.radius = (int)radius;
-        ba.S = NT_BLUR * EPT + 2 * (int)radius;
+        ba.S = blur_nt * EPT + 2 * (int)radius;
         sshg_gaussian_taps(sigma_out, radius, ba.w);
-        blur_smem = (size_t)(BLUR_CHUNK * 12 + 2 * radius + 2 + (size_t)NA * ba.S) * sizeof(double);
-        SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)blur_smem));
+        blur_smem = blur_nt == NT_BLUR ? smem_for(NT_BLUR, BLUR_CHUNK) : wide;
+        if (blur_nt == NT_BLUR)
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR, BLUR_CHUNK>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
+        else
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
     }
-    const int blur_tiles = (int)((p->nE + NT_BLUR * EPT - 1) / (NT_BLUR * EPT));
+    const int blur_tiles = (int)((p->nE + blur_nt * EPT - 1) / (blur_nt * EPT));
     SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
 
     // un-broadened yields of columns [c0, c0 + nc) of the shard -> dst
@@ -889,7 +915,11 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.out = dst;
         b.y.n_tiles = blur_tiles;
         b.y.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
-        yield_blur_kernel<NT_BLUR><<<(unsigned)(nc * blur_tiles), NT_BLUR, blur_smem, st>>>(b);
+        if (blur_nt == NT_BLUR)
+            yield_blur_kernel<NT_BLUR, BLUR_CHUNK><<<(unsigned)(nc * blur_tiles), NT_BLUR, blur_smem, st>>>(b);
+        else
+            yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>
+                <<<(unsigned)(nc * blur_tiles), NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;

@@ -89,11 +89,12 @@ def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, co
 
 def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, mref=True, consts=None,
                       sinc_normalized=True, zzz_phi_quirk=True, t_range=None, d_range=None, stream=None,
-                      sigma_out=0.0):
+                      sigma_out=0.0, out_ptr=None):
     """Device-resident sweep: every array is a CUDA torch tensor (float64 / complex128), `out` a
     float64 CUDA tensor [T_shard, D_shard, 4, P, E] (allocated if None).  Asynchronous: the kernels
     are queued on torch's current stream (or `stream`).  sigma_out > 0: yields broadened along the
-    energy axis in the same pass (K3)."""
+    energy axis in the same pass (K3).  `out_ptr` (instead of `out`): a raw device address the shard is
+    written to -- e.g. `PeerCube.slab_ptr()`, the cube in another GPU's memory (returns None then)."""
     import torch
     ctx = _lib.context(energy.device.index)
     s = stream if stream is not None else torch.cuda.current_stream(energy.device)
@@ -108,12 +109,19 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
     shape = (p.t1 - p.t0, p.d1 - p.d0, 4, p.nP, p.nE)
     if tuple(eps1w.shape) != (3, p.nE) or tuple(eps2w.shape) != (3, p.nE) or tuple(chi2.shape) != (18, p.nE):
         raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
-    if out is None:
-        out = torch.empty(shape, dtype=torch.float64, device=energy.device)
-    elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
-        raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
-    _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), out.data_ptr(), _lib.DEVICE),
-               ctx.lib)
+    if out_ptr is not None:
+        if out is not None:
+            raise ValueError("pass either out or out_ptr")
+        if int(out_ptr) % 16:
+            raise ValueError("out_ptr must be 16-byte aligned")
+        dst = int(out_ptr)
+    else:
+        if out is None:
+            out = torch.empty(shape, dtype=torch.float64, device=energy.device)
+        elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
+            raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
+        dst = out.data_ptr()
+    _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), dst, _lib.DEVICE), ctx.lib)
     return out
 
 
@@ -126,7 +134,9 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
     `device` (default), else NumPy arrays.
 
     shard=(rank, world[, 'theta'|'thick']) computes only that rank's slab; with gather=True and an
-    initialised torch.distributed process group the slabs are gathered onto rank 0 (`gather_slabs`).
+    initialised torch.distributed process group the slabs are gathered onto rank 0 (`gather_slabs`, NCCL);
+    gather="peer" (theta shards on one node) instead lets every rank's kernel store its slab directly into
+    rank 0's cube over NVLink (`PeerCube`): no slab buffer, no collective.
     sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles); it is
     done inside the yield kernel (K3: the cube is written once).
     """
@@ -146,13 +156,26 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
             t_range = shard_bounds(theta.size, world, rank)
         else:
             d_range = shard_bounds(thick.size, world, rank)
-    if device:
+    if device and gather == "peer" and t_range is not None:
+        # the gather disappears into the kernel: every rank stores its theta slab straight into rank 0's cube
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", _lib.context().device)
+        put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
+        pc = PeerCube((theta.size, thick.size, 4, phi.size, energy.size), dst=0)
+        yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
+                          mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out, out_ptr=pc.slab_ptr(t_range[0]))
+        torch.cuda.synchronize()
+        dist.barrier()
+        cube = pc.tensor()
+        pc.close()
+    elif device:
         import torch
         dev = torch.device("cuda", _lib.context().device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
         cube = yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
                                  mref=mref, consts=consts, t_range=t_range, d_range=d_range, sigma_out=sigma_out)
-        if gather and shard is not None:
+        if gather and shard is not None:          # True, or "peer" on a thickness shard (not contiguous in the cube)
             cube = gather_slabs(cube, theta.size, thick.size, shard)
     else:
         cube = yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi_rot, mref=mref, consts=consts,
@@ -161,6 +184,96 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
     for k, pol in enumerate(POLS):
         res[pol] = cube[:, :, k] if cube is not None else None     # gather: only rank 0 holds the cube
     return res
+
+
+class _RawCuda:
+    """CUDA array interface over a raw device allocation (keeps its owner alive)."""
+
+    def __init__(self, ptr, shape, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+
+
+class PeerCube:
+    """The full yield cube [T, D, 4, P, E] in the HBM of rank `dst`, mapped into every rank of the node.
+
+    north_star's one exchange step is the gather of the theta slabs onto one GPU.  Here the destination
+    rank allocates the cube (through the library, so that it has a CUDA IPC handle), the handle travels
+    through torch.distributed, and every other rank maps the cube into its address space.  A rank then
+    passes `slab_ptr(t_lo)` as the output of the yield kernel: its 128-bit stores go over NVLink /
+    NVSwitch straight into the destination's memory -- the gather needs no slab buffer, no send/recv and
+    no extra pass.  Collective calls (every rank must take part): the constructor and `close`.
+    """
+
+    def __init__(self, shape, dst: int = 0):
+        import torch.distributed as dist
+        self.shape = tuple(int(x) for x in shape)
+        self.rank, self.dst = dist.get_rank(), int(dst)
+        self.ctx = _lib.context()
+        self.owner = self.rank == self.dst
+        self.ptr = None
+        nbytes = 8 * int(np.prod(self.shape, dtype=np.int64))
+        import torch
+        box, err = [None], None
+        if self.owner:
+            try:
+                p = C.c_void_p()
+                _lib.check(self.ctx.lib.sshg_device_alloc(self.ctx.handle, C.byref(p), nbytes), self.ctx.lib)
+                self.ptr = int(p.value)
+                h = C.create_string_buffer(_lib.IPC_HANDLE_BYTES)
+                _lib.check(self.ctx.lib.sshg_ipc_export(self.ctx.handle, C.c_void_p(self.ptr), h), self.ctx.lib)
+                box[0] = h.raw
+            except Exception as e:              # the peers are waiting in the broadcast: tell them
+                err = e
+        dist.broadcast_object_list(box, src=self.dst)
+        if box[0] is not None and not self.owner:
+            try:
+                p = C.c_void_p()
+                _lib.check(self.ctx.lib.sshg_ipc_open(self.ctx.handle, box[0], C.byref(p)), self.ctx.lib)
+                self.ptr = int(p.value)
+            except Exception as e:
+                err = e
+        # every rank must agree before anybody stores through the mapping
+        ok = torch.tensor([0 if (err is not None or self.ptr is None) else 1], device=torch.device("cuda", self.ctx.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            self._release()
+            raise RuntimeError("PeerCube: mapping the cube of rank %d failed on some rank%s"
+                               % (self.dst, (": %r" % (err,)) if err is not None else ""))
+
+    def slab_ptr(self, t_lo: int) -> int:
+        """Address of theta row `t_lo` of the cube (valid on every rank)."""
+        return self.ptr + 8 * int(t_lo) * int(np.prod(self.shape[1:], dtype=np.int64))
+
+    def tensor(self):
+        """The cube as a torch tensor on the destination rank (None elsewhere); the tensor keeps the
+        allocation alive."""
+        if not self.owner:
+            return None
+        import torch
+        return torch.as_tensor(_RawCuda(self.ptr, self.shape, self), device=torch.device("cuda", self.ctx.device))
+
+    def close(self):
+        """Peers unmap the cube (after their queued kernels finished); the owner's memory lives until the
+        tensor / this object is dropped."""
+        if not self.owner:
+            self._release()
+
+    def _release(self):
+        if not self.ptr:
+            return
+        if self.owner:
+            self.ctx.lib.sshg_device_free(self.ctx.handle, C.c_void_p(self.ptr))
+        else:
+            self.ctx.lib.sshg_ipc_close(self.ctx.handle, C.c_void_p(self.ptr))
+        self.ptr = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
 
 
 def broaden_energy_device(cube, sigma):

@@ -1,5 +1,6 @@
 """Worker of tests/test_gpu_multigpu.py (launched by torch.distributed.run, one rank per GPU):
-theta-sharded sweep, bitwise comparison of every shard with the single-GPU result, NCCL gather."""
+theta-sharded sweep, bitwise comparison of every shard with the single-GPU result, NCCL gather, and the
+gather by peer stores (every rank's kernel writes into rank 0's cube over NVLink)."""
 import os
 import sys
 
@@ -61,6 +62,24 @@ def main():
         ok = ok and bool(torch.equal(part, whole))
     else:
         ok = ok and part is None
+
+    # the gather without a collective: every rank's kernel stores its slab into rank 0's cube (CUDA IPC, NVLink)
+    pc = grid.PeerCube((11, 1, 4, 73, 1000), dst=0)
+    grid.yield_grid_device(*args, consts=consts, t_range=(lo, hi), out_ptr=pc.slab_ptr(lo))
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        ok = ok and bool(torch.equal(pc.tensor(), full_local))
+    else:
+        ok = ok and pc.tensor() is None
+    pc.close()
+    del pc
+    part = grid.shgyield_grid(shard=(rank, world), gather="peer", **kw)["cube"]     # with the output broadening (K3)
+    if rank == 0:
+        ok = ok and bool(torch.equal(part, whole))
+    else:
+        ok = ok and part is None
+    del part
 
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)

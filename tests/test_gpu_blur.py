@@ -59,15 +59,18 @@ BLUR_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("path", ["fused", "two_pass"])
+@pytest.mark.parametrize("path", ["fused", "fused64", "fused128", "two_pass"])
 @pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0])
 @pytest.mark.parametrize("nE,theta,phi,thick", BLUR_SHAPES, ids=[str(i) for i in range(len(BLUR_SHAPES))])
 def test_broadened_sweep_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, thick, sigma, path):
-    """radius 1, 5, 20 (the default sigma_out = 5) and 64 (the largest fused radius)."""
-    monkeypatch.setenv("SSHG_K3", "1" if path == "fused" else "0")
+    """radius 1, 5, 20 (the default sigma_out = 5) and 64 (the largest fused radius); K3 with the tile width
+    the library picks and with 128- / 256-energy tiles forced."""
+    monkeypatch.setenv("SSHG_K3", "0" if path == "two_pass" else "1")
+    if path in ("fused64", "fused128"):
+        monkeypatch.setenv("SSHG_K3_NT", path[5:])
     cfg = _small_cfg(nE, theta, phi, thick, seed=3)
     got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
-    _check(got, _blurred_oracle(cfg, consts, sigma), path == "fused", (nE, sigma, path))
+    _check(got, _blurred_oracle(cfg, consts, sigma), path != "two_pass", (nE, sigma, path))
 
 
 def test_sparse_phi_sweeps_and_large_radii_take_the_two_pass_path(grid, consts, monkeypatch):
