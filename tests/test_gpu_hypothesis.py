@@ -87,3 +87,33 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind):
         w = np.broadcast_to(want[pol], (nT, nD, phi.size, nE))
         ok, msg = cases.parity_ok(got[:, :, k], w, rtol=1e-10, scale=scale)
         assert ok, (seed, grid_kind, os.environ.get("SSHG_K2_SPARSE"), pol, msg)
+
+
+@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 900), nT=st.integers(1, 3), nD=st.integers(1, 2),
+       sigma=st.floats(0.13, 16.0), grid_kind=st.sampled_from(["paired", "paired_tail", "free"]),
+       tiles=st.sampled_from(["64", "128"]))
+def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
+    """K3 (yields broadened along E inside the kernel, both tile widths) on generated media / tensors /
+    grids against the oracle's broad(yield, sigma_out) -- absolute bound of the harmonic form plus the
+    parity metric with the relative window from 1e-4 of the maximum (tests/test_gpu_blur.py)."""
+    from shgyield_b200 import grid
+    from tests.test_gpu_blur import _check
+    rng = np.random.default_rng(seed)
+    energy, eps1w, eps2w, chi = _spectra(rng, nE)
+    theta = np.sort(rng.uniform(0, 90, nT))
+    thick = rng.uniform(0, 80, nD)
+    h = int(rng.integers(4, 12))
+    base = np.sort(rng.uniform(0, 180, h))
+    phi = {"paired": np.concatenate([base, base + 180.0]),
+           "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
+           "free": rng.uniform(0, 360, 2 * h + 1)}[grid_kind]
+    os.environ["SSHG_K3_NT"] = tiles
+    try:
+        got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS, sigma_out=sigma)
+    finally:
+        os.environ.pop("SSHG_K3_NT", None)
+    raw = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
+    want = np.stack([orc.gaussian_filter1d(np.broadcast_to(raw[p], (nT, nD, phi.size, nE)), sigma, axis=-1)
+                     for p in cases.POLS], axis=2)
+    _check(got, want, True, (seed, nE, sigma, grid_kind, tiles))
