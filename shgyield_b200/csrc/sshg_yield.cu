@@ -28,6 +28,12 @@ constexpr int EPT = 2;         // energies per thread
 constexpr int CHUNK_BIG = 384;    // phi items per shared-memory table chunk (18 KB)
 constexpr int CHUNK_SMALL = 256;  // ... 12 KB for the 64-thread CTAs (32 KB of shared memory each)
 constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
+#ifndef SSHG_NSEG_MAX
+#define SSHG_NSEG_MAX 2
+#endif
+#ifndef SSHG_NSEG_WAVES
+#define SSHG_NSEG_WAVES 7.0
+#endif
 
 struct YieldArgs {
     const double2* eps1w;      // [3][nE]
@@ -42,6 +48,7 @@ struct YieldArgs {
     long long col0;            // first local column of this launch (out points at it)
     int nTs, nDs, t0, d0;      // shard extents / offsets
     int n_tiles;
+    int n_seg;                 // the phi items of a column are cut into n_seg segments, one CTA each (short launches)
     int vec_ok;                // 128-bit stores allowed (nE even, out 16-B aligned)
     Physics ph;
 };
@@ -168,7 +175,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 
     const long long blk = blockIdx.x;
     const int tile = (int)(blk % a.n_tiles);
-    const long long lcol = blk / a.n_tiles;     // column within this launch
+    const int seg = (int)((blk / a.n_tiles) % a.n_seg);
+    const long long lcol = blk / a.n_tiles / a.n_seg;   // column within this launch
     const long long col = a.col0 + lcol;        // local column of the shard = tl * nDs + dl
     const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
     const int tid = threadIdx.x;
@@ -221,8 +229,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
         return c;
     };
 
-    for (long long base = 0; base < items; base += CHUNK) {
-        const int n_items = (int)min((long long)CHUNK, items - base);
+    const long long seg_len = (items + a.n_seg - 1) / a.n_seg;
+    const long long seg_hi = min(items, (seg + 1) * seg_len);
+    for (long long base = seg * seg_len; base < seg_hi; base += CHUNK) {
+        const int n_items = (int)min((long long)CHUNK, seg_hi - base);
         __syncthreads();                        // previous chunk fully consumed; columns parked
         for (int i = tid; i < n_items * 6; i += NT) tabs[i] = a.tab[1 + base * 6 + i];
         __syncthreads();
@@ -287,10 +297,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 // (C) sweeps the azimuth, phi / phi + 180 deg pairs sharing the even and odd harmonic sums.
 // Accuracy: the sum of harmonics cancels where the yield has a node in phi, so the error is absolute --
 // a few 1e-15 of the column's azimuthal mean -- instead of relative (tests/test_hostmath.py).
-constexpr int NT_BLUR = 64;                     // 128-energy tiles, 3 CTAs/SM at radius 20
-constexpr int BLUR_CHUNK = 128;                 // phi items per table chunk (12 doubles each: 12 KB)
-constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM
-constexpr int BLUR_CHUNK_WIDE = 16;
+constexpr int NT_BLUR = 64;                     // 128-energy tiles
+constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 28
 constexpr int NA = 3 * NH + NH_SS;              // harmonic spectra per column (46)
 constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
 
@@ -298,6 +306,7 @@ struct BlurArgs {
     YieldArgs y;                                // y.tab: harmonic table, 12 doubles per item
     int radius;
     int S;                                      // staged energies per CTA = 2 NT + 2 radius
+    int chunk;                                  // phi items per table chunk (what fits behind the parked harmonics)
     double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
 };
 
@@ -419,18 +428,21 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
     }
 }
 
-template <int NT, int BLUR_CHUNK>
+// shared memory: wf[2 R + 2] | raw[NA][S], later blur[NA][2 NT] in its place | ... up to the end of the allocation;
+// the phi table chunks live behind blur (the tail of raw is dead by then).
+template <int NT>
 __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
     extern __shared__ double smem[];
     const YieldArgs& a = b.y;
-    const int R = b.radius, S = b.S;
-    double* tabs = smem;                        // [BLUR_CHUNK][12]
-    double* wf = tabs + BLUR_CHUNK * 12;        // [2 R + 2] full taps (padded to an even count)
+    const int R = b.radius, S = b.S, BLUR_CHUNK = b.chunk;
+    double* wf = smem;                          // [2 R + 2] full taps (padded to an even count)
     double* raw = wf + 2 * R + 2;               // [NA][S]
+    double* tabs = raw + NA * NT * EPT;         // [chunk][12], valid once every FIR has been done
 
     const long long blk = blockIdx.x;
     const int tile = (int)(blk % a.n_tiles);
-    const long long lcol = blk / a.n_tiles;
+    const int seg = (int)((blk / a.n_tiles) % a.n_seg);
+    const long long lcol = blk / a.n_tiles / a.n_seg;
     const long long col = a.col0 + lcol;
     const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
     const int tid = threadIdx.x;
@@ -490,24 +502,49 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
     const bool vec = a.vec_ok != 0;
     const long long rows_per_pol = a.nP * nE;
     double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+    const long long seg_len = (items + a.n_seg - 1) / a.n_seg;
+    const long long seg_hi = min(items, (seg + 1) * seg_len);
 
+    // ---- (B) broadened harmonics of this thread's two energies, parked in place of the raw spectra -----------
+    // blur[m][2 NT] aliases the start of raw: spectrum m's slot lies inside raw rows <= m, which every thread
+    // has finished reading once the barrier after that polarisation's FIR is passed; later polarisations'
+    // raw rows are untouched.  Each thread only ever reads back the two values it wrote itself.
+    constexpr int TE = NT * EPT;
+    double* blur = raw + tid * EPT;
 #pragma unroll 1
     for (int pol = 0; pol < 4; ++pol) {
-        // ---- (B) broadened harmonics of this thread's two energies ---------------------------------------
         double A0[NH], A1[NH];
         const double* x = raw + (pol * NH) * S + tid * EPT;
         if (pol == 3) fir_pair<NH_SS>(x, S, R, wf, A0, A1);
         else fir_pair<NH>(x, S, R, wf, A0, A1);
-        double* prow = out_col + pol * rows_per_pol;
-        // ---- (C) azimuthal sweep, table chunk by chunk ---------------------------------------------------
-        for (long long base = 0; base < items; base += BLUR_CHUNK) {
-            const int n_items = (int)min((long long)BLUR_CHUNK, items - base);
-            __syncthreads();                    // previous chunk fully consumed
-            for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
-            __syncthreads();
-            if (!active) continue;
-            const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
-            const int n_single = n_items - n_pair;
+        __syncthreads();
+        const int nh = pol == 3 ? NH_SS : NH;
+#pragma unroll
+        for (int m = 0; m < NH; ++m)
+            if (m < nh) *reinterpret_cast<double2*>(blur + (pol * NH + m) * TE) = make_double2(A0[m], A1[m]);
+    }
+
+    // ---- (C) azimuthal sweep: table chunk by chunk, the four polarisations per chunk -----------------------
+    for (long long base = seg * seg_len; base < seg_hi; base += BLUR_CHUNK) {
+        const int n_items = (int)min((long long)BLUR_CHUNK, seg_hi - base);
+        __syncthreads();                        // previous chunk fully consumed
+        for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
+        __syncthreads();
+        if (!active) continue;
+        const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
+        const int n_single = n_items - n_pair;
+#pragma unroll 1
+        for (int pol = 0; pol < 4; ++pol) {
+            double A0[NH], A1[NH];
+            const int nh = pol == 3 ? NH_SS : NH;
+#pragma unroll
+            for (int m = 0; m < NH; ++m)
+                if (m < nh) {
+                    const double2 v = *reinterpret_cast<const double2*>(blur + (pol * NH + m) * TE);
+                    A0[m] = v.x;
+                    A1[m] = v.y;
+                }
+            double* prow = out_col + pol * rows_per_pol;
             double* plo = prow + base * nE;
             double* phi_ = prow + (base + H) * nE;
             double* psg = prow + (base + n_pair + H) * nE;
@@ -802,6 +839,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         else if (atoi(env) == NT_BIG) nt = NT_BIG;
     }
     a.n_tiles = (int)((p->nE + nt * EPT - 1) / (nt * EPT));
+    a.n_seg = 1;
     a.ph = make_physics(p->phys);
 
     const int64_t cols = (int64_t)a.nTs * a.nDs;
@@ -841,40 +879,65 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     BlurArgs ba{};
     size_t blur_smem = 0;
-    // Tile width: 256-energy tiles (128 threads) halve the halo overhead and measured 0.94 of the HBM peak
-    // against 0.89 on a 46-theta shard of config 5 -- as long as two of them fit on an SM (radius <= 22);
-    // beyond that 128-energy tiles (3 .. 2 CTAs/SM) win.  SSHG_K3_NT=64|128 overrides (tuning).
-    int blur_nt = NT_BLUR;
-    auto smem_for = [&](int nt, int chunk) {
-        return (size_t)(chunk * 12 + 2 * radius + 2 + (size_t)NA * (nt * EPT + 2 * radius)) * sizeof(double);
-    };
+    // Tile width and shared-memory plan of K3.  A CTA needs wf[2 R + 2] + raw[46][tile + 2 R]; once the FIRs are
+    // done only blur[46][tile] of that is live and the phi table chunks use everything behind it.  256-energy
+    // tiles (128 threads) halve the halo overhead and measured 0.94 of the HBM peak against 0.89 on a 46-theta
+    // shard of config 5 -- as long as two of them fit on an SM (radius <= 28); beyond that 128-energy tiles
+    // (3 .. 2 CTAs/SM).  The allocation is grown up to the occupancy's share of the SM so that the table chunks
+    // are as long as possible (each chunk costs two CTA-wide barriers).  SSHG_K3_NT=64|128 overrides (tuning).
+    int blur_nt = NT_BLUR, blur_per_sm = 1;
     if (fused) {
-        const size_t wide = smem_for(NT_BLUR_WIDE, BLUR_CHUNK_WIDE);
-        int per_sm = 0;
-        if (wide <= (size_t)227 * 1024) {
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wide));
-            SSHG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
-                                                                    NT_BLUR_WIDE, wide));
-        }
-        if (per_sm >= 2 && p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
+        const size_t sm_bytes = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
+        auto need = [&](int nt) { return (size_t)(2 * radius + 2 + (size_t)NA * (nt * EPT + 2 * radius)) * sizeof(double); };
+        auto share = [&](int per_sm) { return sm_bytes / per_sm - 1024; };     // 1 KB per CTA is reserved by the system
+        const bool wide_fits2 = need(NT_BLUR_WIDE) <= share(2);
+        if (wide_fits2 && p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
         if (const char* env = getenv("SSHG_K3_NT")) {
             if (atoi(env) == NT_BLUR) blur_nt = NT_BLUR;
-            else if (atoi(env) == NT_BLUR_WIDE && per_sm >= 1) blur_nt = NT_BLUR_WIDE;
+            else if (atoi(env) == NT_BLUR_WIDE && need(NT_BLUR_WIDE) <= cta_max) blur_nt = NT_BLUR_WIDE;
         }
+        const int reg_limit = blur_nt == NT_BLUR ? 4 : 2;                      // 212 registers per thread
+        blur_per_sm = 1;
+        for (int k = reg_limit; k >= 1; --k)
+            if (need(blur_nt) <= share(k)) { blur_per_sm = k; break; }
+        if (blur_nt == NT_BLUR && blur_per_sm > 3) blur_per_sm = 3;            // more table, fewer barriers
+        // grow the allocation to this occupancy's share, but not beyond what the whole table needs
+        const size_t live = (size_t)(2 * radius + 2 + (size_t)NA * blur_nt * EPT) * sizeof(double);
+        const size_t items_max = (size_t)p->nP;                                // un-paired grid: one item per phi
+        size_t total = live + items_max * 12 * sizeof(double);
+        if (total > share(blur_per_sm)) total = share(blur_per_sm);
+        if (total < need(blur_nt)) total = need(blur_nt);
+        if (total > cta_max) total = cta_max;
+        blur_smem = total & ~(size_t)15;
         ba.radius = (int)radius;
         ba.S = blur_nt * EPT + 2 * (int)radius;
+        ba.chunk = (int)((blur_smem - live) / (12 * sizeof(double)));
+        SSHG_REQUIRE(ba.chunk >= 1 && blur_smem >= need(blur_nt), "sshg_yield: internal: K3 shared-memory plan");
         sshg_gaussian_taps(sigma_out, radius, ba.w);
-        blur_smem = blur_nt == NT_BLUR ? smem_for(NT_BLUR, BLUR_CHUNK) : wide;
         if (blur_nt == NT_BLUR)
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR, BLUR_CHUNK>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)blur_smem));
         else
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)blur_smem));
     }
     const int blur_tiles = (int)((p->nE + blur_nt * EPT - 1) / (blur_nt * EPT));
     SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
+
+    // Short launches: a CTA that is left alone at the end of a launch still needs its full azimuthal sweep
+    // (~40-75 us), and every CTA starts with a store-free setup phase.  Cutting the phi items of a column
+    // into segments (one CTA each, the setup is repeated) shortens both.  SSHG_NSEG overrides (tuning).
+    auto pick_segments = [&](int64_t ctas, int per_sm, double below_waves) -> int {
+        if (const char* env = getenv("SSHG_NSEG")) {
+            const int v = atoi(env);
+            return v < 1 ? 1 : (v > 16 ? 16 : v);
+        }
+        const double waves = (double)ctas / ((double)ctx->num_sms * per_sm);
+        const long long items = p->nP - p->nP / 2;
+        int ns = 1;
+        while (ns < SSHG_NSEG_MAX && waves < below_waves && items / (2 * ns) >= 32) ns *= 2;
+        return ns;
+    };
 
     // un-broadened yields of columns [c0, c0 + nc) of the shard -> dst
     auto launch_raw = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
@@ -898,11 +961,13 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.col0 = c0;
         b.out = dst;
         b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
+        b.n_seg = pick_segments(nc * a.n_tiles, nt == NT_BIG ? 2 : 6, SSHG_NSEG_WAVES);
+        SSHG_REQUIRE(nc * a.n_tiles * b.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
+        const unsigned ctas = (unsigned)(nc * a.n_tiles * b.n_seg);
         if (nt == NT_BIG)
-            yield_grid_kernel<NT_BIG, CHUNK_BIG><<<(unsigned)(nc * a.n_tiles), NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
+            yield_grid_kernel<NT_BIG, CHUNK_BIG><<<ctas, NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
         else
-            yield_grid_kernel<NT_SMALL, CHUNK_SMALL>
-                <<<(unsigned)(nc * a.n_tiles), NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
+            yield_grid_kernel<NT_SMALL, CHUNK_SMALL><<<ctas, NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
@@ -915,11 +980,14 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.out = dst;
         b.y.n_tiles = blur_tiles;
         b.y.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
+        b.y.n_seg = pick_segments(nc * blur_tiles, blur_per_sm, 0.0);        // K3's setup (halo, harmonics, FIR) is too
+                                                                            // heavy to repeat: measured slower (tuning only)
+        SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
+        const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
-            yield_blur_kernel<NT_BLUR, BLUR_CHUNK><<<(unsigned)(nc * blur_tiles), NT_BLUR, blur_smem, st>>>(b);
+            yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
         else
-            yield_blur_kernel<NT_BLUR_WIDE, BLUR_CHUNK_WIDE>
-                <<<(unsigned)(nc * blur_tiles), NT_BLUR_WIDE, blur_smem, st>>>(b);
+            yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
