@@ -1,0 +1,283 @@
+// K3 device code: the yield cube broadened along the energy axis inside the yield kernel.
+// Included by sshg_yield.cu inside its anonymous namespace (uses YieldArgs, EPT, store2, ldc and the
+// physics of sshg_math.cuh); the host-side plan (tile width, shared-memory budget, fallbacks) is in
+// sshg_yield.cu::yield_impl.
+#pragma once
+
+// ---- K3: the yield cube broadened along the energy axis (sigma_out > 0), in ONE pass --------------------
+// The reference broadens every yield spectrum after the fact (broad(., sigma_out), shg.py:26-28, 433-436;
+// sigma_out = 5 is the API default).  Done literally on a cube that is a second pass over HBM (read 8 B +
+// write 8 B per point) and 2 radius + 1 FMAs per point -- 3.7x the cost of K2.  Here the broadening is
+// moved in front of the azimuthal sweep instead: |r(phi)|^2 is a trigonometric polynomial of degree 6 in
+// phi (sshg_math.cuh::harmonics7), the Gaussian FIR along E is linear, so it is applied to the 13 (sS: 7)
+// harmonic spectra of a column -- 46 FIRs per (theta, d) column instead of 4 nP -- and each point is then
+// a 13-term real sum.  Per point that is 7 FP64 instructions (sS: 3) against 10 (5) in K2, so the broadened
+// cube is again bound by its 8 B/point store stream.
+//
+// A CTA of NT threads owns 2 NT consecutive energies of a column.  (A) it evaluates column setup +
+// coefficients + harmonics for those energies plus a halo of `radius` on each side ('reflect' boundary of
+// scipy.ndimage at the ends of the axis) into shared memory, raw[46][S]; (B) per polarisation every
+// thread filters the harmonic spectra for its two energies (one LDS.128 feeds 4 FMAs) and parks the
+// results in shared memory in place of the raw spectra, which are dead by then; (C) the azimuth is swept
+// table chunk by table chunk (the chunks live behind the parked harmonics, so they are as long as the
+// CTA's shared-memory share allows), four polarisations per chunk, phi / phi + 180 deg pairs sharing the
+// even and odd harmonic sums.
+// Accuracy: the sum of harmonics cancels where the yield has a node in phi, so the error is absolute --
+// a few 1e-15 of the column's azimuthal mean -- instead of relative (tests/test_hostmath.py).
+constexpr int NT_BLUR = 64;                     // 128-energy tiles
+constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 28
+constexpr int NA = 3 * NH + NH_SS;              // harmonic spectra per column (46)
+constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
+
+struct BlurArgs {
+    YieldArgs y;                                // y.tab: harmonic table, 12 doubles per item
+    int radius;
+    int S;                                      // staged energies per CTA = 2 NT + 2 radius
+    int chunk;                                  // phi items per table chunk (what fits behind the parked harmonics)
+    double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
+};
+
+__global__ void phi_harm_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
+                                      int allow_pairs) {
+    __shared__ int bad;
+    const long long H = nP / 2;
+    if (threadIdx.x == 0) bad = (allow_pairs && H > 0) ? 0 : 1;
+    __syncthreads();
+    if (allow_pairs && H > 0) {
+        int mybad = 0;
+        for (long long j = threadIdx.x; j < H; j += blockDim.x)
+            if (phi[j + H] != phi[j] + 180.0) mybad = 1;
+        if (mybad) bad = 1;
+    }
+    __syncthreads();
+    const long long h = bad ? 0 : H;
+    if (threadIdx.x == 0) tab[0] = (double)h;
+    const long long items = nP - h;
+    for (long long i = threadIdx.x; i < items; i += blockDim.x) {
+        double t[12];
+        phi_harmonics(phi[i < h ? i : i + h], t);
+#pragma unroll
+        for (int k = 0; k < 12; ++k) tab[2 + i * 12 + k] = t[k];     // items start 16-byte aligned
+    }
+}
+
+__device__ __forceinline__ long long reflect_index(long long i, long long n) {
+    if (i >= 0 && i < n) return i;
+    long long m = i % (2 * n);
+    if (m < 0) m += 2 * n;
+    return m >= n ? 2 * n - 1 - m : m;
+}
+
+// (B) Gaussian FIR of NHH harmonic spectra for two adjacent energies: x points at this thread's window
+// x[0 .. 2 R + 1] of the first spectrum (spectra are S doubles apart), wf[0 .. 2 R] are the full taps.
+// out0 = sum_t wf[t] x[t], out1 = sum_t wf[t] x[t + 1].  Absent taps at the two ends are skipped, not
+// multiplied by zero (a NaN sample must not spread beyond the radius).
+template <int NHH>
+__device__ __forceinline__ void fir_pair(const double* __restrict__ x, int S, int R, const double* __restrict__ wf,
+                                         double* A0, double* A1) {
+    {
+        const double w0 = wf[0], w1 = wf[1];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S);
+            A0[m] = fma(v.y, w1, v.x * w0);
+            A1[m] = v.y * w0;
+        }
+    }
+#pragma unroll 1
+    for (int j = 1; j < R; ++j) {
+        const double wa = wf[2 * j - 1], wb = wf[2 * j], wc = wf[2 * j + 1];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S + 2 * j);
+            A0[m] = fma(v.y, wc, fma(v.x, wb, A0[m]));
+            A1[m] = fma(v.y, wb, fma(v.x, wa, A1[m]));
+        }
+    }
+    {
+        const double wa = wf[2 * R - 1], wb = wf[2 * R];
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S + 2 * R);
+            A0[m] = fma(v.x, wb, A0[m]);
+            A1[m] = fma(v.y, wb, fma(v.x, wa, A1[m]));
+        }
+    }
+}
+
+// (C) azimuthal sweep of the harmonic form, two energies per thread.  tb: items of 12 doubles
+// {cos, sin of 2, 4, 6 phi | cos, sin of 1, 3, 5 phi}.
+template <bool SS>
+__device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
+                                           int n_pair, int n_single, double* plo, double* phi_, double* psg,
+                                           long long stride, bool vec, bool valid1) {
+#pragma unroll 2
+    for (int i = 0; i < n_pair + n_single; ++i) {
+        double t[12];
+#pragma unroll
+        for (int j = 0; j < (SS ? 3 : 6); ++j) {
+            const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
+            t[2 * j] = v.x;
+            t[2 * j + 1] = v.y;
+        }
+        tb += 12;
+        double ye0 = A0[0], ye1 = A1[0];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            ye0 = fma(A0[1 + j], t[j], ye0);
+            ye1 = fma(A1[1 + j], t[j], ye1);
+        }
+        double yo0 = 0.0, yo1 = 0.0;
+        if (!SS) {
+            yo0 = A0[7] * t[6];
+            yo1 = A1[7] * t[6];
+#pragma unroll
+            for (int j = 1; j < 6; ++j) {
+                yo0 = fma(A0[7 + j], t[6 + j], yo0);
+                yo1 = fma(A1[7 + j], t[6 + j], yo1);
+            }
+        }
+        if (i < n_pair) {
+            if (SS) {
+                store2(plo, ye0, ye1, vec, valid1);
+                store2(phi_, ye0, ye1, vec, valid1);
+            } else {
+                store2(plo, ye0 + yo0, ye1 + yo1, vec, valid1);
+                store2(phi_, ye0 - yo0, ye1 - yo1, vec, valid1);
+            }
+            plo += stride;
+            phi_ += stride;
+        } else {
+            if (SS) store2(psg, ye0, ye1, vec, valid1);
+            else store2(psg, ye0 + yo0, ye1 + yo1, vec, valid1);
+            psg += stride;
+        }
+    }
+}
+
+// shared memory: wf[2 R + 2] | raw[NA][S], later blur[NA][2 NT] in its place | ... up to the end of the allocation;
+// the phi table chunks live behind blur (the tail of raw is dead by then).
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
+    extern __shared__ double smem[];
+    const YieldArgs& a = b.y;
+    const int R = b.radius, S = b.S, BLUR_CHUNK = b.chunk;
+    double* wf = smem;                          // [2 R + 2] full taps (padded to an even count)
+    double* raw = wf + 2 * R + 2;               // [NA][S]
+    double* tabs = raw + NA * NT * EPT;         // [chunk][12], valid once every FIR has been done
+
+    const long long blk = blockIdx.x;
+    const int tile = (int)(blk % a.n_tiles);
+    const int seg = (int)((blk / a.n_tiles) % a.n_seg);
+    const long long lcol = blk / a.n_tiles / a.n_seg;
+    const long long col = a.col0 + lcol;
+    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+    const int tid = threadIdx.x;
+    const long long nE = a.nE;
+    const long long tile_e0 = (long long)tile * NT * EPT;
+
+    for (int t = tid; t <= 2 * R; t += NT) wf[t] = b.w[t < R ? R - t : t - R];
+
+    // ---- (A) harmonic spectra of the staged energies (tile + halo) --------------------------------------
+    {
+        double st, ct;
+        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
+        const double thick = a.thick_nm[a.d0 + dl];
+#pragma unroll 1
+        for (int i = tid; i < S; i += NT) {
+            const long long g = tile_e0 - R + i;
+            if (g >= nE + R) break;             // no output of this axis reaches that far
+            const long long e = reflect_index(g, nE);
+            cplx e1[3], e2[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                e1[m] = ldc(a.eps1w + m * nE + e);
+                e2[m] = ldc(a.eps2w + m * nE + e);
+            }
+            const Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
+            auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+            double* dst = raw + i;
+#pragma unroll 1
+            for (int pol = 0; pol < 4; ++pol) {
+                if (pol == 3) {
+                    cplx kk[4];
+                    coeffs_ss(c, chi, kk);
+                    double H[NH_SS];
+                    harmonics4(kk, H);
+#pragma unroll
+                    for (int m = 0; m < NH_SS; ++m) dst[(3 * NH + m) * S] = H[m];
+                } else {
+                    cplx kk[7];
+                    if (pol == 0) coeffs_pp(c, chi, a.ph, kk);
+                    else if (pol == 1) coeffs_ps(c, chi, kk);
+                    else coeffs_sp(c, chi, kk);
+                    double H[NH];
+                    harmonics7(kk, H);
+#pragma unroll
+                    for (int m = 0; m < NH; ++m) dst[(pol * NH + m) * S] = H[m];
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const long long e0 = tile_e0 + (long long)tid * EPT;
+    const bool active = e0 < nE;
+    const bool valid1 = e0 + 1 < nE;
+    const long long H = (long long)a.tab[0];
+    const long long items = a.nP - H;
+    const bool vec = a.vec_ok != 0;
+    const long long rows_per_pol = a.nP * nE;
+    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+    const long long seg_len = (items + a.n_seg - 1) / a.n_seg;
+    const long long seg_hi = min(items, (seg + 1) * seg_len);
+
+    // ---- (B) broadened harmonics of this thread's two energies, parked in place of the raw spectra -----------
+    // blur[m][2 NT] aliases the start of raw: spectrum m's slot lies inside raw rows <= m, which every thread
+    // has finished reading once the barrier after that polarisation's FIR is passed; later polarisations'
+    // raw rows are untouched.  Each thread only ever reads back the two values it wrote itself.
+    constexpr int TE = NT * EPT;
+    double* blur = raw + tid * EPT;
+#pragma unroll 1
+    for (int pol = 0; pol < 4; ++pol) {
+        double A0[NH], A1[NH];
+        const double* x = raw + (pol * NH) * S + tid * EPT;
+        if (pol == 3) fir_pair<NH_SS>(x, S, R, wf, A0, A1);
+        else fir_pair<NH>(x, S, R, wf, A0, A1);
+        __syncthreads();
+        const int nh = pol == 3 ? NH_SS : NH;
+#pragma unroll
+        for (int m = 0; m < NH; ++m)
+            if (m < nh) *reinterpret_cast<double2*>(blur + (pol * NH + m) * TE) = make_double2(A0[m], A1[m]);
+    }
+
+    // ---- (C) azimuthal sweep: table chunk by chunk, the four polarisations per chunk -----------------------
+    for (long long base = seg * seg_len; base < seg_hi; base += BLUR_CHUNK) {
+        const int n_items = (int)min((long long)BLUR_CHUNK, seg_hi - base);
+        __syncthreads();                        // previous chunk fully consumed
+        for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
+        __syncthreads();
+        if (!active) continue;
+        const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
+        const int n_single = n_items - n_pair;
+#pragma unroll 1
+        for (int pol = 0; pol < 4; ++pol) {
+            double A0[NH], A1[NH];
+            const int nh = pol == 3 ? NH_SS : NH;
+#pragma unroll
+            for (int m = 0; m < NH; ++m)
+                if (m < nh) {
+                    const double2 v = *reinterpret_cast<const double2*>(blur + (pol * NH + m) * TE);
+                    A0[m] = v.x;
+                    A1[m] = v.y;
+                }
+            double* prow = out_col + pol * rows_per_pol;
+            double* plo = prow + base * nE;
+            double* phi_ = prow + (base + H) * nE;
+            double* psg = prow + (base + n_pair + H) * nE;
+            if (pol == 3) sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+            else sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+        }
+    }
+}
+

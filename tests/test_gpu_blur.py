@@ -177,3 +177,17 @@ def test_config5_shard_broadened_full_rows_vs_oracle(grid, consts):
         for k, pol in enumerate(cases.POLS):
             want = orc.gaussian_filter1d(raw[pol], 5.0, axis=-1)
             assert np.max(np.abs(got[k] - want)) < 1e-13 * np.max(want), (it, pol)
+
+
+@pytest.mark.parametrize("nseg", ["2", "3", "5", "16"])
+@pytest.mark.parametrize("sigma", [0.0, 2.0])
+def test_phi_segments_change_nothing(grid, consts, monkeypatch, nseg, sigma):
+    """Short launches cut the phi items of a column into segments, one CTA each (K2; K3 under SSHG_NSEG):
+    uneven splits, more segments than items, pairs + un-paired tail -- bitwise the un-segmented result."""
+    for phi in (np.arange(0, 360, 2.5), np.linspace(0, 360, 41), np.linspace(0, 350, 7)):
+        cfg = _small_cfg(300, [20.0, 70.0], phi, [10.0], seed=9)
+        monkeypatch.setenv("SSHG_NSEG", "1")
+        one = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
+        monkeypatch.setenv("SSHG_NSEG", nseg)
+        many = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
+        assert np.array_equal(one, many), (nseg, sigma, phi.size)
