@@ -23,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=true",
     "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden",
-    "-shared",
+    "-shared", "-ldl",
 ]
 
 

@@ -357,6 +357,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
 
 extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_t rows, int64_t n,
                             int64_t row_stride, int64_t elem_stride, double sigma, int where) {
+    SSHG_TRACE("sshg_gauss1d");
     SSHG_REQUIRE(ctx && in && out, "sshg_gauss1d: null argument");
     SSHG_REQUIRE(in != out, "sshg_gauss1d: in-place filtering is not supported");
     SSHG_REQUIRE(rows > 0 && n > 0, "sshg_gauss1d: rows and n must be positive");

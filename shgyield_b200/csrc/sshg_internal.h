@@ -5,6 +5,17 @@
 #include <stddef.h>
 #include "../../include/sshg.h"
 
+// Tracing: every compute entry point of the C ABI is an NVTX range (header-only NVTX 3; a no-op unless a
+// profiler is attached), e.g. `ncu --nvtx --nvtx-include "sshg_yield/" ...` profiles only the yield kernels.
+#include <nvtx3/nvToolsExt.h>
+struct sshg_trace_range {
+    explicit sshg_trace_range(const char* name) { nvtxRangePushA(name); }
+    ~sshg_trace_range() { nvtxRangePop(); }
+    sshg_trace_range(const sshg_trace_range&) = delete;
+    sshg_trace_range& operator=(const sshg_trace_range&) = delete;
+};
+#define SSHG_TRACE(name) sshg_trace_range sshg_trace_range_(name)
+
 #define SSHG_NSCRATCH 24
 #define SSHG_TAP_HOST 64
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)

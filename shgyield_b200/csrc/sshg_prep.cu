@@ -277,6 +277,7 @@ static uint64_t axis_hash_of(const double* x, int64_t n) {
 
 extern "C" int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out, int64_t nE, double gamma_deg,
                            int xxy_quirk, int where) {
+    SSHG_TRACE("sshg_rotate");
     SSHG_REQUIRE(ctx && chi_in && chi_out, "sshg_rotate: null argument");
     SSHG_REQUIRE(nE > 0, "sshg_rotate: nE must be positive");
     SSHG_REQUIRE(chi_in != chi_out, "sshg_rotate: in-place rotation is not supported");
@@ -318,6 +319,7 @@ extern "C" int sshg_rotate(sshg_ctx* ctx, const double* chi_in, double* chi_out,
 
 extern "C" int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
                                     const double* xq, int64_t nq, double* out, int where) {
+    SSHG_TRACE("sshg_spline_resample");
     SSHG_REQUIRE(ctx && x && y && xq && out, "sshg_spline_resample: null argument");
     SSHG_REQUIRE(rows > 0 && nq > 0, "sshg_spline_resample: rows and nq must be positive");
     SSHG_REQUIRE(n >= 4, "sshg_spline_resample: a cubic interpolating spline needs at least 4 samples (got %lld)",
@@ -391,6 +393,7 @@ static int spline_finish(sshg_ctx* ctx, void* dflag, void* dout, double* out, si
 // rows stay on the device between K1 and the spline kernels.
 extern "C" int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const double* y, int64_t rows, int64_t n,
                                      double sigma, const double* xq, int64_t nq, double* out, int where) {
+    SSHG_TRACE("sshg_broaden_resample");
     SSHG_REQUIRE(ctx && x && y && xq && out, "sshg_broaden_resample: null argument");
     SSHG_REQUIRE(rows > 0 && nq > 0, "sshg_broaden_resample: rows and nq must be positive");
     SSHG_REQUIRE(n >= 4, "sshg_broaden_resample: a cubic interpolating spline needs at least 4 samples (got %lld)",

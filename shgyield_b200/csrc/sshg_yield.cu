@@ -493,6 +493,7 @@ constexpr size_t grid_smem(int nt, int chunk) { return (size_t)(chunk * 6 + EPT 
 }  // namespace
 
 static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where) {
+    SSHG_TRACE("sshg_yield");
     SSHG_REQUIRE(ctx && p && out, "sshg_yield: null argument");
     SSHG_REQUIRE(sigma_out >= 0.0 && isfinite(sigma_out), "sshg_yield: sigma_out must be finite and >= 0 (got %g)",
                  sigma_out);
@@ -784,6 +785,7 @@ extern "C" int sshg_yield_broadened(sshg_ctx* ctx, const sshg_problem* p, double
 }
 
 static int points_impl(sshg_ctx* ctx, const sshg_points* p, double* out, int where, bool amp) {
+    SSHG_TRACE("sshg_yield_points");
     SSHG_REQUIRE(ctx && p && out, "sshg_yield_points: null argument");
     SSHG_REQUIRE(p->n > 0 && p->nE > 0, "sshg_yield_points: n and nE must be positive");
     SSHG_REQUIRE(p->energy_eV && p->eidx && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
