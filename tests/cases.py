@@ -140,6 +140,14 @@ MATERIALS = {"si111": si111_material, "full": full_tensor_material, "selftest": 
              "si111_nan": si111_nan_material}
 
 
+# ---- a sweep with the output broadening, produced by the reference angle by angle (ref_blur_rows.npz) ----
+BLUR_SWEEP = dict(energy=np.linspace(0.5, 5.0, 451), theta=np.array([0.0, 33.0, 65.0, 88.0]),
+                  phi=np.array([0.0, 29.98, 30.0, 77.0, 180.0, 209.98, 210.0, 257.0, 359.5]))
+BLUR_SWEEP_SIGMAS = (5.0, 1.5)
+BLUR_SWEEP_THICK = 10.0
+BLUR_SWEEP_GAMMA = {"si111": 0, "full": 33}
+
+
 # ---- sampled points of the large grids (configs 3, 4, 5 of BASELINE.json) --------------------
 def config3_axes():
     return dict(energy=np.linspace(0.005, 10.0, 2000), theta=np.arange(0, 90, dtype=np.float64),

@@ -14,6 +14,7 @@ Fixtures
   ref_helpers.npz            rotate / wvec / fresnel / mrc outputs on random inputs
   ref_grid_samples.npz       sampled points of configs 3, 4 (API level) and 5 (kernel level)
   constants.npz              the four scipy.constants values the reference read here
+  ref_blur_rows.npz          shg.shgyield(sigma_out > 0) called angle by angle on a sweep (`--blur` writes only this)
 """
 import os
 import sys
@@ -23,7 +24,9 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
-REF = sys.argv[1] if len(sys.argv) > 1 else "/root/reference"
+ONLY_BLUR = "--blur" in sys.argv
+_pos = [a for a in sys.argv[1:] if not a.startswith("--")]
+REF = _pos[0] if _pos else "/root/reference"
 sys.path.insert(0, REF)
 sys.path.insert(1, REPO)
 sys.dont_write_bytecode = True
@@ -40,7 +43,32 @@ def cols(path, skiprows=0):
     return np.loadtxt(path, unpack=True, skiprows=skiprows)
 
 
+def blur_rows():
+    """The reference's own output broadening on a sweep: shgyield() broadens every array it returns along ALL
+    its axes, so a sweep broadened along the energy axis alone is shgyield() called once per (theta, phi)."""
+    z = cases.load_spectra()
+    out = {}
+    for mat, gamma in (("si111", 0), ("full", 33)):
+        m1, m2, m3, chi2 = cases.MATERIALS[mat](z)
+        for k, (key, val) in enumerate(cases.BLUR_SWEEP.items()):
+            out[key] = np.asarray(val, dtype=np.float64)
+        E, TH, PH = cases.BLUR_SWEEP["energy"], cases.BLUR_SWEEP["theta"], cases.BLUR_SWEEP["phi"]
+        for sigma in cases.BLUR_SWEEP_SIGMAS:
+            cube = np.empty((len(TH), 4, len(PH), len(E)))
+            for it, th in enumerate(TH):
+                for ip, ph in enumerate(PH):
+                    res = ref.shgyield(energy=E, eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, theta=th, phi=ph,
+                                       thick=cases.BLUR_SWEEP_THICK, gamma=gamma, sigma_out=sigma)
+                    for k, pol in enumerate(cases.POLS):
+                        cube[it, k, ip] = res[pol]
+            out["%s_sigma%g" % (mat, sigma)] = cube
+    np.savez_compressed(os.path.join(HERE, "ref_blur_rows.npz"), **out)
+    print("ref_blur_rows.npz", os.path.getsize(os.path.join(HERE, "ref_blur_rows.npz")), "bytes")
+
+
 def main():
+    if ONLY_BLUR:
+        return blur_rows()
     # ---- spectra ---------------------------------------------------------------------------
     spectra = {}
     for name in ("SiBulk-chi1-xx", "SiBulk-chi1-yy", "SiBulk-chi1-zz",
@@ -144,6 +172,7 @@ def main():
         zz = fn(E, e1, e2, ch, np.radians(theta[it]), np.radians(phi[ip]), 10.0, True)
         gs["c5_" + pol] = pref * np.absolute(1 / np.sqrt(e1["M2"]) * zz) ** 2
     np.savez_compressed(os.path.join(HERE, "ref_grid_samples.npz"), **gs)
+    blur_rows()
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".npz"):
             print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(HERE, f))))

@@ -191,3 +191,24 @@ def test_phi_segments_change_nothing(grid, consts, monkeypatch, nseg, sigma):
         monkeypatch.setenv("SSHG_NSEG", nseg)
         many = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
         assert np.array_equal(one, many), (nseg, sigma, phi.size)
+
+
+@pytest.mark.parametrize("path", ["fused", "two_pass"])
+@pytest.mark.parametrize("mat", ["si111", "full"])
+def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
+    """shgyield_grid(sigma_out) against rows produced by the UNMODIFIED reference, shgyield() called once per
+    (theta, phi) (tests/golden/ref_blur_rows.npz; phi includes points 0.02 deg from the C3v nodes of Si(111))."""
+    monkeypatch.setenv("SSHG_K3", "1" if path == "fused" else "0")
+    z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](cases.load_spectra())
+    for sigma in cases.BLUR_SWEEP_SIGMAS:
+        res = grid.shgyield_grid(z["energy"], m1, m2, m3, chi2, z["theta"], z["phi"], cases.BLUR_SWEEP_THICK,
+                                 gamma=cases.BLUR_SWEEP_GAMMA[mat], sigma_out=sigma, device=False)
+        want = z["%s_sigma%g" % (mat, sigma)]                           # [T, 4, P, E]
+        got = res["cube"][:, 0]                                         # [T, 4, P, E]
+        top = float(np.max(want))
+        for k, pol in enumerate(cases.POLS):
+            ok, msg = cases.parity_ok(got[:, k], want[:, k], rtol=RTOL, scale=top, rel_floor=1e-4 if path == "fused" else 1e-6)
+            assert ok, (mat, sigma, path, pol, msg)
+            colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
+            assert np.max(np.abs(got[:, k] - want[:, k]) / colmax) < 5e-14, (mat, sigma, path, pol)

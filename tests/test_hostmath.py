@@ -220,3 +220,26 @@ def test_harmonic_form_commutes_with_output_broadening(harness, material, sigma)
             # the error of the harmonic form is absolute: a few 1e-15 of the column's maximum over phi
             colmax = np.maximum(want[pol].max(axis=0, keepdims=True), 1e-12 * sc)
             assert np.max(np.abs(got[i] - want[pol]) / colmax) < 5e-14, (material, sigma, theta, pol)
+
+
+@pytest.mark.parametrize("mat", ["si111", "full"])
+def test_harmonic_form_vs_reference_broadened_rows(harness, mat):
+    """K3's algorithm (CPU run of the kernel's own functions) against shgyield(sigma_out) of the UNMODIFIED
+    reference, called once per (theta, phi): tests/golden/ref_blur_rows.npz."""
+    consts = util.load_consts()
+    z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
+    E, TH, PH = z["energy"], z["theta"], z["phi"]
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](cases.load_spectra())
+    e1, e2, ch, thick = orc.prepare(E, m1, m2, m3, chi2, cases.BLUR_SWEEP_THICK, cases.BLUR_SWEEP_GAMMA[mat], 0.0, 0.0,
+                                    "3-layer")
+    eps1w, eps2w, chi = util.pack_eps(e1, E.size), util.pack_eps(e2, E.size), util.pack_chi(ch, E.size)
+    for sigma in cases.BLUR_SWEEP_SIGMAS:
+        want = z["%s_sigma%g" % (mat, sigma)]                           # [T, 4, P, E]
+        top = float(np.max(want))
+        for it, th in enumerate(TH):
+            got = _blur_column(harness, E, eps1w, eps2w, chi, th, thick, PH, sigma, consts)     # [4, P, E]
+            for k, pol in enumerate(cases.POLS):
+                ok, msg = cases.parity_ok(got[k], want[it, k], rtol=1e-10, scale=top, rel_floor=1e-4)
+                assert ok, (mat, sigma, th, pol, msg)
+                colmax = np.maximum(np.max(want[it, k], axis=0, keepdims=True), 1e-12 * top)
+                assert np.max(np.abs(got[k] - want[it, k]) / colmax) < 5e-14, (mat, sigma, th, pol)
