@@ -1,7 +1,8 @@
 """
 `python shgyield.py <input.yml>` -- the command line the reference's README documents
 (README.md:49-50).  Scalar theta / phi write the reference's text table (main.py:139-142);
-lists of theta / phi / thickness run a sweep on the GPU and write the cube to an .npz file.
+lists of theta / phi / thickness run a sweep on the GPU and write the cube to an .npz file; under
+`python -m torch.distributed.run --nproc-per-node N shgyield.py <input.yml>` the sweep is sharded over N GPUs.
 """
 from __future__ import annotations
 
@@ -30,7 +31,27 @@ def main(argv=None) -> int:
         print("wrote %s (%d energies x 4 polarisations)" % (out, np.size(res["energy"])))
         return 0
     from .grid import shgyield_grid
-    res = shgyield_grid(device=False, **cfg)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # launched by torch.distributed.run, one rank per GPU: theta (or thickness) shards, the cube gathered on
+        # rank 0 by peer stores over NVLink (theta shards) or NCCL (thickness shards); rank 0 writes the file
+        import torch
+        import torch.distributed as dist
+        rank, local = int(os.environ["RANK"]), int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        try:
+            res = shgyield_grid(device=True, shard=(rank, world), gather="peer", **cfg)
+            if rank == 0:
+                cube = res["cube"].cpu().numpy()
+                res = dict(res, cube=cube, **{pol: cube[:, :, k] for k, pol in enumerate(("pp", "ps", "sp", "ss"))})
+            dist.barrier()
+        finally:
+            dist.destroy_process_group()
+        if rank != 0:
+            return 0
+    else:
+        res = shgyield_grid(device=False, **cfg)
     if not out.endswith(".npz"):
         out = os.path.splitext(out)[0] + ".npz"
     np.savez(out, energy=res["energy"], theta=res["theta"], phi=res["phi"], thick=res["thick"],
