@@ -373,8 +373,12 @@ __global__ void __launch_bounds__(SNT, SSHG_SPARSE_MINB) yield_sparse_kernel(con
     const bool recur = a.dinfo[0] != 0.0 && a.ph.mref;
     const double d_step = a.dinfo[1];
     int tl_cur = -1;
+    int tl = (int)(c_lo / a.nDs), dl = (int)(c_lo % a.nDs) - 1;      // one division per run, not per column
     for (long long col = c_lo; col < c_hi; ++col) {
-        const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+        if (++dl == a.nDs) {
+            dl = 0;
+            ++tl;
+        }
         const double thick = a.thick_nm[a.d0 + dl];
         const bool fresh = tl != tl_cur;
         if (fresh) {                                       // new angle of incidence
