@@ -118,14 +118,19 @@ def cpu_baseline(target_s=12.0):
     try:
         pool.run(_cpu_tasks(cores))                                  # warm-up (imports, page faults)
         pts, dt = pool.run(_cpu_tasks(cores, cores))
-        rounds = max(1, min(40, int(target_s / max(dt, 1e-3))))
+        rounds = max(1, min(120, int(target_s / max(dt, 1e-3))))
         pts, dt = pool.run(_cpu_tasks(cores * rounds, 2 * cores))
     finally:
         pool.close()
+    # the reference itself is single-threaded: the same tasks on ONE core (SURVEY 8d asks for both figures)
+    _cpu_task(_cpu_tasks(1)[0])
+    t0 = time.perf_counter()
+    pts1 = sum(_cpu_task(t) for t in _cpu_tasks(4, 1))
+    dt1 = time.perf_counter() - t0
     return {"value": pts / dt, "unit": "points/s", "cores": cores, "kind": "port",
             "sample": "%d tasks of 1 theta x %d phi x %d E x 4 pol (%.3g points) of the same workload, "
                       "NumPy oracle port of shg.py, one process per core" % (cores * rounds, CPU_PHI_CHUNK, N_ENERGY, pts),
-            "seconds": dt}
+            "seconds": dt, "single_core_value": pts1 / dt1}
 
 
 def run_reference(args):
