@@ -117,3 +117,41 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     want = np.stack([orc.gaussian_filter1d(np.broadcast_to(raw[p], (nT, nD, phi.size, nE)), sigma, axis=-1)
                      for p in cases.POLS], axis=2)
     _check(got, want, True, (seed, nE, sigma, grid_kind, tiles))
+
+
+_SHAPES = [(), (1,), (5,), (3, 1), (2, 1, 1), (1, 4), (2, 3)]
+
+
+@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+@given(seed=st.integers(0, 2 ** 31 - 1), es=st.sampled_from([(), (7,), (40,), (2, 5)]), ts=st.sampled_from(_SHAPES),
+       ps=st.sampled_from(_SHAPES), ds=st.sampled_from([(), (1,), (3, 1, 1)]), sigma_out=st.sampled_from([0.0, 0.7, 2.0]),
+       mode=st.sampled_from(["3-layer", "2-layer", "fresnel"]), mref=st.booleans(), grid_path=st.booleans())
+def test_api_broadcast_shapes_random(seed, es, ts, ps, ds, sigma_out, mode, mref, grid_path):
+    """The drop-in shgyield() on generated NumPy-broadcast shapes of energy / theta / phi / thick (0-d to 3-d),
+    modes, gamma and sigmas -- points kernel and grid kernel (threshold lowered), N-D output broadening --
+    against the oracle's shgyield()."""
+    from shgyield_b200 import shg
+    rng = np.random.default_rng(seed)
+    try:
+        shape = np.broadcast_shapes(es, ts, ps, ds)
+    except ValueError:
+        return                                               # not broadcastable: nothing to compare
+    m1, m2, m3, chi2 = cases.full_tensor_material(cases.load_spectra(), seed=seed % 7)
+    energy = rng.uniform(0.3, 9.5, es) if es else float(rng.uniform(0.3, 9.5))
+    theta = rng.uniform(0, 89, ts) if ts else float(rng.uniform(0, 89))
+    phi = rng.uniform(-180, 540, ps) if ps else float(rng.uniform(-180, 540))
+    thick = rng.uniform(0, 60, ds) if ds else float(rng.uniform(0, 60))
+    kw = dict(gamma=float(rng.uniform(-90, 180)), sigma_eps=float(rng.choice([0.0, 1.5])), sigma_chi=float(rng.choice([0.0, 3.0])),
+              sigma_out=sigma_out, mode=mode, mref=mref)
+    old = shg.GRID_MIN_POINTS
+    shg.GRID_MIN_POINTS = 1 if grid_path else old
+    try:
+        got = shg.shgyield(energy, m1, m2, m3, chi2, theta, phi, thick, **kw)
+    finally:
+        shg.GRID_MIN_POINTS = old
+    want = orc.shgyield(energy, m1, m2, m3, chi2, theta, phi, thick, consts=CONSTS, **kw)
+    scale = max(float(np.max(np.abs(want[p]))) for p in cases.POLS)
+    for pol in cases.POLS:
+        assert np.shape(got[pol]) == np.shape(want[pol]) == shape, (pol, np.shape(got[pol]), shape)
+        ok, msg = cases.parity_ok(got[pol], want[pol], rtol=1e-10, scale=scale)
+        assert ok, (seed, es, ts, ps, ds, kw, grid_path, pol, msg)
