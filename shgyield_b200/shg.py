@@ -344,6 +344,9 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     e_arr = np.asarray(energy, dtype=np.float64)
     eps1w, eps2w, chi_rot, thick = _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
                                                    sigma_chi, mode)
+    if not mref:
+        thick = 0.0               # the reference never touches `thick` without multiple reflections (shg.py:179, 192),
+                                  # so its shape does not enter the broadcast of the result either
     t_arr, p_arr, d_arr = (np.asarray(v, dtype=np.float64) for v in (theta, phi, thick))
     shape = np.broadcast_shapes(e_arr.shape, t_arr.shape, p_arr.shape, d_arr.shape)
     ndim = len(shape)
