@@ -11,6 +11,7 @@ from tests import cases, util
 
 pytestmark = pytest.mark.gpu
 CONSTS = util.load_consts()
+MORE = int(os.environ.get("SSHG_HYP_SCALE", "1"))       # SSHG_HYP_SCALE=8: a longer soak run of the same tests
 
 
 def _spectra(rng, nE):
@@ -36,7 +37,7 @@ def _oracle(energy, eps1w, eps2w, chi, theta, phi, thick, **kw):
     return orc.yield_points(energy, e1, e2, ch, theta, phi, thick, consts=CONSTS, **kw)
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=40 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), n=st.integers(1, 700), mref=st.booleans(), sn=st.booleans(), zq=st.booleans())
 def test_points_kernel_random(seed, n, mref, sn, zq):
     from shgyield_b200 import shg
@@ -55,7 +56,7 @@ def test_points_kernel_random(seed, n, mref, sn, zq):
         assert ok, (seed, pol, msg)
 
 
-@settings(max_examples=25, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=25 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 1300), nT=st.integers(1, 5), nD=st.integers(1, 3),
        grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]),
        kernel=st.sampled_from(["dense", "sparse"]))
@@ -89,7 +90,7 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind):
         assert ok, (seed, grid_kind, os.environ.get("SSHG_K2_SPARSE"), pol, msg)
 
 
-@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=20 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 900), nT=st.integers(1, 3), nD=st.integers(1, 2),
        sigma=st.floats(0.13, 16.0), grid_kind=st.sampled_from(["paired", "paired_tail", "free"]),
        tiles=st.sampled_from(["64", "128"]))
@@ -122,7 +123,7 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
 _SHAPES = [(), (1,), (5,), (3, 1), (2, 1, 1), (1, 4), (2, 3)]
 
 
-@settings(max_examples=30, deadline=None, suppress_health_check=list(HealthCheck))
+@settings(max_examples=30 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), es=st.sampled_from([(), (7,), (40,), (2, 5)]), ts=st.sampled_from(_SHAPES),
        ps=st.sampled_from(_SHAPES), ds=st.sampled_from([(), (1,), (3, 1, 1)]), sigma_out=st.sampled_from([0.0, 0.7, 2.0]),
        mode=st.sampled_from(["3-layer", "2-layer", "fresnel"]), mref=st.booleans(), grid_path=st.booleans())
