@@ -36,7 +36,11 @@ def _blurred_oracle(cfg, consts, sigma, **kw):
     return orc.gaussian_filter1d(_oracle_cube(cfg, consts, **kw), sigma, axis=-1)
 
 
-def _check(got, want, fused, what):
+def _check(got, want, fused, what, col_bound=5e-14):
+    """parity metric + K3's absolute bound.  col_bound: 5e-14 of the column's maximum over phi on the smooth
+    spectra of these tests; the generated media of tests/test_gpu_hypothesis.py (gain media, |exponents| of
+    several hundred) make the yield itself ill-conditioned -- there K2 and the oracle already differ by
+    ~5e-14 relative -- and pass a looser bound."""
     assert got.shape == want.shape
     top = np.max(want)
     for k, pol in enumerate(cases.POLS):
@@ -44,7 +48,7 @@ def _check(got, want, fused, what):
         ok, msg = cases.parity_ok(a, b, rtol=RTOL, scale=top, rel_floor=1e-4 if fused else 1e-6)
         assert ok, (what, pol, msg)
         colmax = np.maximum(np.max(b, axis=2, keepdims=True), 1e-12 * top)       # max over phi of every column
-        assert np.max(np.abs(a - b) / colmax) < 5e-14, (what, pol)
+        assert np.max(np.abs(a - b) / colmax) < col_bound, (what, pol)
 
 
 BLUR_SHAPES = [

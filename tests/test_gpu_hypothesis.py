@@ -117,7 +117,7 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     raw = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
     want = np.stack([orc.gaussian_filter1d(np.broadcast_to(raw[p], (nT, nD, phi.size, nE)), sigma, axis=-1)
                      for p in cases.POLS], axis=2)
-    _check(got, want, True, (seed, nE, sigma, grid_kind, tiles))
+    _check(got, want, True, (seed, nE, sigma, grid_kind, tiles), col_bound=5e-12)
 
 
 _SHAPES = [(), (1,), (5,), (3, 1), (2, 1, 1), (1, 4), (2, 3)]
