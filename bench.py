@@ -35,10 +35,11 @@ N_ENERGY, N_THETA, N_PHI = 20000, 181, 721
 WORKLOAD = "synthetic scale (BASELINE.json configs[4]): 20000 E x 181 theta x 721 phi x 4 pol, d = 10 nm, seed 20250"
 METRIC = "SSHG yield points/sec (E x theta x phi x pol)"
 # dram__bytes_read.sum + dram__bytes_write.sum of yield_grid_kernel per algorithmic byte, from the ncu
-# --set full capture of a 37-theta (5-wave) launch of the same kernel on the same sweep:
-# (17.0336 + 0.0633) GB / 17.0689 GB (profiles/r01_k2b_ncu_full.txt).  The full 83.5 GB launch itself
-# is not captured (ncu replays each kernel ~40 times with save/restore of everything it writes).
-NCU_TRAFFIC_PER_ALG_BYTE = 1.0016
+# --set full capture of a 37-theta launch of the same kernel on the same sweep (final code of round 1):
+# (17.0565 + 0.0556) GB / 17.0689 GB (profiles/r01_k2_final_ncu_full.txt; 1.0016 in the earlier capture
+# profiles/r01_k2b_ncu_full.txt).  The full 83.5 GB launch itself is not captured (ncu replays each kernel
+# ~40 times with save/restore of everything it writes).
+NCU_TRAFFIC_PER_ALG_BYTE = 1.0025
 E2E_THETAS = 8            # thetas of each rank's shard that the end-to-end leg evaluates per step
 CPU_PHI_CHUNK = 8         # phi values per CPU task (keeps NumPy temporaries ~100 MB)
 
@@ -484,7 +485,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": NCU_TRAFFIC_PER_ALG_BYTE * 8.0 * my_pts,
                          "traffic_source": "ncu dram read+write bytes per algorithmic byte (%.4f, 37-theta launch of the "
-                                           "same kernel, profiles/r01_k2b_ncu_full.txt) x this launch's algorithmic "
+                                           "same kernel, profiles/r01_k2_final_ncu_full.txt) x this launch's algorithmic "
                                            "bytes" % NCU_TRAFFIC_PER_ALG_BYTE,
                          "peak_source": peak_src,
                          "kernel": "yield_grid_kernel (K2); algorithmic bytes = 8 B x %.4g points per launch; "
