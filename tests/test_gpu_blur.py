@@ -216,3 +216,38 @@ def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
             assert ok, (mat, sigma, path, pol, msg)
             colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
             assert np.max(np.abs(got[:, k] - want[:, k]) / colmax) < 5e-14, (mat, sigma, path, pol)
+
+
+@pytest.mark.parametrize("tag", ["c3", "c4"])
+def test_config3_config4_full_size_broadened(grid, tag):
+    """Configs 3 and 4 of BASELINE.json at full size WITH the reference's default output broadening
+    (sigma_out = 5): complete (theta, thickness, phi) rows against the oracle's shgyield() called for that
+    angle -- including the exact C3v node rows of Si(111) -- plus the symmetries of the un-broadened cube,
+    which the broadening along E preserves.  Config 3 takes K3, config 4 (P = 1) K2s -> K1."""
+    import torch
+    axes = cases.config3_axes() if tag == "c3" else cases.config4_axes()
+    m1, m2, m3, chi2 = cases.si111_material(cases.load_spectra())
+    res = grid.shgyield_grid(axes["energy"], m1, m2, m3, chi2, axes["theta"], axes["phi"], axes["thick"],
+                             gamma=axes["gamma"], sigma_out=5.0)
+    torch.cuda.synchronize()
+    cube = res["cube"]                                                  # [T, D, 4, P, E]
+    assert bool(torch.isfinite(cube).all())
+    top = float(cube.max())
+    assert float(cube.min()) >= -1e-13 * top                            # the harmonic sum may undershoot 0 by rounding
+    rows = [(0, 0, 0), (33, 0, 30), (65, 0, 90), (65, 0, 91), (89, 0, 359), (12, 0, 180)] if tag == "c3" else \\
+           [(0, 0, 0), (65, 9, 0), (89, 99, 0), (30, 50, 0)]
+    for it, idd, ip in rows:
+        ref = orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][idd],
+                           gamma=axes["gamma"], sigma_out=5.0)
+        sc = max(float(np.max(ref[p])) for p in cases.POLS)
+        for k, pol in enumerate(cases.POLS):
+            got = cube[it, idd, k, ip].cpu().numpy()
+            ok, msg = cases.parity_ok(got, ref[pol], rtol=RTOL, scale=sc, rel_floor=1e-4 if tag == "c3" else 1e-6)
+            assert ok, (tag, it, idd, ip, pol, msg)
+    if tag == "c3":
+        ss = res["ss"][:, 0]
+        scale = float(ss.max())
+        assert float((ss[:, :120] - ss[:, 120:240]).abs().max()) <= 1e-10 * scale
+        assert float((ss[:, :180] - ss[:, 180:]).abs().max()) <= 1e-10 * scale
+    del cube, res
+    torch.cuda.empty_cache()
