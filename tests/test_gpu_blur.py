@@ -234,8 +234,8 @@ def test_config3_config4_full_size_broadened(grid, tag):
     assert bool(torch.isfinite(cube).all())
     top = float(cube.max())
     assert float(cube.min()) >= -1e-13 * top                            # the harmonic sum may undershoot 0 by rounding
-    rows = [(0, 0, 0), (33, 0, 30), (65, 0, 90), (65, 0, 91), (89, 0, 359), (12, 0, 180)] if tag == "c3" else \\
-           [(0, 0, 0), (65, 9, 0), (89, 99, 0), (30, 50, 0)]
+    rows = {"c3": [(0, 0, 0), (33, 0, 30), (65, 0, 90), (65, 0, 91), (89, 0, 359), (12, 0, 180)],
+            "c4": [(0, 0, 0), (65, 9, 0), (89, 99, 0), (30, 50, 0)]}[tag]
     for it, idd, ip in rows:
         ref = orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][idd],
                            gamma=axes["gamma"], sigma_out=5.0)
