@@ -68,11 +68,15 @@ typedef struct {
     int32_t sinc_normalized; /* 1: np.sinc = sin(pi x)/(pi x) as shipped (shg.py:183); 0: sin(x)/x */
     int32_t zzz_phi_quirk;   /* 1: chi_zzz term of r_pP times sin(phi)^3 as shipped (shg.py:269);
                                 0: sin(theta)^3 (Eq. 50 of PRB 94, 115314)          */
-    int32_t flags;           /* SSHG_FLAG_* bits, 0 for the yield entry points              */
+    int32_t flags;           /* SSHG_FLAG_* bits                                            */
 } sshg_physics;
 
 /* sshg_physics.flags */
 #define SSHG_FLAG_RADIANS 1  /* theta / phi of a point list are in radians (the reference's helpers) */
+#define SSHG_FLAG_STRICT_BROADENING 2  /* sshg_yield_broadened: broaden every yield row itself (yield kernel, then the
+                                          Gaussian FIR, slab by slab) instead of the 13 azimuthal harmonics of a column.
+                                          ~4.5x slower; keeps the element-wise 1e-10 even on rows that are within
+                                          1e-3 of an azimuthal node of the yield (DESIGN.md, K3 accuracy) */
 
 /* A rectangular sweep: energy x theta x phi x thickness (x 4 polarisations).
  * Replaces the reference's NumPy broadcast over rad_pp/ps/sp/ss + prefactor

@@ -20,6 +20,7 @@ SSHG_OK, SSHG_EINVAL, SSHG_ECUDA, SSHG_ENOMEM = 0, -1, -2, -3
 HOST, IN_DEVICE, OUT_DEVICE, DEVICE = 0, 1, 2, 3
 ABI_VERSION = 1
 FLAG_RADIANS = 1
+FLAG_STRICT_BROADENING = 2
 IPC_HANDLE_BYTES = 64
 
 c_double_p = C.POINTER(C.c_double)

@@ -26,6 +26,7 @@ def main(argv=None) -> int:
     sweep = any(np.ndim(cfg[k]) > 0 for k in ("theta", "phi", "thick"))
     if not sweep:
         from .shg import shgyield
+        cfg.pop("strict", None)
         res = shgyield(**cfg)
         io.save_spectrum(out, res)
         print("wrote %s (%d energies x 4 polarisations)" % (out, np.size(res["energy"])))

@@ -544,6 +544,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     const long long radius = sigma_out > 1e-15 ? (long long)(4.0 * sigma_out + 0.5) : 0;
     SSHG_REQUIRE(radius < (1LL << 28), "sshg_yield: sigma_out %g is too large", sigma_out);
     bool fused = radius >= 1 && radius <= BLUR_RMAX && !sparse;
+    if (p->phys.flags & SSHG_FLAG_STRICT_BROADENING) fused = false;
     if (const char* env = getenv("SSHG_K3")) fused = fused && atoi(env) != 0;
     const bool two_pass = radius >= 1 && !fused;
 

@@ -67,14 +67,18 @@ def _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, phys, t_range=None, 
 
 
 def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, consts=None, sinc_normalized=True,
-                    zzz_phi_quirk=True, t_range=None, d_range=None, out=None, pinned=False, sigma_out=0.0):
+                    zzz_phi_quirk=True, t_range=None, d_range=None, out=None, pinned=False, sigma_out=0.0,
+                    strict_broadening=False):
     """Host arrays in, host cube out: float64 [T_shard, D_shard, 4, P, E].  The library computes
     slabs on the device and copies slab k back while slab k+1 is computed.  sigma_out > 0 broadens
-    every yield spectrum along the energy axis (shg.py:433-436) inside the yield kernel."""
+    every yield spectrum along the energy axis (shg.py:433-436) inside the yield kernel (K3; its error is
+    absolute, <= 5e-14 of the column's maximum over phi); strict_broadening=True filters every row itself
+    (yield kernel -> Gaussian FIR, ~4.5x slower, element-wise 1e-10 also next to azimuthal nodes)."""
     ctx = _lib.context()
     keep = []
-    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, _physics(consts, mref, sinc_normalized, zzz_phi_quirk),
-                 t_range, d_range, keep)
+    flags = _lib.FLAG_STRICT_BROADENING if strict_broadening else 0
+    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2,
+                 _physics(consts, mref, sinc_normalized, zzz_phi_quirk, flags), t_range, d_range, keep)
     shape = (p.t1 - p.t0, p.d1 - p.d0, 4, p.nP, p.nE)
     if keep[4].shape != (3, p.nE) or keep[5].shape != (3, p.nE) or keep[6].shape != (18, p.nE):
         raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
@@ -89,7 +93,7 @@ def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, co
 
 def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, mref=True, consts=None,
                       sinc_normalized=True, zzz_phi_quirk=True, t_range=None, d_range=None, stream=None,
-                      sigma_out=0.0, out_ptr=None):
+                      sigma_out=0.0, out_ptr=None, strict_broadening=False):
     """Device-resident sweep: every array is a CUDA torch tensor (float64 / complex128), `out` a
     float64 CUDA tensor [T_shard, D_shard, 4, P, E] (allocated if None).  Asynchronous: the kernels
     are queued on torch's current stream (or `stream`).  sigma_out > 0: yields broadened along the
@@ -104,8 +108,9 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
                   (eps1w, torch.complex128), (eps2w, torch.complex128), (chi2, torch.complex128)):
         if not (t.is_cuda and t.dtype == dt and t.is_contiguous()):
             raise ValueError("device sweep needs contiguous CUDA tensors of float64 / complex128")
-    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2, _physics(consts, mref, sinc_normalized, zzz_phi_quirk),
-                 t_range, d_range, keep)
+    flags = _lib.FLAG_STRICT_BROADENING if strict_broadening else 0
+    p = _problem(energy, theta, phi, thick, eps1w, eps2w, chi2,
+                 _physics(consts, mref, sinc_normalized, zzz_phi_quirk, flags), t_range, d_range, keep)
     shape = (p.t1 - p.t0, p.d1 - p.d0, 4, p.nP, p.nE)
     if tuple(eps1w.shape) != (3, p.nE) or tuple(eps2w.shape) != (3, p.nE) or tuple(chi2.shape) != (18, p.nE):
         raise ValueError("eps1w/eps2w must be [3, nE] and chi2 [18, nE]")
@@ -126,7 +131,7 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
 
 
 def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0, sigma_chi=0.0,
-                  sigma_out=0.0, mode="3-layer", mref=True, device=True, shard=None, gather=False):
+                  sigma_out=0.0, mode="3-layer", mref=True, device=True, shard=None, gather=False, strict=False):
     """
     Sweep with the reference's material arguments (same meaning as shg.shgyield) over explicit 1-D
     axes energy[E], theta[T], phi[P], thick[D].  Returns {'energy','theta','phi','thick',
@@ -138,7 +143,9 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
     gather="peer" (theta shards on one node) instead lets every rank's kernel store its slab directly into
     rank 0's cube over NVLink (`PeerCube`): no slab buffer, no collective.
     sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles); it is
-    done inside the yield kernel (K3: the cube is written once).
+    done inside the yield kernel (K3: the cube is written once; error <= 5e-14 of a column's maximum over phi).
+    strict=True broadens every row itself instead (K2 -> K1 by slabs, ~4.5x slower, element-wise 1e-10 also
+    on rows next to an azimuthal node of the yield).
     """
     energy = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
     theta = np.atleast_1d(np.asarray(theta, dtype=np.float64)).ravel()
@@ -164,7 +171,8 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
         pc = PeerCube((theta.size, thick.size, 4, phi.size, energy.size), dst=0)
         yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
-                          mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out, out_ptr=pc.slab_ptr(t_range[0]))
+                          mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out, out_ptr=pc.slab_ptr(t_range[0]),
+                          strict_broadening=strict)
         torch.cuda.synchronize()
         dist.barrier()
         cube = pc.tensor()
@@ -174,12 +182,13 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
         dev = torch.device("cuda", _lib.context().device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
         cube = yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
-                                 mref=mref, consts=consts, t_range=t_range, d_range=d_range, sigma_out=sigma_out)
+                                 mref=mref, consts=consts, t_range=t_range, d_range=d_range, sigma_out=sigma_out,
+                                 strict_broadening=strict)
         if gather and shard is not None:          # True, or "peer" on a thickness shard (not contiguous in the cube)
             cube = gather_slabs(cube, theta.size, thick.size, shard)
     else:
         cube = yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi_rot, mref=mref, consts=consts,
-                               t_range=t_range, d_range=d_range, sigma_out=sigma_out)
+                               t_range=t_range, d_range=d_range, sigma_out=sigma_out, strict_broadening=strict)
     res = {"energy": energy, "theta": theta, "phi": phi, "thick": thick, "cube": cube}
     for k, pol in enumerate(POLS):
         res[pol] = cube[:, :, k] if cube is not None else None     # gather: only rank 0 holds the cube

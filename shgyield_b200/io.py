@@ -111,7 +111,7 @@ def load_input(path: str) -> dict:
         parameters: {theta, phi, gamma: 0, energy: {min, max, step} | [..], mode: 3-layer, mref: true,
                      output: spectrum.dat}
         multiref:   {thickness: nm}
-        broadening: {eps: 0, chi: 0, out: 5}          # sigmas in samples, as in shgyield()
+        broadening: {eps: 0, chi: 0, out: 5, strict: false}   # sigmas in samples, as in shgyield()
         chi1:       {chib: path | {xx,yy,zz}, chil: path | {xx,yy,zz}, norm: 1.0, vacuum: 1.0}
         chi2:       {scale: 1e-18, abc: path | 0 | abc | -abc, ...}
 
@@ -143,6 +143,7 @@ def load_input(path: str) -> dict:
         "gamma": par.get("gamma", 0),
         "sigma_eps": float(brd.get("eps", 0.0)), "sigma_chi": float(brd.get("chi", 0.0)),
         "sigma_out": float(brd.get("out", 5.0)),
+        "strict": bool(brd.get("strict", False)),          # sweeps only: broaden every row itself (see shgyield_grid)
         "mode": par.get("mode", "3-layer"), "mref": bool(par.get("mref", True)),
         "output": par.get("output", "spectrum.dat"),
     }

@@ -46,10 +46,10 @@ def physical_constants() -> dict:
                 "eps0": constants.epsilon_0, "c": constants.c}
 
 
-def _physics(consts, mref=True, sinc_normalized=True, zzz_phi_quirk=True) -> _lib.Physics:
+def _physics(consts, mref=True, sinc_normalized=True, zzz_phi_quirk=True, flags=0) -> _lib.Physics:
     c = consts or physical_constants()
     return _lib.Physics(c["h_eVs"], c["hbar_eVs"], c["eps0"], c["c"], int(bool(mref)), int(bool(sinc_normalized)),
-                        int(bool(zzz_phi_quirk)), 0)
+                        int(bool(zzz_phi_quirk)), int(flags))
 
 
 # ---------------------------------------------------------------------------------------------

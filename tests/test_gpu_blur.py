@@ -234,20 +234,43 @@ def test_config3_config4_full_size_broadened(grid, tag):
     assert bool(torch.isfinite(cube).all())
     top = float(cube.max())
     assert float(cube.min()) >= -1e-13 * top                            # the harmonic sum may undershoot 0 by rounding
-    rows = {"c3": [(0, 0, 0), (33, 0, 30), (65, 0, 90), (65, 0, 91), (89, 0, 359), (12, 0, 180)],
-            "c4": [(0, 0, 0), (65, 9, 0), (89, 99, 0), (30, 50, 0)]}[tag]
-    for it, idd, ip in rows:
-        ref = orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][idd],
-                           gamma=axes["gamma"], sigma_out=5.0)
-        sc = max(float(np.max(ref[p])) for p in cases.POLS)
+    # complete rows: per (theta, thickness) a set of azimuths that includes exact C3v nodes (0, 30, 90, 180 deg),
+    # near-node rows (1, 91) and an off-node row (45); M = max over those rows of the oracle, a lower bound of the
+    # column's maximum over phi.  K3's statement is |error| <= 5e-14 * column maximum (here 1e-13 * M), which
+    # implies 1e-10 relative wherever the yield exceeds 1e-3 of its column maximum; the two-pass path of config 4
+    # holds the strict metric.
+    cols = {"c3": [(0, 0), (65, 0), (89, 0)], "c4": [(0, 0), (65, 9), (89, 99)]}[tag]
+    phis = [0, 1, 30, 45, 90, 91, 180, 359] if tag == "c3" else [0]
+    for it, idd in cols:
+        ref = {ip: orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][idd],
+                                gamma=axes["gamma"], sigma_out=5.0) for ip in phis}
         for k, pol in enumerate(cases.POLS):
-            got = cube[it, idd, k, ip].cpu().numpy()
-            ok, msg = cases.parity_ok(got, ref[pol], rtol=RTOL, scale=sc, rel_floor=1e-4 if tag == "c3" else 1e-6)
-            assert ok, (tag, it, idd, ip, pol, msg)
+            want = np.stack([ref[ip][pol] for ip in phis])                              # [len(phis), E]
+            got = cube[it, idd, k][torch.tensor(phis, device=cube.device)].cpu().numpy()
+            if tag == "c3":
+                M = np.maximum(want.max(axis=0, keepdims=True), 1e-30)
+                assert np.max(np.abs(got - want) / M) < 1e-13, (tag, it, pol)
+                assert np.max(np.abs(got - want)) <= RTOL * top
+            else:
+                ok, msg = cases.parity_ok(got, want, rtol=RTOL, scale=float(want.max()))
+                assert ok, (tag, it, idd, pol, msg)
     if tag == "c3":
         ss = res["ss"][:, 0]
         scale = float(ss.max())
         assert float((ss[:, :120] - ss[:, 120:240]).abs().max()) <= 1e-10 * scale
         assert float((ss[:, :180] - ss[:, 180:]).abs().max()) <= 1e-10 * scale
+        # strict=True (SSHG_FLAG_STRICT_BROADENING: every row filtered itself) holds the element-wise metric row by
+        # row, node rows included
+        del cube, res
+        res = grid.shgyield_grid(axes["energy"], m1, m2, m3, chi2, axes["theta"], axes["phi"], axes["thick"],
+                                 gamma=axes["gamma"], sigma_out=5.0, strict=True)
+        cube = res["cube"]
+        for it, ip in ((0, 0), (0, 1), (65, 45), (65, 90), (89, 359)):
+            ref = orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][0],
+                               gamma=axes["gamma"], sigma_out=5.0)
+            sc = max(float(np.max(ref[p])) for p in cases.POLS)
+            for k, pol in enumerate(cases.POLS):
+                ok, msg = cases.parity_ok(cube[it, 0, k, ip].cpu().numpy(), ref[pol], rtol=RTOL, scale=sc)
+                assert ok, ("strict", it, ip, pol, msg)
     del cube, res
     torch.cuda.empty_cache()
