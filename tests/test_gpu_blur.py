@@ -244,6 +244,7 @@ def test_config3_config4_full_size_broadened(grid, tag):
     for it, idd in cols:
         ref = {ip: orc.shgyield(axes["energy"], m1, m2, m3, chi2, axes["theta"][it], axes["phi"][ip], axes["thick"][idd],
                                 gamma=axes["gamma"], sigma_out=5.0) for ip in phis}
+        sc4 = max(float(np.max(ref[ip][p])) for ip in phis for p in cases.POLS)
         for k, pol in enumerate(cases.POLS):
             want = np.stack([ref[ip][pol] for ip in phis])                              # [len(phis), E]
             got = cube[it, idd, k][torch.tensor(phis, device=cube.device)].cpu().numpy()
@@ -252,7 +253,7 @@ def test_config3_config4_full_size_broadened(grid, tag):
                 assert np.max(np.abs(got - want) / M) < 1e-13, (tag, it, pol)
                 assert np.max(np.abs(got - want)) <= RTOL * top
             else:
-                ok, msg = cases.parity_ok(got, want, rtol=RTOL, scale=float(want.max()))
+                ok, msg = cases.parity_ok(got, want, rtol=RTOL, scale=sc4)      # sP / pS of Si(111) at phi = 30: pure node noise
                 assert ok, (tag, it, idd, pol, msg)
     if tag == "c3":
         ss = res["ss"][:, 0]
