@@ -34,6 +34,8 @@ struct BlurArgs {
     int radius;
     int S;                                      // staged energies per CTA = 2 NT + 2 radius
     int chunk;                                  // phi items per table chunk (what fits behind the parked harmonics)
+    unsigned char* flags;                       // [column][fix-up tile][pol][row]: 1 = re-evaluate strictly (or null)
+    int fx_tiles;                               // fix-up tiles (FX_TILE energies) per column
     double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
 };
 
@@ -107,10 +109,21 @@ __device__ __forceinline__ void fir_pair(const double* __restrict__ x, int S, in
 
 // (C) azimuthal sweep of the harmonic form, two energies per thread.  tb: items of 12 doubles
 // {cos, sin of 2, 4, 6 phi | cos, sin of 1, 3, 5 phi}.
+// Points whose yield is far below the amplitude bound U >= max_phi y of their column are where the harmonic
+// sum cancels: |error| <= 5e-14 U is then no longer small against the value.  They are flagged, per
+// (column, fix-up tile, polarisation, row), and `yield_blur_fixup_kernel` re-evaluates those row segments the
+// strict way (NODE_FRACTION, amplitude_bound: sshg_math.cuh).
+constexpr int FX_NT = 64;                       // fix-up kernel: threads per CTA
+constexpr int FX_TILE = FX_NT * EPT;            // ... and energies per tile (flag granularity along E)
+
 template <bool SS>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                           long long stride, bool vec, bool valid1) {
+                                           long long stride, bool vec, bool valid1, unsigned char* flo,
+                                           unsigned char* fhi, unsigned char* fsg) {
+    const bool flagging = flo != nullptr;
+    const double thr0 = flagging ? NODE_FRACTION * amplitude_bound(A0, SS) : -1.0;
+    const double thr1 = (flagging && valid1) ? NODE_FRACTION * amplitude_bound(A1, SS) : -1.0;
 #pragma unroll 2
     for (int i = 0; i < n_pair + n_single; ++i) {
         double t[12];
@@ -138,18 +151,17 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
             }
         }
         if (i < n_pair) {
-            if (SS) {
-                store2(plo, ye0, ye1, vec, valid1);
-                store2(phi_, ye0, ye1, vec, valid1);
-            } else {
-                store2(plo, ye0 + yo0, ye1 + yo1, vec, valid1);
-                store2(phi_, ye0 - yo0, ye1 - yo1, vec, valid1);
-            }
+            const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
+            store2(plo, a0, a1, vec, valid1);
+            store2(phi_, s0, s1, vec, valid1);
+            if ((a0 < thr0) | (a1 < thr1)) flo[i] = 1;
+            if ((s0 < thr0) | (s1 < thr1)) fhi[i] = 1;
             plo += stride;
             phi_ += stride;
         } else {
-            if (SS) store2(psg, ye0, ye1, vec, valid1);
-            else store2(psg, ye0 + yo0, ye1 + yo1, vec, valid1);
+            const double a0 = ye0 + yo0, a1 = ye1 + yo1;
+            store2(psg, a0, a1, vec, valid1);
+            if ((a0 < thr0) | (a1 < thr1)) fsg[i - n_pair] = 1;
             psg += stride;
         }
     }
@@ -275,9 +287,156 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             double* plo = prow + base * nE;
             double* phi_ = prow + (base + H) * nE;
             double* psg = prow + (base + n_pair + H) * nE;
-            if (pol == 3) sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
-            else sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+            unsigned char *flo = nullptr, *fhi = nullptr, *fsg = nullptr;
+            if (b.flags) {                      // flag block of this (column, fix-up tile, polarisation): one byte per row
+                unsigned char* fb = b.flags + ((lcol * b.fx_tiles + e0 / FX_TILE) * 4 + pol) * a.nP;
+                flo = fb + base;
+                fhi = fb + base + H;
+                fsg = fb + base + n_pair + H;
+            }
+            if (pol == 3) sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg);
+            else sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg);
         }
     }
 }
 
+
+// ---- K3 fix-up: the flagged row segments, evaluated the strict way ----------------------------------------
+// A CTA owns the FX_TILE energies of one (column, fix-up tile).  If none of its 4 nP flags is set it exits.
+// Otherwise it evaluates the column setup for its energies + halo (parked in shared memory), per polarisation with
+// flagged rows the 7 (sS: 4) complex coefficients of K2, and per flagged row the un-broadened yields |r(phi)|^2
+// of the staged energies exactly as K2 does, filters them along E and overwrites K3's values.  The yields it
+// writes are relative-accurate next to an azimuthal node, like the reference's.
+struct FixArgs {
+    YieldArgs y;                                // y.tab unused
+    const double* phi_deg;
+    const unsigned char* flags;
+    int radius;
+    int S;                                      // FX_TILE + 2 radius
+    double w[BLUR_RMAX + 1];
+};
+
+__global__ void __launch_bounds__(FX_NT) yield_blur_fixup_kernel(const __grid_constant__ FixArgs b) {
+    extern __shared__ double smem[];
+    const YieldArgs& a = b.y;
+    const int R = b.radius, S = b.S;
+    double* wf = smem;                          // [2 R + 2]
+    double* cols = wf + 2 * R + 2;              // [NCOL][S]   parked Column, struct of arrays
+    double* kb = cols + NCOL * S;               // [14][S]     coefficients of the current polarisation
+    double* rowbuf = kb + 14 * S;               // [S]         un-broadened yields of the current row
+
+    const long long blk = blockIdx.x;
+    const int tile = (int)(blk % a.n_tiles);
+    const long long lcol = blk / a.n_tiles;
+    const int tid = threadIdx.x;
+    const long long nE = a.nE, nP = a.nP;
+    const unsigned char* fb = b.flags + (lcol * a.n_tiles + tile) * 4 * nP;
+
+    int any = 0;
+    for (long long i = tid; i < 4 * nP; i += FX_NT) any |= fb[i];
+    if (!__syncthreads_or(any)) return;
+
+    const long long col = a.col0 + lcol;
+    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
+    const long long tile_e0 = (long long)tile * FX_TILE;
+    for (int t = tid; t <= 2 * R; t += FX_NT) wf[t] = b.w[t < R ? R - t : t - R];
+    {
+        double st, ct;
+        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
+        const double thick = a.thick_nm[a.d0 + dl];
+#pragma unroll 1
+        for (int i = tid; i < S; i += FX_NT) {
+            const long long g = tile_e0 - R + i;
+            if (g >= nE + R) break;
+            const long long e = reflect_index(g, nE);
+            cplx e1[3], e2[3];
+#pragma unroll
+            for (int m = 0; m < 3; ++m) {
+                e1[m] = ldc(a.eps1w + m * nE + e);
+                e2[m] = ldc(a.eps2w + m * nE + e);
+            }
+            const Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
+            const cplx v[10] = {c.Gpp, c.Gps, c.Gsp, c.Gss, c.A, c.Bz, c.Q, c.a2, c.ab, c.b2};
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                cols[(2 * j) * S + i] = v[j].re;
+                cols[(2 * j + 1) * S + i] = v[j].im;
+            }
+        }
+    }
+    __syncthreads();
+
+    const long long e0 = tile_e0 + (long long)tid * EPT;
+    const bool active = e0 < nE, valid1 = e0 + 1 < nE;
+    const bool vec = a.vec_ok != 0;
+    const long long rows_per_pol = nP * nE;
+    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+
+#pragma unroll 1
+    for (int pol = 0; pol < 4; ++pol) {
+        int anyp = 0;
+        for (long long i = tid; i < nP; i += FX_NT) anyp |= fb[pol * nP + i];
+        if (!__syncthreads_or(anyp)) continue;
+        const int nk = pol == 3 ? 4 : 7;
+#pragma unroll 1
+        for (int i = tid; i < S; i += FX_NT) {
+            const long long g = tile_e0 - R + i;
+            if (g >= nE + R) break;
+            const long long e = reflect_index(g, nE);
+            auto parked = [&](int j) { return mk(cols[(2 * j) * S + i], cols[(2 * j + 1) * S + i]); };
+            Column c;
+            c.Gpp = parked(0); c.Gps = parked(1); c.Gsp = parked(2); c.Gss = parked(3);
+            c.A = parked(4); c.Bz = parked(5); c.Q = parked(6);
+            c.a2 = parked(7); c.ab = parked(8); c.b2 = parked(9);
+            auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
+            cplx kk[7];
+            if (pol == 0) coeffs_pp(c, chi, a.ph, kk);
+            else if (pol == 1) coeffs_ps(c, chi, kk);
+            else if (pol == 2) coeffs_sp(c, chi, kk);
+            else coeffs_ss(c, chi, kk);
+            for (int j = 0; j < nk; ++j) {
+                kb[(2 * j) * S + i] = kk[j].re;
+                kb[(2 * j + 1) * S + i] = kk[j].im;
+            }
+        }
+        __syncthreads();
+#pragma unroll 1
+        for (long long row = 0; row < nP; ++row) {
+            if (!fb[pol * nP + row]) continue;                  // the same byte for every thread: uniform branch
+            double bb[6];
+            phi_basis(b.phi_deg[row], bb);
+            for (int i = tid; i < S; i += FX_NT) {
+                double re, im;
+                if (pol == 3) {                                 // k[0..3] multiply {c^3, s c^2, s^2 c, s^3}
+                    re = kb[0 * S + i] * bb[2];
+                    im = kb[1 * S + i] * bb[2];
+#pragma unroll
+                    for (int j = 1; j < 4; ++j) {
+                        re = fma(kb[(2 * j) * S + i], bb[j + 2], re);
+                        im = fma(kb[(2 * j + 1) * S + i], bb[j + 2], im);
+                    }
+                } else {
+                    re = kb[0 * S + i];
+                    im = kb[1 * S + i];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) {
+                        re = fma(kb[(2 * j + 2) * S + i], bb[j], re);
+                        im = fma(kb[(2 * j + 3) * S + i], bb[j], im);
+                    }
+                }
+                rowbuf[i] = fma(re, re, im * im);
+            }
+            __syncthreads();
+            if (active) {
+                const double* x = rowbuf + tid * EPT;               // x[0 .. 2 R + 1]
+                double o0 = x[R] * wf[R], o1 = x[R + 1] * wf[R];    // centre tap, then the pairs from the farthest inwards
+                for (int j = R; j >= 1; --j) {
+                    o0 = fma(x[R - j] + x[R + j], wf[R + j], o0);
+                    o1 = fma(x[R + 1 - j] + x[R + 1 + j], wf[R + j], o1);
+                }
+                store2(out_col + (pol * nP + row) * nE, o0, o1, vec, valid1);
+            }
+            __syncthreads();
+        }
+    }
+}

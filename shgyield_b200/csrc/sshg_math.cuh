@@ -337,6 +337,20 @@ SSHG_HD void phi_harmonics(double phi_deg, double t[12]) {
     }
 }
 
+// U = |C0| + sum_q sqrt(C_q^2 + S_q^2) >= max over phi of the harmonic sum.  The rounding error of that sum is
+// <= 5e-14 U, so a value below NODE_FRACTION * U (the yield next to an azimuthal node) is no longer accurate to
+// 1e-10 relative: K3 flags it and the fix-up kernel re-evaluates it the strict way.  With 1e-3 everything
+// that is NOT flagged keeps an element-wise error below 5e-11.
+constexpr double NODE_FRACTION = 1e-3;
+
+SSHG_HD double amplitude_bound(const double* H, bool odd_only) {
+    double u = fabs(H[0]);
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+        if (!odd_only || j < 3) u += sqrt(fma(H[1 + 2 * j], H[1 + 2 * j], H[2 + 2 * j] * H[2 + 2 * j]));
+    return u;
+}
+
 SSHG_HD double harmonic_yield(const double* H, const double t[12], bool odd_only) {
     double ye = H[0];
 #pragma unroll

@@ -706,7 +706,13 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         ctx->launches++;
         return SSHG_OK;
     };
-    // K3: the same columns, broadened along the energy axis, in one pass
+    // K3: the same columns, broadened along the energy axis, in one pass; then the fix-up kernel re-evaluates the
+    // row segments K3 flagged (yield next to an azimuthal node) the strict way.  SSHG_K3_FIXUP=0 disables (tests).
+    const bool fixup = !(getenv("SSHG_K3_FIXUP") && atoi(getenv("SSHG_K3_FIXUP")) == 0);
+    const int fx_tiles = (int)((p->nE + FX_TILE - 1) / FX_TILE);
+    const size_t fx_smem = (size_t)(2 * radius + 2 + (size_t)(NCOL + 14 + 1) * (FX_TILE + 2 * radius)) * sizeof(double);
+    if (fused && fixup)
+        SSHG_CUDA(cudaFuncSetAttribute(yield_blur_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fx_smem));
     auto launch_blur = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
         BlurArgs b = ba;
         b.y = a;
@@ -717,6 +723,14 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.n_seg = pick_segments(nc * blur_tiles, blur_per_sm, 0.0);        // K3's setup (halo, harmonics, FIR) is too
                                                                             // heavy to repeat: measured slower (tuning only)
         SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
+        void* flags = nullptr;
+        const size_t flag_bytes = (size_t)nc * fx_tiles * 4 * (size_t)p->nP;
+        if (fixup) {
+            if (int rc = sshg_scratch(ctx, 13, flag_bytes, &flags)) return rc;
+            SSHG_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, st));
+        }
+        b.flags = (unsigned char*)flags;
+        b.fx_tiles = fx_tiles;
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
             yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
@@ -724,6 +738,21 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
             yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
+        if (fixup) {
+            SSHG_REQUIRE(nc * fx_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
+            FixArgs f{};
+            f.y = b.y;
+            f.y.n_tiles = fx_tiles;
+            f.y.n_seg = 1;
+            f.phi_deg = (const double*)dphi;
+            f.flags = (const unsigned char*)flags;
+            f.radius = ba.radius;
+            f.S = FX_TILE + 2 * ba.radius;
+            for (int k = 0; k <= ba.radius; ++k) f.w[k] = ba.w[k];
+            yield_blur_fixup_kernel<<<(unsigned)(nc * fx_tiles), FX_NT, fx_smem, st>>>(f);
+            SSHG_CUDA(cudaGetLastError());
+            ctx->launches++;
+        }
         return SSHG_OK;
     };
 

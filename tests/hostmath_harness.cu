@@ -164,8 +164,10 @@ extern "C" int hostmath_sparse_walk(const sshg_points* p, long long e, double th
 // ---- K3 on the CPU: harmonic form of one (theta, thickness) column, broadened along the energy axis ----
 // p: a point list whose spectra columns are the energy axis (eidx unused); theta / thickness scalars;
 // phi: nP azimuths; w: r + 1 Gaussian taps (w[0] centre); out[pol][nP][nE].
+// strict_nodes: 1 = as the product (K3 + fix-up kernel): values below NODE_FRACTION of the column's amplitude bound flag
+// their (polarisation, row, 128-energy tile), which is then re-evaluated row-wise (|r|^2 per energy, FIR); 0 = K3 alone.
 extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, double thick_nm, const double* phi_deg,
-                                    long long nP, const double* w, int r, double* out) {
+                                    long long nP, const double* w, int r, int strict_nodes, double* out) {
     Physics ph;
     ph.kd = 1e-9 / (p->phys.h_eVs * p->phys.c);
     ph.pref = 100.0 / (p->phys.hbar_eVs * sqrt(2.0 * p->phys.eps0 * p->phys.c * p->phys.c * p->phys.c));
@@ -214,16 +216,58 @@ extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, doub
             for (int j = -r; j <= r; ++j) acc = fma(raw[(size_t)a * nE + reflect(e + j)], w[j < 0 ? -j : j], acc);
             blur[(size_t)a * nE + e] = acc;
         }
+    // un-broadened coefficients of every energy, kept for the strict re-evaluation of flagged row segments
+    std::vector<cplx> kk((size_t)4 * 7 * nE);
+    for (long long e = 0; e < nE; ++e) {
+        cplx e1[3], e2[3];
+        for (int m = 0; m < 3; ++m) {
+            e1[m] = mk(p->eps1w[2 * (m * nE + e)], p->eps1w[2 * (m * nE + e) + 1]);
+            e2[m] = mk(p->eps2w[2 * (m * nE + e)], p->eps2w[2 * (m * nE + e) + 1]);
+        }
+        const Column c = column_setup(e1, e2, p->energy_eV[e], st, ct, thick_nm, ph);
+        auto chi = [&](int q) { return mk(p->chi2[2 * (q * nE + e)], p->chi2[2 * (q * nE + e) + 1]); };
+        cplx k[7];
+        coeffs_pp(c, chi, ph, k); for (int j = 0; j < 7; ++j) kk[(size_t)(0 * 7 + j) * nE + e] = k[j];
+        coeffs_ps(c, chi, k);     for (int j = 0; j < 7; ++j) kk[(size_t)(1 * 7 + j) * nE + e] = k[j];
+        coeffs_sp(c, chi, k);     for (int j = 0; j < 7; ++j) kk[(size_t)(2 * 7 + j) * nE + e] = k[j];
+        coeffs_ss(c, chi, k);     for (int j = 0; j < 4; ++j) kk[(size_t)(3 * 7 + j) * nE + e] = k[j];
+    }
+    const long long FXT = 128;                                  // FX_TILE of the kernel
     for (long long ip = 0; ip < nP; ++ip) {
-        double t[12];
+        double t[12], bb[6];
         phi_harmonics(phi_deg[ip], t);
-        for (int pol = 0; pol < 4; ++pol)
+        phi_basis(phi_deg[ip], bb);
+        for (int pol = 0; pol < 4; ++pol) {
+            std::vector<char> flag((size_t)((nE + FXT - 1) / FXT), 0);
             for (long long e = 0; e < nE; ++e) {
                 double H[NH];
                 const int nh = pol == 3 ? NH_SS : NH;
                 for (int m = 0; m < nh; ++m) H[m] = blur[(size_t)(off[pol] + m) * nE + e];
-                out[((size_t)pol * nP + ip) * nE + e] = harmonic_yield(H, t, pol == 3);
+                const double y = harmonic_yield(H, t, pol == 3);
+                out[((size_t)pol * nP + ip) * nE + e] = y;
+                if (strict_nodes && y < NODE_FRACTION * amplitude_bound(H, pol == 3)) flag[(size_t)(e / FXT)] = 1;
             }
+            for (size_t tl = 0; tl < flag.size(); ++tl) {
+                if (!flag[tl]) continue;
+                auto raw_y = [&](long long e) {
+                    const cplx* k = &kk[(size_t)(pol * 7) * nE + e];
+                    double re, im;
+                    if (pol == 3) {
+                        re = k[0].re * bb[2]; im = k[0].im * bb[2];
+                        for (int j = 1; j < 4; ++j) { re = fma(k[(size_t)j * nE].re, bb[j + 2], re); im = fma(k[(size_t)j * nE].im, bb[j + 2], im); }
+                    } else {
+                        re = k[0].re; im = k[0].im;
+                        for (int j = 0; j < 6; ++j) { re = fma(k[(size_t)(j + 1) * nE].re, bb[j], re); im = fma(k[(size_t)(j + 1) * nE].im, bb[j], im); }
+                    }
+                    return fma(re, re, im * im);
+                };
+                for (long long e = (long long)tl * FXT; e < nE && e < (long long)(tl + 1) * FXT; ++e) {
+                    double acc = raw_y(e) * w[0];
+                    for (int j = r; j >= 1; --j) acc = fma(raw_y(reflect(e - j)) + raw_y(reflect(e + j)), w[j], acc);
+                    out[((size_t)pol * nP + ip) * nE + e] = acc;
+                }
+            }
+        }
     }
     return 0;
 }

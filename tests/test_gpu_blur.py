@@ -4,9 +4,11 @@ broadening of shgyield() (broad(., sigma_out) along the energy axis, reference s
 computed in one pass, against the CPU oracle (un-broadened yields -> scipy-style gaussian filter row by
 row) and against the two-pass device path (K2 -> K1, SSHG_K3=0).
 
-Tolerance: tests/cases.py::parity_ok with rtol 1e-10; K3's error is absolute (a few 1e-15 of the column's
-maximum over phi, checked here as < 5e-14), so the element-wise relative part of the metric starts at
-1e-4 of the maximum for it (1e-6 for the two-pass path).
+Tolerance: tests/cases.py::parity_ok with rtol 1e-10 in the strict metric (element-wise wherever the yield is
+>= 1e-6 of the maximum).  The harmonic sum of K3 alone has an absolute error (a few 1e-15 of the column's
+maximum over phi, checked here as < 5e-14); the segments where that is not enough -- values below 1e-3 of the
+column's amplitude bound, i.e. next to an azimuthal node -- are flagged by K3 and re-evaluated row-wise by
+yield_blur_fixup_kernel, so the product holds the strict metric (SSHG_K3_FIXUP=0 shows K3 alone).
 """
 import os
 
@@ -45,7 +47,7 @@ def _check(got, want, fused, what, col_bound=5e-14):
     top = np.max(want)
     for k, pol in enumerate(cases.POLS):
         a, b = got[:, :, k], want[:, :, k]
-        ok, msg = cases.parity_ok(a, b, rtol=RTOL, scale=top, rel_floor=1e-4 if fused else 1e-6)
+        ok, msg = cases.parity_ok(a, b, rtol=RTOL, scale=top)      # K3 + fix-up and the two-pass path: the strict metric
         assert ok, (what, pol, msg)
         colmax = np.maximum(np.max(b, axis=2, keepdims=True), 1e-12 * top)       # max over phi of every column
         assert np.max(np.abs(a - b) / colmax) < col_bound, (what, pol)
@@ -153,7 +155,7 @@ def test_api_sweep_with_output_broadening_matches_the_reference_loop(grid):
             ref = orc.shgyield(energy, m1, m2, m3, chi2, th, ph, 10.0, gamma=35, sigma_out=5.0)
             sc = max(np.max(ref[p]) for p in cases.POLS)
             for pol in cases.POLS:
-                ok, msg = cases.parity_ok(res[pol][it, 0, ip], ref[pol], rtol=RTOL, scale=sc, rel_floor=1e-4)
+                ok, msg = cases.parity_ok(res[pol][it, 0, ip], ref[pol], rtol=RTOL, scale=sc)
                 assert ok, (th, ph, pol, msg)
 
 
@@ -212,8 +214,12 @@ def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
         got = res["cube"][:, 0]                                         # [T, 4, P, E]
         top = float(np.max(want))
         for k, pol in enumerate(cases.POLS):
-            ok, msg = cases.parity_ok(got[:, k], want[:, k], rtol=RTOL, scale=top, rel_floor=1e-4 if path == "fused" else 1e-6)
+            ok, msg = cases.parity_ok(got[:, k], want[:, k], rtol=RTOL, scale=top)
             assert ok, (mat, sigma, path, pol, msg)
+            for it in range(want.shape[0]):                     # row by row: the rows 0.02 deg from a node included
+                for ip in range(want.shape[2]):
+                    ok, msg = cases.parity_ok(got[it, k, ip], want[it, k, ip], rtol=RTOL, scale=top)
+                    assert ok, (mat, sigma, path, pol, "row", it, ip, msg)
             colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
             assert np.max(np.abs(got[:, k] - want[:, k]) / colmax) < 5e-14, (mat, sigma, path, pol)
 
@@ -235,10 +241,9 @@ def test_config3_config4_full_size_broadened(grid, tag):
     top = float(cube.max())
     assert float(cube.min()) >= -1e-13 * top                            # the harmonic sum may undershoot 0 by rounding
     # complete rows: per (theta, thickness) a set of azimuths that includes exact C3v nodes (0, 30, 90, 180 deg),
-    # near-node rows (1, 91) and an off-node row (45); M = max over those rows of the oracle, a lower bound of the
-    # column's maximum over phi.  K3's statement is |error| <= 5e-14 * column maximum (here 1e-13 * M), which
-    # implies 1e-10 relative wherever the yield exceeds 1e-3 of its column maximum; the two-pass path of config 4
-    # holds the strict metric.
+    # near-node rows (1, 91) and an off-node row (45), each against the oracle in the strict metric ROW BY ROW
+    # (K3 flags the near-node segments and the fix-up kernel re-evaluates them); M = max over those rows of the
+    # oracle, a lower bound of the column's maximum over phi, for K3's absolute bound.
     cols = {"c3": [(0, 0), (65, 0), (89, 0)], "c4": [(0, 0), (65, 9), (89, 99)]}[tag]
     phis = [0, 1, 30, 45, 90, 91, 180, 359] if tag == "c3" else [0]
     for it, idd in cols:
@@ -252,6 +257,9 @@ def test_config3_config4_full_size_broadened(grid, tag):
                 M = np.maximum(want.max(axis=0, keepdims=True), 1e-30)
                 assert np.max(np.abs(got - want) / M) < 1e-13, (tag, it, pol)
                 assert np.max(np.abs(got - want)) <= RTOL * top
+                for j, ip in enumerate(phis):
+                    ok, msg = cases.parity_ok(got[j], want[j], rtol=RTOL, scale=sc4)
+                    assert ok, (tag, it, ip, pol, msg)
             else:
                 ok, msg = cases.parity_ok(got, want, rtol=RTOL, scale=sc4)      # sP / pS of Si(111) at phi = 30: pure node noise
                 assert ok, (tag, it, idd, pol, msg)
@@ -275,3 +283,27 @@ def test_config3_config4_full_size_broadened(grid, tag):
                 assert ok, ("strict", it, ip, pol, msg)
     del cube, res
     torch.cuda.empty_cache()
+
+
+def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metric(grid, monkeypatch):
+    """Si(111) rows 0.02 deg from the C3v nodes: without the fix-up kernel (SSHG_K3_FIXUP=0) K3's error is 5e-14 of
+    the column maximum, i.e. > 1e-10 relative on those rows; with it every row holds the strict metric."""
+    z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
+    m1, m2, m3, chi2 = cases.si111_material(cases.load_spectra())
+    want = z["si111_sigma5"]                                            # [T, 4, P, E]
+    top = float(np.max(want))
+    run = lambda: grid.shgyield_grid(z["energy"], m1, m2, m3, chi2, z["theta"], z["phi"], cases.BLUR_SWEEP_THICK,
+                                     gamma=0, sigma_out=5.0, device=False)["cube"][:, 0]
+    monkeypatch.setenv("SSHG_K3_FIXUP", "0")
+    alone = run()
+    monkeypatch.delenv("SSHG_K3_FIXUP")
+    fixed = run()
+    worst_alone = worst_fixed = 0.0
+    for k in range(4):
+        colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
+        assert np.max(np.abs(alone[:, k] - want[:, k]) / colmax) < 5e-14
+        sel = want[:, k] >= 1e-6 * top
+        worst_alone = max(worst_alone, float(np.max(np.abs(alone[:, k] - want[:, k])[sel] / want[:, k][sel])))
+        worst_fixed = max(worst_fixed, float(np.max(np.abs(fixed[:, k] - want[:, k])[sel] / want[:, k][sel])))
+    assert worst_fixed < 1e-10 < worst_alone, (worst_fixed, worst_alone)
+    assert np.count_nonzero(alone != fixed) > 0
