@@ -122,8 +122,16 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
                                            long long stride, bool vec, bool valid1, unsigned char* flo,
                                            unsigned char* fhi, unsigned char* fsg) {
     const bool flagging = flo != nullptr;
-    const double thr0 = flagging ? NODE_FRACTION * amplitude_bound(A0, SS) : -1.0;
-    const double thr1 = (flagging && valid1) ? NODE_FRACTION * amplitude_bound(A1, SS) : -1.0;
+    const double u0 = flagging ? amplitude_bound(A0, SS) : -1.0, u1 = (flagging && valid1) ? amplitude_bound(A1, SS) : -1.0;
+    const double thr0 = NODE_FRACTION * u0, thr1 = NODE_FRACTION * u1;          // negative (never hit) when not flagging
+    const double deep0 = DEEP_FRACTION * u0, deep1 = DEEP_FRACTION * u1;
+    // rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel;
+    // at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
+    auto node = [&](double& y0, double& y1, unsigned char* flag) {
+        if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) *flag = 1;
+        if (y0 < thr0) y0 = fmax(y0, 0.0);
+        if (y1 < thr1) y1 = fmax(y1, 0.0);
+    };
 #pragma unroll 2
     for (int i = 0; i < n_pair + n_single; ++i) {
         double t[12];
@@ -151,17 +159,17 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
             }
         }
         if (i < n_pair) {
-            const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
+            double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
+            if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, flo + i);
+            if ((s0 < thr0) | (s1 < thr1)) node(s0, s1, fhi + i);
             store2(plo, a0, a1, vec, valid1);
             store2(phi_, s0, s1, vec, valid1);
-            if ((a0 < thr0) | (a1 < thr1)) flo[i] = 1;
-            if ((s0 < thr0) | (s1 < thr1)) fhi[i] = 1;
             plo += stride;
             phi_ += stride;
         } else {
-            const double a0 = ye0 + yo0, a1 = ye1 + yo1;
+            double a0 = ye0 + yo0, a1 = ye1 + yo1;
+            if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, fsg + (i - n_pair));
             store2(psg, a0, a1, vec, valid1);
-            if ((a0 < thr0) | (a1 < thr1)) fsg[i - n_pair] = 1;
             psg += stride;
         }
     }

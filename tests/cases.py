@@ -211,3 +211,27 @@ def case_scale(gold: dict, prefix=""):
         if v.size:
             m = max(m, float(np.max(np.abs(v))))
     return m
+
+
+def rows_parity_ok(got, want, rtol=1e-10):
+    """Row-wise form of the metric for arrays [..., rows, E] of one polarisation: every row that reaches 1e-6 of the
+    array's maximum somewhere is held to `parity_ok` against ITS OWN maximum (element-wise rtol down to 1e-6 of the
+    row's maximum) -- this is what catches a loss of relative accuracy on rows next to an azimuthal node.  Rows
+    that stay below 1e-6 of the array's maximum everywhere (exact symmetry nodes) are outside the element-wise part
+    of the metric: they must agree to rtol * array maximum and must not be negative."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    top = float(np.max(np.abs(want[np.isfinite(want)]))) if np.isfinite(want).any() else 0.0
+    g2, w2 = got.reshape(-1, got.shape[-1]), want.reshape(-1, want.shape[-1])
+    for r in range(w2.shape[0]):
+        fin = np.isfinite(w2[r])
+        rmax = float(np.max(np.abs(w2[r][fin]))) if fin.any() else 0.0
+        if rmax >= 1e-6 * top:
+            ok, msg = parity_ok(g2[r], w2[r], rtol=rtol)
+            if not ok:
+                return False, "row %d (max %.3e of array max %.3e): %s" % (r, rmax, top, msg)
+        else:
+            if not np.array_equal(np.isfinite(g2[r]), fin):
+                return False, "row %d: non-finite pattern differs" % r
+            if fin.any() and (np.max(np.abs(g2[r][fin] - w2[r][fin])) > rtol * top or np.min(g2[r][fin]) < 0.0):
+                return False, "node row %d: abs err %.3e or negative" % (r, np.max(np.abs(g2[r][fin] - w2[r][fin])))
+    return True, "ok"

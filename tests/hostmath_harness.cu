@@ -243,9 +243,15 @@ extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, doub
                 double H[NH];
                 const int nh = pol == 3 ? NH_SS : NH;
                 for (int m = 0; m < nh; ++m) H[m] = blur[(size_t)(off[pol] + m) * nE + e];
-                const double y = harmonic_yield(H, t, pol == 3);
+                double y = harmonic_yield(H, t, pol == 3);
+                if (strict_nodes) {
+                    const double u = amplitude_bound(H, pol == 3);
+                    if (y < NODE_FRACTION * u) {
+                        if (y > DEEP_FRACTION * u) flag[(size_t)(e / FXT)] = 1;
+                        y = fmax(y, 0.0);
+                    }
+                }
                 out[((size_t)pol * nP + ip) * nE + e] = y;
-                if (strict_nodes && y < NODE_FRACTION * amplitude_bound(H, pol == 3)) flag[(size_t)(e / FXT)] = 1;
             }
             for (size_t tl = 0; tl < flag.size(); ++tl) {
                 if (!flag[tl]) continue;

@@ -217,9 +217,8 @@ def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
             ok, msg = cases.parity_ok(got[:, k], want[:, k], rtol=RTOL, scale=top)
             assert ok, (mat, sigma, path, pol, msg)
             for it in range(want.shape[0]):                     # row by row: the rows 0.02 deg from a node included
-                for ip in range(want.shape[2]):
-                    ok, msg = cases.parity_ok(got[it, k, ip], want[it, k, ip], rtol=RTOL, scale=top)
-                    assert ok, (mat, sigma, path, pol, "row", it, ip, msg)
+                ok, msg = cases.rows_parity_ok(got[it, k], want[it, k])
+                assert ok, (mat, sigma, path, pol, "theta", it, msg)
             colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
             assert np.max(np.abs(got[:, k] - want[:, k]) / colmax) < 5e-14, (mat, sigma, path, pol)
 
@@ -257,9 +256,8 @@ def test_config3_config4_full_size_broadened(grid, tag):
                 M = np.maximum(want.max(axis=0, keepdims=True), 1e-30)
                 assert np.max(np.abs(got - want) / M) < 1e-13, (tag, it, pol)
                 assert np.max(np.abs(got - want)) <= RTOL * top
-                for j, ip in enumerate(phis):
-                    ok, msg = cases.parity_ok(got[j], want[j], rtol=RTOL, scale=sc4)
-                    assert ok, (tag, it, ip, pol, msg)
+                ok, msg = cases.rows_parity_ok(got, want)
+                assert ok, (tag, it, pol, msg)
             else:
                 ok, msg = cases.parity_ok(got, want, rtol=RTOL, scale=sc4)      # sP / pS of Si(111) at phi = 30: pure node noise
                 assert ok, (tag, it, idd, pol, msg)
@@ -286,8 +284,8 @@ def test_config3_config4_full_size_broadened(grid, tag):
 
 
 def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metric(grid, monkeypatch):
-    """Si(111) rows 0.02 deg from the C3v nodes: without the fix-up kernel (SSHG_K3_FIXUP=0) K3's error is 5e-14 of
-    the column maximum, i.e. > 1e-10 relative on those rows; with it every row holds the strict metric."""
+    """Si(111) rows 0.02 deg from the C3v nodes: without the fix-up kernel (SSHG_K3_FIXUP=0) K3 holds its absolute
+    bound; the fix-up re-evaluates the near-node segments and every row holds the strict metric."""
     z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
     m1, m2, m3, chi2 = cases.si111_material(cases.load_spectra())
     want = z["si111_sigma5"]                                            # [T, 4, P, E]
@@ -298,15 +296,12 @@ def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metri
     alone = run()
     monkeypatch.delenv("SSHG_K3_FIXUP")
     fixed = run()
-    worst_alone = worst_fixed = 0.0
     for k in range(4):
         colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)
-        assert np.max(np.abs(alone[:, k] - want[:, k]) / colmax) < 5e-14
-        for ip in (1, 5):                                               # phi = 29.98 and 209.98 deg
-            w = want[:, k, ip]
-            sel = (w >= 1e-6 * np.max(w, axis=-1, keepdims=True)) & (w >= 1e-12 * top)
-            if sel.any():
-                worst_alone = max(worst_alone, float(np.max(np.abs(alone[:, k, ip] - w)[sel] / w[sel])))
-                worst_fixed = max(worst_fixed, float(np.max(np.abs(fixed[:, k, ip] - w)[sel] / w[sel])))
-    assert worst_fixed < 1e-10 < worst_alone, (worst_fixed, worst_alone)
-    assert np.count_nonzero(alone != fixed) > 0
+        assert np.max(np.abs(alone[:, k] - want[:, k]) / colmax) < 5e-14            # K3 alone: the absolute bound
+        assert np.max(np.abs(alone[:, k] - fixed[:, k]) / colmax) < 1e-13           # the fix-up moves values within it
+        for it in range(want.shape[0]):
+            ok, msg = cases.rows_parity_ok(fixed[it, k], want[it, k])               # ... and restores the strict metric
+            assert ok, (k, it, msg)
+    assert np.count_nonzero(alone != fixed) > 0                                      # near-node segments were re-evaluated
+    assert float(np.min(fixed)) >= 0.0
