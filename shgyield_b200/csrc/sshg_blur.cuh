@@ -115,6 +115,7 @@ __device__ __forceinline__ void fir_pair(const double* __restrict__ x, int S, in
 // strict way (NODE_FRACTION, amplitude_bound: sshg_math.cuh).
 constexpr int FX_NT = 64;                       // fix-up kernel: threads per CTA
 constexpr int FX_TILE = FX_NT * EPT;            // ... and energies per tile (flag granularity along E)
+constexpr int FX_RB = 4;                        // flagged rows evaluated together
 
 template <bool SS>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(FX_NT) yield_blur_fixup_kernel(const __grid_co
     double* wf = smem;                          // [2 R + 2]
     double* cols = wf + 2 * R + 2;              // [NCOL][S]   parked Column, struct of arrays
     double* kb = cols + NCOL * S;               // [14][S]     coefficients of the current polarisation
-    double* rowbuf = kb + 14 * S;               // [S]         un-broadened yields of the current row
+    double* rowbuf = kb + 14 * S;               // [FX_RB][S]  un-broadened yields of the current batch of rows
 
     const long long blk = blockIdx.x;
     const int tile = (int)(blk % a.n_tiles);
@@ -408,41 +409,70 @@ __global__ void __launch_bounds__(FX_NT) yield_blur_fixup_kernel(const __grid_co
             }
         }
         __syncthreads();
+        // flagged rows of this polarisation, FX_RB at a time: one pass over the staged energies evaluates the
+        // un-broadened yields of the whole batch, one pass filters them (two barriers per batch, FX_RB independent
+        // FMA chains per thread)
+        long long row = 0;
 #pragma unroll 1
-        for (long long row = 0; row < nP; ++row) {
-            if (!fb[pol * nP + row]) continue;                  // the same byte for every thread: uniform branch
-            double bb[6];
-            phi_basis(b.phi_deg[row], bb);
+        while (row < nP) {
+            int rows[FX_RB], nb = 0;
+            for (; row < nP && nb < FX_RB; ++row)
+                if (fb[pol * nP + row]) rows[nb++] = (int)row;      // the same bytes for every thread: uniform
+            if (nb == 0) break;
+            double bb[FX_RB][6];
+#pragma unroll
+            for (int q = 0; q < FX_RB; ++q) phi_basis(b.phi_deg[rows[q < nb ? q : 0]], bb[q]);
             for (int i = tid; i < S; i += FX_NT) {
-                double re, im;
-                if (pol == 3) {                                 // k[0..3] multiply {c^3, s c^2, s^2 c, s^3}
-                    re = kb[0 * S + i] * bb[2];
-                    im = kb[1 * S + i] * bb[2];
+                double kr[7], ki[7];
 #pragma unroll
-                    for (int j = 1; j < 4; ++j) {
-                        re = fma(kb[(2 * j) * S + i], bb[j + 2], re);
-                        im = fma(kb[(2 * j + 1) * S + i], bb[j + 2], im);
+                for (int j = 0; j < 7; ++j)
+                    if (j < nk) {
+                        kr[j] = kb[(2 * j) * S + i];
+                        ki[j] = kb[(2 * j + 1) * S + i];
                     }
-                } else {
-                    re = kb[0 * S + i];
-                    im = kb[1 * S + i];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        re = fma(kb[(2 * j + 2) * S + i], bb[j], re);
-                        im = fma(kb[(2 * j + 3) * S + i], bb[j], im);
+                for (int q = 0; q < FX_RB; ++q) {
+                    double re, im;
+                    if (pol == 3) {                             // k[0..3] multiply {c^3, s c^2, s^2 c, s^3}
+                        re = kr[0] * bb[q][2];
+                        im = ki[0] * bb[q][2];
+#pragma unroll
+                        for (int j = 1; j < 4; ++j) {
+                            re = fma(kr[j], bb[q][j + 2], re);
+                            im = fma(ki[j], bb[q][j + 2], im);
+                        }
+                    } else {
+                        re = kr[0];
+                        im = ki[0];
+#pragma unroll
+                        for (int j = 0; j < 6; ++j) {
+                            re = fma(kr[j + 1], bb[q][j], re);
+                            im = fma(ki[j + 1], bb[q][j], im);
+                        }
                     }
+                    rowbuf[q * S + i] = fma(re, re, im * im);
                 }
-                rowbuf[i] = fma(re, re, im * im);
             }
             __syncthreads();
             if (active) {
-                const double* x = rowbuf + tid * EPT;               // x[0 .. 2 R + 1]
-                double o0 = x[R] * wf[R], o1 = x[R + 1] * wf[R];    // centre tap, then the pairs from the farthest inwards
-                for (int j = R; j >= 1; --j) {
-                    o0 = fma(x[R - j] + x[R + j], wf[R + j], o0);
-                    o1 = fma(x[R + 1 - j] + x[R + 1 + j], wf[R + j], o1);
+                double o0[FX_RB], o1[FX_RB];
+                const double* x = rowbuf + tid * EPT;               // x[q S + 0 .. 2 R + 1]
+#pragma unroll
+                for (int q = 0; q < FX_RB; ++q) {                   // centre tap, then the pairs from the farthest inwards
+                    o0[q] = x[q * S + R] * wf[R];
+                    o1[q] = x[q * S + R + 1] * wf[R];
                 }
-                store2(out_col + (pol * nP + row) * nE, o0, o1, vec, valid1);
+                for (int j = R; j >= 1; --j) {
+                    const double w = wf[R + j];
+#pragma unroll
+                    for (int q = 0; q < FX_RB; ++q) {
+                        o0[q] = fma(x[q * S + R - j] + x[q * S + R + j], w, o0[q]);
+                        o1[q] = fma(x[q * S + R + 1 - j] + x[q * S + R + 1 + j], w, o1[q]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < FX_RB; ++q)
+                    if (q < nb) store2(out_col + (pol * nP + rows[q]) * nE, o0[q], o1[q], vec, valid1);
             }
             __syncthreads();
         }

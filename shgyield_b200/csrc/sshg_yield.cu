@@ -710,7 +710,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // row segments K3 flagged (yield next to an azimuthal node) the strict way.  SSHG_K3_FIXUP=0 disables (tests).
     const bool fixup = !(getenv("SSHG_K3_FIXUP") && atoi(getenv("SSHG_K3_FIXUP")) == 0);
     const int fx_tiles = (int)((p->nE + FX_TILE - 1) / FX_TILE);
-    const size_t fx_smem = (size_t)(2 * radius + 2 + (size_t)(NCOL + 14 + 1) * (FX_TILE + 2 * radius)) * sizeof(double);
+    const size_t fx_smem = (size_t)(2 * radius + 2 + (size_t)(NCOL + 14 + FX_RB) * (FX_TILE + 2 * radius)) * sizeof(double);
     if (fused && fixup)
         SSHG_CUDA(cudaFuncSetAttribute(yield_blur_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fx_smem));
     auto launch_blur = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {

@@ -205,6 +205,7 @@ def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
     """shgyield_grid(sigma_out) against rows produced by the UNMODIFIED reference, shgyield() called once per
     (theta, phi) (tests/golden/ref_blur_rows.npz; phi includes points 0.02 deg from the C3v nodes of Si(111))."""
     monkeypatch.setenv("SSHG_K3", "1" if path == "fused" else "0")
+    monkeypatch.setenv("SSHG_K2_SPARSE", "0")                            # 9 azimuths: K3 only when the dense path is forced
     z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
     m1, m2, m3, chi2 = cases.MATERIALS[mat](cases.load_spectra())
     for sigma in cases.BLUR_SWEEP_SIGMAS:
@@ -292,6 +293,7 @@ def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metri
     top = float(np.max(want))
     run = lambda: grid.shgyield_grid(z["energy"], m1, m2, m3, chi2, z["theta"], z["phi"], cases.BLUR_SWEEP_THICK,
                                      gamma=0, sigma_out=5.0, device=False)["cube"][:, 0]
+    monkeypatch.setenv("SSHG_K2_SPARSE", "0")                            # 9 azimuths: force the dense path (K3)
     monkeypatch.setenv("SSHG_K3_FIXUP", "0")
     alone = run()
     monkeypatch.delenv("SSHG_K3_FIXUP")

@@ -110,10 +110,12 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
            "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
            "free": rng.uniform(0, 360, 2 * h + 1)}[grid_kind]
     os.environ["SSHG_K3_NT"] = tiles
+    os.environ["SSHG_K2_SPARSE"] = "0"                     # fewer than 16 azimuths would otherwise take K2s -> K1
     try:
         got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS, sigma_out=sigma)
     finally:
         os.environ.pop("SSHG_K3_NT", None)
+        os.environ.pop("SSHG_K2_SPARSE", None)
     raw = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
     want = np.stack([orc.gaussian_filter1d(np.broadcast_to(raw[p], (nT, nD, phi.size, nE)), sigma, axis=-1)
                      for p in cases.POLS], axis=2)
