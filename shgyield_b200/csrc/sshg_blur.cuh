@@ -35,7 +35,10 @@ struct BlurArgs {
     int S;                                      // staged energies per CTA = 2 NT + 2 radius
     int chunk;                                  // phi items per table chunk (what fits behind the parked harmonics)
     unsigned char* flags;                       // [column][fix-up tile][pol][row]: 1 = re-evaluate strictly (or null)
+    int* work;                                  // work[0]: number of (column, tile) blocks with a flag; work[1 + k]: the
+                                                // k-th such block; work[1 + blocks + t]: block t already listed
     int fx_tiles;                               // fix-up tiles (FX_TILE energies) per column
+    int n_blocks;                               // columns of the launch x fx_tiles
     double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
 };
 
@@ -121,7 +124,7 @@ template <bool SS>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
                                            long long stride, bool vec, bool valid1, unsigned char* flo,
-                                           unsigned char* fhi, unsigned char* fsg) {
+                                           unsigned char* fhi, unsigned char* fsg, int* work, int* listed, int block_id) {
     const bool flagging = flo != nullptr;
     const double u0 = flagging ? amplitude_bound(A0, SS) : -1.0, u1 = (flagging && valid1) ? amplitude_bound(A1, SS) : -1.0;
     const double thr0 = NODE_FRACTION * u0, thr1 = NODE_FRACTION * u1;          // negative (never hit) when not flagging
@@ -129,7 +132,10 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
     // rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel;
     // at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
     auto node = [&](double& y0, double& y1, unsigned char* flag) {
-        if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) *flag = 1;
+        if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) {
+            *flag = 1;
+            if (atomicExch(listed, 1) == 0) work[1 + atomicAdd(work, 1)] = block_id;   // first flag of this block
+        }
         if (y0 < thr0) y0 = fmax(y0, 0.0);
         if (y1 < thr1) y1 = fmax(y1, 0.0);
     };
@@ -297,14 +303,22 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             double* phi_ = prow + (base + H) * nE;
             double* psg = prow + (base + n_pair + H) * nE;
             unsigned char *flo = nullptr, *fhi = nullptr, *fsg = nullptr;
+            int* listed = nullptr;
+            int block_id = 0;
             if (b.flags) {                      // flag block of this (column, fix-up tile, polarisation): one byte per row
-                unsigned char* fb = b.flags + ((lcol * b.fx_tiles + e0 / FX_TILE) * 4 + pol) * a.nP;
+                block_id = (int)(lcol * b.fx_tiles + e0 / FX_TILE);
+                unsigned char* fb = b.flags + ((long long)block_id * 4 + pol) * a.nP;
                 flo = fb + base;
                 fhi = fb + base + H;
                 fsg = fb + base + n_pair + H;
+                listed = b.work + 1 + b.n_blocks + block_id;
             }
-            if (pol == 3) sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg);
-            else sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg);
+            if (pol == 3)
+                sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg, b.work,
+                                 listed, block_id);
+            else
+                sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg, b.work,
+                                  listed, block_id);
         }
     }
 }
@@ -320,6 +334,7 @@ struct FixArgs {
     YieldArgs y;                                // y.tab unused
     const double* phi_deg;
     const unsigned char* flags;
+    const int* work;                            // the list K3 filled (see BlurArgs)
     int radius;
     int S;                                      // FX_TILE + 2 radius
     double w[BLUR_RMAX + 1];
@@ -334,21 +349,21 @@ __global__ void __launch_bounds__(FX_NT) yield_blur_fixup_kernel(const __grid_co
     double* kb = cols + NCOL * S;               // [14][S]     coefficients of the current polarisation
     double* rowbuf = kb + 14 * S;               // [FX_RB][S]  un-broadened yields of the current batch of rows
 
-    const long long blk = blockIdx.x;
-    const int tile = (int)(blk % a.n_tiles);
-    const long long lcol = blk / a.n_tiles;
     const int tid = threadIdx.x;
     const long long nE = a.nE, nP = a.nP;
-    const unsigned char* fb = b.flags + (lcol * a.n_tiles + tile) * 4 * nP;
-
-    int any = 0;
-    for (long long i = tid; i < 4 * nP; i += FX_NT) any |= fb[i];
-    if (!__syncthreads_or(any)) return;
+    const int n_work = b.work[0];               // blocks with at least one flagged row segment (usually few or none)
+    for (int t = tid; t <= 2 * b.radius; t += FX_NT) wf[t] = b.w[t < b.radius ? b.radius - t : t - b.radius];
+#pragma unroll 1
+    for (int item = blockIdx.x; item < n_work; item += gridDim.x) {
+    __syncthreads();                            // the previous block's shared memory is no longer read
+    const long long blk = b.work[1 + item];
+    const int tile = (int)(blk % a.n_tiles);
+    const long long lcol = blk / a.n_tiles;
+    const unsigned char* fb = b.flags + blk * 4 * nP;
 
     const long long col = a.col0 + lcol;
     const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
     const long long tile_e0 = (long long)tile * FX_TILE;
-    for (int t = tid; t <= 2 * R; t += FX_NT) wf[t] = b.w[t < R ? R - t : t - R];
     {
         double st, ct;
         sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
@@ -477,4 +492,5 @@ __global__ void __launch_bounds__(FX_NT) yield_blur_fixup_kernel(const __grid_co
             __syncthreads();
         }
     }
+    }   // work items
 }

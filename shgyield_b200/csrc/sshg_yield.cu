@@ -723,14 +723,20 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.n_seg = pick_segments(nc * blur_tiles, blur_per_sm, 0.0);        // K3's setup (halo, harmonics, FIR) is too
                                                                             // heavy to repeat: measured slower (tuning only)
         SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
-        void* flags = nullptr;
-        const size_t flag_bytes = (size_t)nc * fx_tiles * 4 * (size_t)p->nP;
+        void *flags = nullptr, *work = nullptr;
+        const size_t n_blocks = (size_t)nc * fx_tiles;
+        const size_t flag_bytes = n_blocks * 4 * (size_t)p->nP, work_bytes = (1 + 2 * n_blocks) * sizeof(int);
         if (fixup) {
+            SSHG_REQUIRE(n_blocks < (1ULL << 30), "sshg_yield: too many tiles for one launch");
             if (int rc = sshg_scratch(ctx, 13, flag_bytes, &flags)) return rc;
+            if (int rc = sshg_scratch(ctx, 14, work_bytes, &work)) return rc;
             SSHG_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, st));
+            SSHG_CUDA(cudaMemsetAsync(work, 0, work_bytes, st));
         }
         b.flags = (unsigned char*)flags;
+        b.work = (int*)work;
         b.fx_tiles = fx_tiles;
+        b.n_blocks = (int)n_blocks;
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
             yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
@@ -746,10 +752,13 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
             f.y.n_seg = 1;
             f.phi_deg = (const double*)dphi;
             f.flags = (const unsigned char*)flags;
+            f.work = (const int*)work;
             f.radius = ba.radius;
             f.S = FX_TILE + 2 * ba.radius;
             for (int k = 0; k <= ba.radius; ++k) f.w[k] = ba.w[k];
-            yield_blur_fixup_kernel<<<(unsigned)(nc * fx_tiles), FX_NT, fx_smem, st>>>(f);
+            // a fixed grid walks the list of flagged blocks (its length is only known on the device)
+            const size_t fx_grid = n_blocks < (size_t)4 * ctx->num_sms ? n_blocks : (size_t)4 * ctx->num_sms;
+            yield_blur_fixup_kernel<<<(unsigned)fx_grid, FX_NT, fx_smem, st>>>(f);
             SSHG_CUDA(cudaGetLastError());
             ctx->launches++;
         }
