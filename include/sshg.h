@@ -74,9 +74,9 @@ typedef struct {
 /* sshg_physics.flags */
 #define SSHG_FLAG_RADIANS 1  /* theta / phi of a point list are in radians (the reference's helpers) */
 #define SSHG_FLAG_STRICT_BROADENING 2  /* sshg_yield_broadened: broaden every yield row itself (yield kernel, then the
-                                          Gaussian FIR, slab by slab) instead of the 13 azimuthal harmonics of a column.
-                                          ~4.5x slower; keeps the element-wise 1e-10 even on rows that are within
-                                          1e-3 of an azimuthal node of the yield (DESIGN.md, K3 accuracy) */
+                                          Gaussian FIR, slab by slab, ~4.5x slower) instead of broadening the 13
+                                          azimuthal harmonics of a column and re-evaluating only the row segments
+                                          next to an azimuthal node (the default) */
 
 /* A rectangular sweep: energy x theta x phi x thickness (x 4 polarisations).
  * Replaces the reference's NumPy broadcast over rad_pp/ps/sp/ss + prefactor
@@ -176,8 +176,9 @@ SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out,
  * shg.py:26-28, 433-436; sigma_out in SAMPLES of the energy axis, 5.0 is the reference's default):
  * out[t][d][pol][p][:] = gaussian_filter(yield[t][d][pol][p][:], sigma_out) with scipy.ndimage's taps,
  * radius int(4 sigma + 0.5) and 'reflect' boundary.  Dense sweeps are broadened inside the yield kernel
- * (the FIR is applied to the 13 azimuthal harmonics of a column before the phi sweep), so the
- * cube is written once; sigma_out = 0 is sshg_yield. */
+ * (the FIR is applied to the 13 azimuthal harmonics of a column before the phi sweep; row segments whose
+ * yield is next to an azimuthal node are re-evaluated row-wise by a second, usually idle, kernel: DESIGN.md K3),
+ * so the cube is written once; sigma_out = 0 is sshg_yield. */
 SSHG_API int sshg_yield_broadened(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where);
 
 /* ---- the reference's public helper functions, element-wise over n values ------------------

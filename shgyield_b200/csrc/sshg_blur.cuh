@@ -22,8 +22,9 @@
 // table chunk by table chunk (the chunks live behind the parked harmonics, so they are as long as the
 // CTA's shared-memory share allows), four polarisations per chunk, phi / phi + 180 deg pairs sharing the
 // even and odd harmonic sums.
-// Accuracy: the sum of harmonics cancels where the yield has a node in phi, so the error is absolute --
-// a few 1e-15 of the column's azimuthal mean -- instead of relative (tests/test_hostmath.py).
+// Accuracy: the sum of harmonics cancels where the yield has a node in phi, so its error is absolute --
+// <= 5e-14 of the column's amplitude bound -- instead of relative.  Values next to a node are flagged in the
+// sweep and re-evaluated row-wise by yield_blur_fixup_kernel (below), which restores the element-wise 1e-10.
 constexpr int NT_BLUR = 64;                     // 128-energy tiles
 constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 28
 constexpr int NA = 3 * NH + NH_SS;              // harmonic spectra per column (46)

@@ -71,9 +71,9 @@ def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, co
                     strict_broadening=False):
     """Host arrays in, host cube out: float64 [T_shard, D_shard, 4, P, E].  The library computes
     slabs on the device and copies slab k back while slab k+1 is computed.  sigma_out > 0 broadens
-    every yield spectrum along the energy axis (shg.py:433-436) inside the yield kernel (K3; its error is
-    absolute, <= 5e-14 of the column's maximum over phi); strict_broadening=True filters every row itself
-    (yield kernel -> Gaussian FIR, ~4.5x slower, element-wise 1e-10 also next to azimuthal nodes)."""
+    every yield spectrum along the energy axis (shg.py:433-436) inside the yield kernel (K3; row segments next
+    to an azimuthal node are re-evaluated row-wise by the fix-up kernel); strict_broadening=True filters every
+    row itself (yield kernel -> Gaussian FIR, ~4.5x slower)."""
     ctx = _lib.context()
     keep = []
     flags = _lib.FLAG_STRICT_BROADENING if strict_broadening else 0
@@ -143,9 +143,9 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
     gather="peer" (theta shards on one node) instead lets every rank's kernel store its slab directly into
     rank 0's cube over NVLink (`PeerCube`): no slab buffer, no collective.
     sigma_out > 0 broadens along the energy axis only (a sweep has no meaning for blurring angles); it is
-    done inside the yield kernel (K3: the cube is written once; error <= 5e-14 of a column's maximum over phi).
-    strict=True broadens every row itself instead (K2 -> K1 by slabs, ~4.5x slower, element-wise 1e-10 also
-    on rows next to an azimuthal node of the yield).
+    done inside the yield kernel (K3: the cube is written once; the row segments next to an azimuthal node are
+    re-evaluated row-wise, so the result holds the reference to 1e-10 element-wise).  strict=True broadens
+    every row itself instead (K2 -> K1 by slabs, ~4.5x slower).
     """
     energy = np.atleast_1d(np.asarray(energy, dtype=np.float64)).ravel()
     theta = np.atleast_1d(np.asarray(theta, dtype=np.float64)).ravel()
