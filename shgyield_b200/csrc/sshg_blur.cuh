@@ -126,12 +126,20 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
                                            long long stride, bool vec, bool valid1, unsigned char* flo,
                                            unsigned char* fhi, unsigned char* fsg, int* work, int* listed, int block_id) {
+#ifdef SSHG_K3_NOFLAG                            // A/B measurement only: the sweep without the node test
+    const bool flagging = false;
+#else
     const bool flagging = flo != nullptr;
-    const double u0 = flagging ? amplitude_bound(A0, SS) : -1.0, u1 = (flagging && valid1) ? amplitude_bound(A1, SS) : -1.0;
-    const double thr0 = NODE_FRACTION * u0, thr1 = NODE_FRACTION * u1;          // negative (never hit) when not flagging
+#endif
+    const double u0 = flagging ? amplitude_bound(A0, SS) : 0.0, u1 = (flagging && valid1) ? amplitude_bound(A1, SS) : 0.0;
+    const double thr0 = NODE_FRACTION * u0, thr1 = NODE_FRACTION * u1;
     const double deep0 = DEEP_FRACTION * u0, deep1 = DEEP_FRACTION * u1;
-    // rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel;
-    // at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
+    // Common path: one integer compare per value (the high word of a double orders like the double; a negative
+    // value is "below" any threshold, a NaN above) -- the FP64 pipe sees nothing of the node test.  INT_MIN when
+    // not flagging: never below.
+    const int h0 = flagging ? __double2hiint(thr0) : (int)0x80000000, h1 = (flagging && valid1) ? __double2hiint(thr1) : (int)0x80000000;
+    // Rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel (and
+    // its block listed once); at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
     auto node = [&](double& y0, double& y1, unsigned char* flag) {
         if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) {
             *flag = 1;
@@ -168,15 +176,15 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
         }
         if (i < n_pair) {
             double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
-            if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, flo + i);
-            if ((s0 < thr0) | (s1 < thr1)) node(s0, s1, fhi + i);
+            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1)) node(a0, a1, flo + i);
+            if ((__double2hiint(s0) < h0) | (__double2hiint(s1) < h1)) node(s0, s1, fhi + i);
             store2(plo, a0, a1, vec, valid1);
             store2(phi_, s0, s1, vec, valid1);
             plo += stride;
             phi_ += stride;
         } else {
             double a0 = ye0 + yo0, a1 = ye1 + yo1;
-            if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, fsg + (i - n_pair));
+            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1)) node(a0, a1, fsg + (i - n_pair));
             store2(psg, a0, a1, vec, valid1);
             psg += stride;
         }
