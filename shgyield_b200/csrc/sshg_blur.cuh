@@ -140,13 +140,13 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
     const int h0 = flagging ? __double2hiint(thr0) : (int)0x80000000, h1 = (flagging && valid1) ? __double2hiint(thr1) : (int)0x80000000;
     // Rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel (and
     // its block listed once); at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
-    auto node = [&](double& y0, double& y1, unsigned char* flag) {
+    // The values are stored first, straight-line; the rare path stores the clamped values again.
+    auto node = [&](double y0, double y1, unsigned char* flag, double* p) {
         if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) {
             *flag = 1;
             if (atomicExch(listed, 1) == 0) work[1 + atomicAdd(work, 1)] = block_id;   // first flag of this block
         }
-        if (y0 < thr0) y0 = fmax(y0, 0.0);
-        if (y1 < thr1) y1 = fmax(y1, 0.0);
+        if ((y0 < 0.0) | (y1 < 0.0)) store2(p, fmax(y0, 0.0), fmax(y1, 0.0), vec, valid1);
     };
 #pragma unroll 2
     for (int i = 0; i < n_pair + n_single; ++i) {
@@ -175,17 +175,20 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
             }
         }
         if (i < n_pair) {
-            double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
-            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1)) node(a0, a1, flo + i);
-            if ((__double2hiint(s0) < h0) | (__double2hiint(s1) < h1)) node(s0, s1, fhi + i);
+            const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
             store2(plo, a0, a1, vec, valid1);
             store2(phi_, s0, s1, vec, valid1);
+            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1) | (__double2hiint(s0) < h0) | (__double2hiint(s1) < h1)) {
+                if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, flo + i, plo);
+                if ((s0 < thr0) | (s1 < thr1)) node(s0, s1, fhi + i, phi_);
+            }
             plo += stride;
             phi_ += stride;
         } else {
-            double a0 = ye0 + yo0, a1 = ye1 + yo1;
-            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1)) node(a0, a1, fsg + (i - n_pair));
+            const double a0 = ye0 + yo0, a1 = ye1 + yo1;
             store2(psg, a0, a1, vec, valid1);
+            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1))
+                if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, fsg + (i - n_pair), psg);
             psg += stride;
         }
     }
