@@ -121,6 +121,48 @@ constexpr int FX_NT = 64;                       // fix-up kernel: threads per CT
 constexpr int FX_TILE = FX_NT * EPT;            // ... and energies per tile (flag granularity along E)
 constexpr int FX_RB = 4;                        // flagged rows evaluated together
 
+// One azimuth item of the harmonic form for two energies: even and odd harmonic sums.
+template <bool SS>
+__device__ __forceinline__ void harm_item(const double* A0, const double* A1, const double* __restrict__ tb, double& ye0,
+                                          double& ye1, double& yo0, double& yo1) {
+    double t[12];
+#pragma unroll
+    for (int j = 0; j < (SS ? 3 : 6); ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
+        t[2 * j] = v.x;
+        t[2 * j + 1] = v.y;
+    }
+    ye0 = A0[0];
+    ye1 = A1[0];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        ye0 = fma(A0[1 + j], t[j], ye0);
+        ye1 = fma(A1[1 + j], t[j], ye1);
+    }
+    yo0 = 0.0;
+    yo1 = 0.0;
+    if (!SS) {
+        yo0 = A0[7] * t[6];
+        yo1 = A1[7] * t[6];
+#pragma unroll
+        for (int j = 1; j < 6; ++j) {
+            yo0 = fma(A0[7 + j], t[6 + j], yo0);
+            yo1 = fma(A1[7 + j], t[6 + j], yo1);
+        }
+    }
+}
+
+// (C) azimuthal sweep of the harmonic form, two energies per thread.  tb: items of 12 doubles
+// {cos, sin of 2, 4, 6 phi | cos, sin of 1, 3, 5 phi}; items below n_pair give the rows i and i + H.
+//
+// Node test.  The hot loop is branch-free: besides the stores it only tracks the minimum of the HIGH WORDS of the
+// values it produced (the high word of a double orders like the double, a negative value is below everything, a
+// NaN above), two integer ops per value.  After every SWEEP_SB items the minimum is compared with the high word of
+// NODE_FRACTION * U; only if a value of the block is that small -- rare -- the block is walked again: values in
+// the band (DEEP, NODE) * U flag their row segment for the fix-up kernel (and list the block once), negative
+// rounding noise at exact nodes is stored again clamped at 0.
+constexpr int SWEEP_SB = 8;
+
 template <bool SS>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
@@ -134,62 +176,50 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
     const double u0 = flagging ? amplitude_bound(A0, SS) : 0.0, u1 = (flagging && valid1) ? amplitude_bound(A1, SS) : 0.0;
     const double thr0 = NODE_FRACTION * u0, thr1 = NODE_FRACTION * u1;
     const double deep0 = DEEP_FRACTION * u0, deep1 = DEEP_FRACTION * u1;
-    // Common path: one integer compare per value (the high word of a double orders like the double; a negative
-    // value is "below" any threshold, a NaN above) -- the FP64 pipe sees nothing of the node test.  INT_MIN when
-    // not flagging: never below.
-    const int h0 = flagging ? __double2hiint(thr0) : (int)0x80000000, h1 = (flagging && valid1) ? __double2hiint(thr1) : (int)0x80000000;
-    // Rare path: values next to a node.  In the band (deep, thr) the segment is flagged for the fix-up kernel (and
-    // its block listed once); at exact nodes (below deep) the rounding noise of the harmonic sum is clamped at 0.
-    // The values are stored first, straight-line; the rare path stores the clamped values again.
+    const int INT_LOWEST = (int)0x80000000;     // when not flagging: nothing is ever below
+    const int h0 = flagging ? __double2hiint(thr0) : INT_LOWEST, h1 = (flagging && valid1) ? __double2hiint(thr1) : INT_LOWEST;
     auto node = [&](double y0, double y1, unsigned char* flag, double* p) {
+        if (!((y0 < thr0) | (y1 < thr1))) return;
         if (((y0 < thr0) & (y0 > deep0)) | ((y1 < thr1) & (y1 > deep1))) {
             *flag = 1;
             if (atomicExch(listed, 1) == 0) work[1 + atomicAdd(work, 1)] = block_id;   // first flag of this block
         }
         if ((y0 < 0.0) | (y1 < 0.0)) store2(p, fmax(y0, 0.0), fmax(y1, 0.0), vec, valid1);
     };
+    const int n_total = n_pair + n_single;
+#pragma unroll 1
+    for (int i0 = 0; i0 < n_total; i0 += SWEEP_SB) {
+        const int i1 = min(i0 + SWEEP_SB, n_total);
+        int mn0 = 0x7fffffff, mn1 = 0x7fffffff;
 #pragma unroll 2
-    for (int i = 0; i < n_pair + n_single; ++i) {
-        double t[12];
-#pragma unroll
-        for (int j = 0; j < (SS ? 3 : 6); ++j) {
-            const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
-            t[2 * j] = v.x;
-            t[2 * j + 1] = v.y;
-        }
-        tb += 12;
-        double ye0 = A0[0], ye1 = A1[0];
-#pragma unroll
-        for (int j = 0; j < 6; ++j) {
-            ye0 = fma(A0[1 + j], t[j], ye0);
-            ye1 = fma(A1[1 + j], t[j], ye1);
-        }
-        double yo0 = 0.0, yo1 = 0.0;
-        if (!SS) {
-            yo0 = A0[7] * t[6];
-            yo1 = A1[7] * t[6];
-#pragma unroll
-            for (int j = 1; j < 6; ++j) {
-                yo0 = fma(A0[7 + j], t[6 + j], yo0);
-                yo1 = fma(A1[7 + j], t[6 + j], yo1);
+        for (int i = i0; i < i1; ++i) {
+            double ye0, ye1, yo0, yo1;
+            harm_item<SS>(A0, A1, tb + 12 * i, ye0, ye1, yo0, yo1);
+            if (i < n_pair) {
+                const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
+                store2(plo + i * stride, a0, a1, vec, valid1);
+                store2(phi_ + i * stride, s0, s1, vec, valid1);
+                mn0 = min(mn0, min(__double2hiint(a0), __double2hiint(s0)));
+                mn1 = min(mn1, min(__double2hiint(a1), __double2hiint(s1)));
+            } else {
+                const double a0 = ye0 + yo0, a1 = ye1 + yo1;
+                store2(psg + (i - n_pair) * stride, a0, a1, vec, valid1);
+                mn0 = min(mn0, __double2hiint(a0));
+                mn1 = min(mn1, __double2hiint(a1));
             }
         }
-        if (i < n_pair) {
-            const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
-            store2(plo, a0, a1, vec, valid1);
-            store2(phi_, s0, s1, vec, valid1);
-            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1) | (__double2hiint(s0) < h0) | (__double2hiint(s1) < h1)) {
-                if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, flo + i, plo);
-                if ((s0 < thr0) | (s1 < thr1)) node(s0, s1, fhi + i, phi_);
+        if ((mn0 < h0) | (mn1 < h1)) {          // rare: a value of this block is next to a node
+#pragma unroll 1
+            for (int i = i0; i < i1; ++i) {
+                double ye0, ye1, yo0, yo1;
+                harm_item<SS>(A0, A1, tb + 12 * i, ye0, ye1, yo0, yo1);     // the same arithmetic: the same bits
+                if (i < n_pair) {
+                    node(ye0 + yo0, ye1 + yo1, flo + i, plo + i * stride);
+                    node(ye0 - yo0, ye1 - yo1, fhi + i, phi_ + i * stride);
+                } else {
+                    node(ye0 + yo0, ye1 + yo1, fsg + (i - n_pair), psg + (i - n_pair) * stride);
+                }
             }
-            plo += stride;
-            phi_ += stride;
-        } else {
-            const double a0 = ye0 + yo0, a1 = ye1 + yo1;
-            store2(psg, a0, a1, vec, valid1);
-            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1))
-                if ((a0 < thr0) | (a1 < thr1)) node(a0, a1, fsg + (i - n_pair), psg);
-            psg += stride;
         }
     }
 }
