@@ -166,10 +166,20 @@ __device__ __forceinline__ void harm_item(const double* A0, const double* A1, co
 #endif
 constexpr int SWEEP_SB = SSHG_SWEEP_SB;
 
-template <bool SS>
+template <bool VEC>
+__device__ __forceinline__ void store2t(double* p, double y0, double y1, bool valid1) {
+    if (VEC) {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(y0, y1));
+    } else {
+        __stcs(p, y0);
+        if (valid1) __stcs(p + 1, y1);
+    }
+}
+
+template <bool SS, bool VEC>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                           long long stride, bool vec, bool valid1, unsigned char* flo,
+                                           long long stride, bool valid1, unsigned char* flo,
                                            unsigned char* fhi, unsigned char* fsg, int* work, int* listed, int block_id) {
 #ifdef SSHG_K3_NOFLAG                            // A/B measurement only: the sweep without the node test
     const bool flagging = false;
@@ -187,42 +197,60 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
             *flag = 1;
             if (atomicExch(listed, 1) == 0) work[1 + atomicAdd(work, 1)] = block_id;   // first flag of this block
         }
-        if ((y0 < 0.0) | (y1 < 0.0)) store2(p, fmax(y0, 0.0), fmax(y1, 0.0), vec, valid1);
+        if ((y0 < 0.0) | (y1 < 0.0)) store2t<VEC>(p, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
     };
-    const int n_total = n_pair + n_single;
+    // pairs first (rows i and i + H), then the un-paired tail; each part in blocks of SWEEP_SB items
 #pragma unroll 1
-    for (int i0 = 0; i0 < n_total; i0 += SWEEP_SB) {
-        const int i1 = min(i0 + SWEEP_SB, n_total);
-        int mn0 = 0x7fffffff, mn1 = 0x7fffffff;
+    for (int part = 0; part < 2; ++part) {
+        const int n = part == 0 ? n_pair : n_single;
+        const double* tp = tb + (part == 0 ? 0 : 12 * n_pair);
+        double* p0 = part == 0 ? plo : psg;
+        double* p1 = phi_;
+        unsigned char* f0 = part == 0 ? flo : fsg;
+#pragma unroll 1
+        for (int i0 = 0; i0 < n; i0 += SWEEP_SB) {
+            const int nb = min(SWEEP_SB, n - i0);
+            int mn0 = 0x7fffffff, mn1 = 0x7fffffff;
+            const double* t = tp;
+            double *q0 = p0, *q1 = p1;
 #pragma unroll 2
-        for (int i = i0; i < i1; ++i) {
-            double ye0, ye1, yo0, yo1;
-            harm_item<SS>(A0, A1, tb + 12 * i, ye0, ye1, yo0, yo1);
-            if (i < n_pair) {
-                const double a0 = ye0 + yo0, a1 = ye1 + yo1, s0 = ye0 - yo0, s1 = ye1 - yo1;
-                store2(plo + i * stride, a0, a1, vec, valid1);
-                store2(phi_ + i * stride, s0, s1, vec, valid1);
-                mn0 = min(mn0, min(__double2hiint(a0), __double2hiint(s0)));
-                mn1 = min(mn1, min(__double2hiint(a1), __double2hiint(s1)));
-            } else {
+            for (int i = 0; i < nb; ++i) {
+                double ye0, ye1, yo0, yo1;
+                harm_item<SS>(A0, A1, t, ye0, ye1, yo0, yo1);
+                t += 12;
                 const double a0 = ye0 + yo0, a1 = ye1 + yo1;
-                store2(psg + (i - n_pair) * stride, a0, a1, vec, valid1);
+                store2t<VEC>(q0, a0, a1, valid1);
+                q0 += stride;
                 mn0 = min(mn0, __double2hiint(a0));
                 mn1 = min(mn1, __double2hiint(a1));
-            }
-        }
-        if ((mn0 < h0) | (mn1 < h1)) {          // rare: a value of this block is next to a node
-#pragma unroll 1
-            for (int i = i0; i < i1; ++i) {
-                double ye0, ye1, yo0, yo1;
-                harm_item<SS>(A0, A1, tb + 12 * i, ye0, ye1, yo0, yo1);     // the same arithmetic: the same bits
-                if (i < n_pair) {
-                    node(ye0 + yo0, ye1 + yo1, flo + i, plo + i * stride);
-                    node(ye0 - yo0, ye1 - yo1, fhi + i, phi_ + i * stride);
-                } else {
-                    node(ye0 + yo0, ye1 + yo1, fsg + (i - n_pair), psg + (i - n_pair) * stride);
+                if (part == 0) {
+                    const double s0 = ye0 - yo0, s1 = ye1 - yo1;
+                    store2t<VEC>(q1, s0, s1, valid1);
+                    q1 += stride;
+                    mn0 = min(mn0, __double2hiint(s0));
+                    mn1 = min(mn1, __double2hiint(s1));
                 }
             }
+            if ((mn0 < h0) | (mn1 < h1)) {      // rare: a value of this block is next to a node
+                t = tp;
+                q0 = p0;
+                q1 = p1;
+#pragma unroll 1
+                for (int i = 0; i < nb; ++i) {
+                    double ye0, ye1, yo0, yo1;
+                    harm_item<SS>(A0, A1, t, ye0, ye1, yo0, yo1);          // the same arithmetic: the same bits
+                    t += 12;
+                    node(ye0 + yo0, ye1 + yo1, f0 + i0 + i, q0);
+                    q0 += stride;
+                    if (part == 0) {
+                        node(ye0 - yo0, ye1 - yo1, fhi + i0 + i, q1);
+                        q1 += stride;
+                    }
+                }
+            }
+            tp += 12 * nb;
+            p0 += (long long)nb * stride;
+            if (part == 0) p1 += (long long)nb * stride;
         }
     }
 }
@@ -358,12 +386,16 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                 fsg = fb + base + n_pair + H;
                 listed = b.work + 1 + b.n_blocks + block_id;
             }
-            if (pol == 3)
-                sweep_harm<true>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg, b.work,
-                                 listed, block_id);
-            else
-                sweep_harm<false>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1, flo, fhi, fsg, b.work,
-                                  listed, block_id);
+#define SSHG_SWEEP(SS_, VEC_) \
+    sweep_harm<SS_, VEC_>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, valid1, flo, fhi, fsg, b.work, listed, block_id)
+            if (vec) {
+                if (pol == 3) SSHG_SWEEP(true, true);
+                else SSHG_SWEEP(false, true);
+            } else {
+                if (pol == 3) SSHG_SWEEP(true, false);
+                else SSHG_SWEEP(false, false);
+            }
+#undef SSHG_SWEEP
         }
     }
 }
