@@ -166,16 +166,6 @@ __device__ __forceinline__ void harm_item(const double* A0, const double* A1, co
 #endif
 constexpr int SWEEP_SB = SSHG_SWEEP_SB;
 
-template <bool VEC>
-__device__ __forceinline__ void store2t(double* p, double y0, double y1, bool valid1) {
-    if (VEC) {
-        __stcs(reinterpret_cast<double2*>(p), make_double2(y0, y1));
-    } else {
-        __stcs(p, y0);
-        if (valid1) __stcs(p + 1, y1);
-    }
-}
-
 template <bool SS, bool VEC>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
@@ -235,7 +225,7 @@ __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, c
                 t = tp;
                 q0 = p0;
                 q1 = p1;
-#pragma unroll 1
+#pragma unroll 2
                 for (int i = 0; i < nb; ++i) {
                     double ye0, ye1, yo0, yo1;
                     harm_item<SS>(A0, A1, t, ye0, ye1, yo0, yo1);          // the same arithmetic: the same bits

@@ -62,6 +62,18 @@ __device__ __forceinline__ void store2(double* p, double y0, double y1, bool vec
     }
 }
 
+// The same with the store width known at compile time: the sweeps are instantiated for both, so that their inner
+// loops carry no branch on it (a run-time flag costs a BSSY / BRA / BSYNC triple per store).
+template <bool VEC>
+__device__ __forceinline__ void store2t(double* p, double y0, double y1, bool valid1) {
+    if (VEC) {
+        __stcs(reinterpret_cast<double2*>(p), make_double2(y0, y1));
+    } else {
+        __stcs(p, y0);
+        if (valid1) __stcs(p + 1, y1);
+    }
+}
+
 // phi table: tab[0] = H (number of (phi, phi+180) pairs), then item rows of 6 doubles.
 // item i < H      -> rows i and i + H of the cube, basis of phi[i]
 // item i >= H     -> row i + H (the un-paired tail), basis of phi[i + H]
@@ -94,9 +106,10 @@ struct Coef7 {
 };
 
 // (C) for a 7-term polarisation, two energies per thread.
+template <bool VEC>
 __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const double* __restrict__ tb,
                                        int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                       long long stride, bool vec, bool valid1) {
+                                       long long stride, bool valid1) {
 #pragma unroll 2
     for (int i = 0; i < n_pair; ++i) {
         const double b0 = tb[0], b1 = tb[1], b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
@@ -111,8 +124,8 @@ __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const d
         double oi1 = fma(k1.i[6], b5, fma(k1.i[5], b4, fma(k1.i[4], b3, k1.i[3] * b2)));
         double ar0 = er0 + or0, ai0 = ei0 + oi0, sr0 = er0 - or0, si0 = ei0 - oi0;
         double ar1 = er1 + or1, ai1 = ei1 + oi1, sr1 = er1 - or1, si1 = ei1 - oi1;
-        store2(plo, fma(ar0, ar0, ai0 * ai0), fma(ar1, ar1, ai1 * ai1), vec, valid1);
-        store2(phi_, fma(sr0, sr0, si0 * si0), fma(sr1, sr1, si1 * si1), vec, valid1);
+        store2t<VEC>(plo, fma(ar0, ar0, ai0 * ai0), fma(ar1, ar1, ai1 * ai1), valid1);
+        store2t<VEC>(phi_, fma(sr0, sr0, si0 * si0), fma(sr1, sr1, si1 * si1), valid1);
         plo += stride;
         phi_ += stride;
     }
@@ -128,7 +141,7 @@ __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const d
                     fma(k1.r[2], b1, fma(k1.r[1], b0, k1.r[0]))))));
         double i1 = fma(k1.i[6], b5, fma(k1.i[5], b4, fma(k1.i[4], b3, fma(k1.i[3], b2,
                     fma(k1.i[2], b1, fma(k1.i[1], b0, k1.i[0]))))));
-        store2(psg, fma(r0, r0, i0 * i0), fma(r1, r1, i1 * i1), vec, valid1);
+        store2t<VEC>(psg, fma(r0, r0, i0 * i0), fma(r1, r1, i1 * i1), valid1);
         psg += stride;
     }
 }
@@ -138,9 +151,10 @@ struct Coef4 {
 };
 
 // (C) for sS: odd part only, so the row at phi + 180 deg equals the row at phi.
+template <bool VEC>
 __device__ __forceinline__ void sweep4(const Coef4& k0, const Coef4& k1, const double* __restrict__ tb,
                                        int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                       long long stride, bool vec, bool valid1) {
+                                       long long stride, bool valid1) {
 #pragma unroll 2
     for (int i = 0; i < n_pair + n_single; ++i) {
         const double b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
@@ -151,12 +165,12 @@ __device__ __forceinline__ void sweep4(const Coef4& k0, const Coef4& k1, const d
         double i1 = fma(k1.i[3], b5, fma(k1.i[2], b4, fma(k1.i[1], b3, k1.i[0] * b2)));
         const double y0 = fma(r0, r0, i0 * i0), y1 = fma(r1, r1, i1 * i1);
         if (i < n_pair) {
-            store2(plo, y0, y1, vec, valid1);
-            store2(phi_, y0, y1, vec, valid1);
+            store2t<VEC>(plo, y0, y1, valid1);
+            store2t<VEC>(phi_, y0, y1, valid1);
             plo += stride;
             phi_ += stride;
         } else {
-            store2(psg, y0, y1, vec, valid1);
+            store2t<VEC>(psg, y0, y1, valid1);
             psg += stride;
         }
     }
@@ -259,7 +273,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
-                sweep4(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+                if (vec) sweep4<true>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
+                else sweep4<false>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
             } else {
                 Coef7 k[2];
 #pragma unroll
@@ -274,7 +289,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 #pragma unroll
                     for (int j = 0; j < 7; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
-                sweep7(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, vec, valid1);
+                if (vec) sweep7<true>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
+                else sweep7<false>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
             }
         }
     }
