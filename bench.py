@@ -500,7 +500,8 @@ def run_ours(args):
                           "unit": "points/s", "hbm_frac_rank0": 8.0 * my_pts / (blur_ms * 1e-3) / 1e9 / peak,
                           "how": "the same cube with shgyield()'s default output broadening (sigma_out = 5 samples "
                                  "along E) in one pass (K3: FIR on the 13 azimuthal harmonics of each column, "
-                                 "yield_blur_kernel), device resident, mean of 5 launches after 0.2 s of warm-up, max over ranks"},
+                                 "yield_blur_kernel, + yield_blur_fixup_kernel for row segments next to an azimuthal "
+                                 "node), device resident, mean of 5 launches after 0.2 s of warm-up, max over ranks"},
             "ms_per_step_device_max": mean_step_ms,
         }
         print(json.dumps(line), flush=True)
