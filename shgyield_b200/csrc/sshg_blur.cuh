@@ -81,6 +81,15 @@ __device__ __forceinline__ long long reflect_index(long long i, long long n) {
 template <int NHH>
 __device__ __forceinline__ void fir_pair(const double* __restrict__ x, int S, int R, const double* __restrict__ wf,
                                          double* A0, double* A1) {
+    if (R == 0) {                               // no broadening (experimental sigma_out = 0 path): the harmonics themselves
+#pragma unroll
+        for (int m = 0; m < NHH; ++m) {
+            const double2 v = *reinterpret_cast<const double2*>(x + m * S);
+            A0[m] = v.x;
+            A1[m] = v.y;
+        }
+        return;
+    }
     {
         const double w0 = wf[0], w1 = wf[1];
 #pragma unroll

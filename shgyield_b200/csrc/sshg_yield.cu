@@ -560,6 +560,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     const long long radius = sigma_out > 1e-15 ? (long long)(4.0 * sigma_out + 0.5) : 0;
     SSHG_REQUIRE(radius < (1LL << 28), "sshg_yield: sigma_out %g is too large", sigma_out);
     bool fused = radius >= 1 && radius <= BLUR_RMAX && !sparse;
+    // EXPERIMENT: SSHG_K2_HARMONIC=1 sends un-broadened dense sweeps through K3 with radius 0
+    // (harmonic sweep, 7 instead of 10 FP64 instructions per point, node segments re-evaluated by the fix-up kernel)
+    if (radius == 0 && !sparse && getenv("SSHG_K2_HARMONIC") && atoi(getenv("SSHG_K2_HARMONIC")) != 0) fused = true;
     if (p->phys.flags & SSHG_FLAG_STRICT_BROADENING) fused = false;
     if (const char* env = getenv("SSHG_K3")) fused = fused && atoi(env) != 0;
     const bool two_pass = radius >= 1 && !fused;
@@ -663,7 +666,8 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         ba.S = blur_nt * EPT + 2 * (int)radius;
         ba.chunk = (int)((blur_smem - live) / (12 * sizeof(double)));
         SSHG_REQUIRE(ba.chunk >= 1 && blur_smem >= need(blur_nt), "sshg_yield: internal: K3 shared-memory plan");
-        sshg_gaussian_taps(sigma_out, radius, ba.w);
+        if (radius >= 1) sshg_gaussian_taps(sigma_out, radius, ba.w);
+        else ba.w[0] = 1.0;
         if (blur_nt == NT_BLUR)
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
