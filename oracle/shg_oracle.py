@@ -16,8 +16,11 @@ Parity status: PINNED.  `tests/test_oracle_golden.py` checks this file against
     `example/reference/si111-reference.out`, 126 x 4 yields),
   * `tests/golden/selftest_reference.npz`   (the `REFERENCE` array of the
     reference's `tests/self_test.py:115-149`),
-  * `tests/golden/ref_outputs_*.npz`        (outputs of the unmodified reference
-    imported from /root/reference by `tests/golden/make_golden.py`).
+  * `tests/golden/ref_api_cases.npz`, `ref_helpers.npz`, `ref_grid_samples.npz`,
+    `ref_blur_rows.npz`                     (outputs of the unmodified reference
+    imported from /root/reference by `tests/golden/make_golden.py`: shgyield()
+    on 25 call shapes, the helper functions, sampled points of configs 3-5, and
+    a sweep broadened along the energy axis angle by angle).
 
 The restatement is table driven (one table row per term of the reference's
 formulas) rather than a transcription; every table cites the lines it follows.
