@@ -169,14 +169,22 @@ def shgyield_grid(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma
         import torch.distributed as dist
         dev = torch.device("cuda", _lib.context().device)
         put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=False)
-        pc = PeerCube((theta.size, thick.size, 4, phi.size, energy.size), dst=0)
-        yield_grid_device(put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot),
-                          mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out, out_ptr=pc.slab_ptr(t_range[0]),
-                          strict_broadening=strict)
-        torch.cuda.synchronize()
-        dist.barrier()
-        cube = pc.tensor()
-        pc.close()
+        dargs = (put(energy), put(theta), put(phi), put(thick), put(eps1w), put(eps2w), put(chi_rot))
+        try:
+            pc = PeerCube((theta.size, thick.size, 4, phi.size, energy.size), dst=0)     # raises on every rank or on none
+        except RuntimeError:
+            pc = None                               # no CUDA IPC / peer access on this node: compute, then NCCL gather
+        if pc is not None:
+            yield_grid_device(*dargs, mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out,
+                              out_ptr=pc.slab_ptr(t_range[0]), strict_broadening=strict)
+            torch.cuda.synchronize()
+            dist.barrier()
+            cube = pc.tensor()
+            pc.close()
+        else:
+            cube = yield_grid_device(*dargs, mref=mref, consts=consts, t_range=t_range, sigma_out=sigma_out,
+                                     strict_broadening=strict)
+            cube = gather_slabs(cube, theta.size, thick.size, shard)
     elif device:
         import torch
         dev = torch.device("cuda", _lib.context().device)
