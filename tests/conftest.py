@@ -12,6 +12,15 @@ warnings.filterwarnings("ignore", category=DeprecationWarning)
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The generated-input tests draw the same examples on every run (a regular test run is reproducible);
+    # SSHG_HYP_SCALE > 1 (the soak runs, tests/test_gpu_hypothesis.py) draws fresh ones.
+    try:
+        from hypothesis import settings
+        settings.register_profile("reproducible", derandomize=True)
+        settings.register_profile("soak", derandomize=False)
+        settings.load_profile("soak" if int(os.environ.get("SSHG_HYP_SCALE", "1")) > 1 else "reproducible")
+    except ImportError:
+        pass
 
 
 def pytest_collection_modifyitems(config, items):
