@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SSHG_ABI_VERSION 1
+#define SSHG_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SSHG_API __attribute__((visibility("default")))
@@ -93,7 +93,10 @@ typedef struct {
     const double* eps2w;      /* [3][nE][2]  eps(2w)                                    */
     const double* chi2;       /* [18][nE][2] chi2 rows in canonical order, ALREADY rotated */
     sshg_physics phys;
-    int64_t t0, t1, d0, d1;   /* shard (t1 = d1 = 0 means the full range)              */
+    int64_t t0, t1, d0, d1;   /* shard [t0, t1) x [d0, d1).  t1 = -1 (d1 = -1) selects the full range, and so does
+                                 t0 = t1 = 0 (a zero-initialised struct).  Any other empty range (t0 == t1 > 0: the
+                                 surplus ranks when there are more ranks than thetas) is legal: nothing is computed
+                                 or stored and the call returns SSHG_OK. */
 } sshg_problem;
 
 /* A list of independent points (the general NumPy-broadcast shape of shgyield()):
@@ -124,6 +127,22 @@ SSHG_API int sshg_ctx_set_stream(sshg_ctx* ctx, void* cuda_stream);
 SSHG_API void* sshg_ctx_stream(sshg_ctx* ctx);
 SSHG_API int sshg_ctx_sync(sshg_ctx* ctx);
 SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by this context so far */
+/* Test and tuning switches of ONE context (nothing in the library reads the environment).  They select
+ * between kernels that compute the same result, except "k3_fixup" = 0, which exists to test the error bound
+ * of the harmonic sums and is documented as NOT holding the element-wise parity metric.
+ * value -1 restores the library's own choice.  Keys:
+ *   "k2_sparse"     0 | 1     dense / sparse-phi yield kernel                 (default: by the number of azimuths)
+ *   "k2_nt"         64 | 256  CTA width of the dense yield kernel
+ *   "k2_recurrence" 0 | 1     phase recurrence on uniform thickness axes      (default 1)
+ *   "k3"            0 | 1     output broadening fused into the yield kernel   (default 1 where it applies)
+ *   "k3_nt"         64 | 128  CTA width of the fused kernel
+ *   "k3_fixup"      0 | 1     strict re-evaluation next to azimuthal nodes    (default 1)   TEST ONLY
+ *   "nseg"          1 .. 16   phi segments per column
+ *   "k1_generic"    0 | 1     generic instead of fixed-radius FIR kernels     (default 0)
+ *   "graphs"        0 | 1     CUDA-graph replay of small point-list calls      (default 1)
+ * Unknown keys and values outside the listed sets fail with SSHG_EINVAL. */
+SSHG_API int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value);
+SSHG_API int sshg_ctx_get_option(sshg_ctx* ctx, const char* key, int64_t* value);
 SSHG_API int sshg_host_alloc(void** ptr, int64_t bytes);  /* page-locked host memory for fast D2H    */
 SSHG_API int sshg_host_free(void* ptr);
 

@@ -7,6 +7,7 @@ call raises RuntimeError.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -18,7 +19,7 @@ LIB_PATH = os.path.join(HERE, "libsshg.so")
 
 SSHG_OK, SSHG_EINVAL, SSHG_ECUDA, SSHG_ENOMEM = 0, -1, -2, -3
 HOST, IN_DEVICE, OUT_DEVICE, DEVICE = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_RADIANS = 1
 FLAG_STRICT_BROADENING = 2
 IPC_HANDLE_BYTES = 64
@@ -59,6 +60,8 @@ SYMBOLS = {
     "sshg_ctx_stream": (C.c_void_p, [C.c_void_p]),
     "sshg_ctx_sync": (C.c_int, [C.c_void_p]),
     "sshg_ctx_launches": (C.c_int64, [C.c_void_p]),
+    "sshg_ctx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "sshg_ctx_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "sshg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "sshg_host_free": (C.c_int, [C.c_void_p]),
     "sshg_device_alloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]),
@@ -151,6 +154,38 @@ class Context:
 
     def sync(self):
         check(self.lib.sshg_ctx_sync(self.handle), self.lib)
+
+    def set_option(self, key: str, value: int | None):
+        """Test / tuning switch of this context (sshg_ctx_set_option, include/sshg.h); None = the library's choice."""
+        check(self.lib.sshg_ctx_set_option(self.handle, key.encode(), -1 if value is None else int(value)), self.lib)
+
+    def get_option(self, key: str) -> int | None:
+        v = C.c_int64()
+        check(self.lib.sshg_ctx_get_option(self.handle, key.encode(), C.byref(v)), self.lib)
+        return None if v.value == -1 else int(v.value)
+
+    @contextlib.contextmanager
+    def options(self, **kv):
+        """`with ctx.options(k3=0, k2_sparse=1): ...` -- sets the switches and restores the previous values."""
+        old = {k: self.get_option(k) for k in kv}
+        try:
+            for k, v in kv.items():
+                self.set_option(k, v)
+            yield self
+        finally:
+            for k, v in old.items():
+                self.set_option(k, v)
+
+    @contextlib.contextmanager
+    def on_stream(self, cuda_stream: int | None):
+        """Queue the library calls of the block on a caller's stream, then return to the context's own stream.
+        Both switches are ordered on the device (events), so the scratch buffers stay consistent and the context
+        never keeps the handle of a stream the caller may destroy."""
+        self.set_stream(cuda_stream)
+        try:
+            yield self
+        finally:
+            self.set_stream(None)
 
     @property
     def launches(self) -> int:

@@ -111,12 +111,14 @@ int sshg_ctx_create(int device, sshg_ctx** out) {
     }
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1};
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
         e = cudaEventCreateWithFlags(&ctx->ev_done[k], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copied[k], cudaEventDisableTiming);
     }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_switch, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         sshg_ctx_destroy(ctx);
         return sshg_cuda_fail(e, "stream/event creation", __FILE__, __LINE__);
@@ -137,6 +139,7 @@ void sshg_ctx_destroy(sshg_ctx* ctx) {
         if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
         if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
     }
+    if (ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     free(ctx);
@@ -147,8 +150,56 @@ int sshg_ctx_set_stream(sshg_ctx* ctx, void* cuda_stream) {
     cudaStream_t next = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     if (next == ctx->stream) return SSHG_OK;
     SSHG_CUDA(cudaSetDevice(ctx->device));
-    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));   // scratch buffers are ordered on the old stream
+    // The scratch buffers are ordered on the old stream: the new stream waits (on the device, no host
+    // synchronisation) for everything queued there.  Callers that adopt a temporary stream switch back to the
+    // context's own stream (NULL) before that stream is destroyed -- the Python binding does so in a finally clause.
+    SSHG_CUDA(cudaEventRecord(ctx->ev_switch, ctx->stream));
+    SSHG_CUDA(cudaStreamWaitEvent(next, ctx->ev_switch, 0));
     ctx->stream = next;
+    return SSHG_OK;
+}
+
+namespace {
+struct OptionKey {
+    const char* key;
+    int sshg_options::*field;
+    int lo, hi;             // allowed values besides -1
+    int only_a, only_b;     // when >= 0: the only two allowed values
+};
+const OptionKey kOptions[] = {
+    {"k2_sparse", &sshg_options::k2_sparse, 0, 1, -1, -1},
+    {"k2_nt", &sshg_options::k2_nt, 0, 0, 64, 256},
+    {"k2_recurrence", &sshg_options::k2_recurrence, 0, 1, -1, -1},
+    {"k3", &sshg_options::k3, 0, 1, -1, -1},
+    {"k3_nt", &sshg_options::k3_nt, 0, 0, 64, 128},
+    {"k3_fixup", &sshg_options::k3_fixup, 0, 1, -1, -1},
+    {"nseg", &sshg_options::nseg, 1, 16, -1, -1},
+    {"k1_generic", &sshg_options::k1_generic, 0, 1, -1, -1},
+    {"graphs", &sshg_options::graphs, 0, 1, -1, -1},
+};
+const OptionKey* find_option(const char* key) {
+    for (const OptionKey& o : kOptions)
+        if (strcmp(o.key, key) == 0) return &o;
+    return nullptr;
+}
+}  // namespace
+
+int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value) {
+    SSHG_REQUIRE(ctx && key, "sshg_ctx_set_option: null argument");
+    const OptionKey* o = find_option(key);
+    SSHG_REQUIRE(o, "sshg_ctx_set_option: unknown option '%s'", key);
+    const bool ok = value == -1 || (o->only_a >= 0 ? (value == o->only_a || value == o->only_b)
+                                                   : (value >= o->lo && value <= o->hi));
+    SSHG_REQUIRE(ok, "sshg_ctx_set_option: value %lld is not allowed for '%s'", (long long)value, key);
+    ctx->opt.*(o->field) = (int)value;
+    return SSHG_OK;
+}
+
+int sshg_ctx_get_option(sshg_ctx* ctx, const char* key, int64_t* value) {
+    SSHG_REQUIRE(ctx && key && value, "sshg_ctx_get_option: null argument");
+    const OptionKey* o = find_option(key);
+    SSHG_REQUIRE(o, "sshg_ctx_get_option: unknown option '%s'", key);
+    *value = ctx->opt.*(o->field);
     return SSHG_OK;
 }
 

@@ -323,7 +323,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         ctx->tap_sigma = sigma;
         ctx->tap_ptr = dw;
     }
-    if (elem_stride == 1 && !getenv("SSHG_K1_GENERIC")) {
+    if (elem_stride == 1 && ctx->opt.k1_generic != 1) {
         switch (r) {                               // radii with a compile-time specialisation
 #define SSHG_FIXED(R_) case R_: return launch_fixed<R_>(ctx, din, dout, rows, n, row_stride, ctx->tap_host);
             SSHG_FIXED(4) SSHG_FIXED(6) SSHG_FIXED(8) SSHG_FIXED(10) SSHG_FIXED(12) SSHG_FIXED(14) SSHG_FIXED(16)

@@ -23,13 +23,28 @@ struct sshg_trace_range {
 #define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel (slot 19: thickness-axis info)
 #define SCR_BROAD 16     // broadened rows handed from K1 to the spline kernels
 
+// Test / tuning switches of a context (sshg_ctx_set_option, include/sshg.h); -1 = the library decides.
+struct sshg_options {
+    int k2_sparse;      // 0 / 1: force the dense / sparse-phi yield kernel
+    int k2_nt;          // 64 / 256: CTA width of the dense yield kernel
+    int k2_recurrence;  // 0: no phase recurrence on uniform thickness axes
+    int k3;             // 0: never fuse the output broadening (K2 -> K1 by slabs)
+    int k3_nt;          // 64 / 128: CTA width of the fused kernel
+    int k3_fixup;       // 0: leave the harmonic sums next to azimuthal nodes as they are (tests of the error bound)
+    int nseg;           // phi segments per column (1 .. 16)
+    int k1_generic;     // 1: never use the fixed-radius FIR kernels
+    int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
+};
+
 struct sshg_ctx {
     int device;
+    sshg_options opt;
     cudaStream_t own_stream;
     cudaStream_t stream;        // own_stream or an adopted caller stream
     cudaStream_t copy_stream;   // D2H of finished slabs while the next slab is computed
     cudaEvent_t ev_done[2];     // slab k computed
     cudaEvent_t ev_copied[2];   // slab k copied to the host
+    cudaEvent_t ev_switch;      // orders the scratch buffers across a change of stream
     int num_sms;
     int64_t launches;
     double tap_sigma;           // sigma whose taps are in scratch[SCR_TAPS] (tap_ptr guards reallocation)

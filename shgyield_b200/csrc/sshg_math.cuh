@@ -338,15 +338,11 @@ SSHG_HD void phi_harmonics(double phi_deg, double t[12]) {
 }
 
 // U = |C0| + sum_q sqrt(C_q^2 + S_q^2) >= max over phi of the harmonic sum.  The rounding error of that sum is
-// <= 5e-14 U, so a value below NODE_FRACTION * U (the yield next to an azimuthal node) is no longer accurate to
-// 1e-10 relative: K3 flags it and the fix-up kernel re-evaluates it the strict way.  With 1e-3 everything
-// that is NOT flagged keeps an element-wise error below 5e-11.
+// <= 5e-14 U, so a value below NODE_FRACTION * U (the yield next to an azimuthal node, or an exact symmetry zero,
+// where the sum returns rounding noise of either sign) is no longer accurate to 1e-10 relative: K3 flags its row
+// and re-evaluates it the reference's way (|r|^2 per energy, then the FIR).  With 1e-3 everything that is NOT
+// flagged keeps an element-wise error below 5e-11.
 constexpr double NODE_FRACTION = 1e-3;
-// Values below DEEP_FRACTION * U are exact nodes (symmetry zeros; K3 returns rounding noise of ~1e-15 U there,
-// clamped at 0).  They are not re-evaluated: U <= 13 max_phi y, so such a value is below 1e-6 of the maximum of
-// any array that contains its column, i.e. outside the element-wise part of the parity metric, and the
-// `1e-10 * max` part holds with four orders to spare.
-constexpr double DEEP_FRACTION = 1e-8;
 
 SSHG_HD double amplitude_bound(const double* H, bool odd_only) {
     double u = fabs(H[0]);

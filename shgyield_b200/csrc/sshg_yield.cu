@@ -523,11 +523,14 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     SSHG_REQUIRE(p->energy_eV && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
                  "sshg_yield: null input array");
     if (int rc = check_physics(p->phys)) return rc;
-    const int64_t t0 = p->t0, t1 = p->t1 ? p->t1 : p->nT, d0 = p->d0, d1 = p->d1 ? p->d1 : p->nD;
-    SSHG_REQUIRE(0 <= t0 && t0 < t1 && t1 <= p->nT, "sshg_yield: bad theta shard [%lld,%lld) of %lld",
+    // shard: t1 = -1 or t0 = t1 = 0 is the full range; any other empty range is a legal no-op (include/sshg.h)
+    const bool t_full = p->t1 == -1 || (p->t0 == 0 && p->t1 == 0), d_full = p->d1 == -1 || (p->d0 == 0 && p->d1 == 0);
+    const int64_t t0 = t_full ? 0 : p->t0, t1 = t_full ? p->nT : p->t1, d0 = d_full ? 0 : p->d0, d1 = d_full ? p->nD : p->d1;
+    SSHG_REQUIRE(0 <= t0 && t0 <= t1 && t1 <= p->nT, "sshg_yield: bad theta shard [%lld,%lld) of %lld",
                  (long long)t0, (long long)t1, (long long)p->nT);
-    SSHG_REQUIRE(0 <= d0 && d0 < d1 && d1 <= p->nD, "sshg_yield: bad thickness shard [%lld,%lld) of %lld",
+    SSHG_REQUIRE(0 <= d0 && d0 <= d1 && d1 <= p->nD, "sshg_yield: bad thickness shard [%lld,%lld) of %lld",
                  (long long)d0, (long long)d1, (long long)p->nD);
+    if (t0 == t1 || d0 == d1) return SSHG_OK;            // empty shard (more ranks than thetas): nothing to do
     SSHG_REQUIRE(p->nP < (1LL << 31) && p->nE < (1LL << 40), "sshg_yield: axis too long");
     SSHG_CUDA(cudaSetDevice(ctx->device));
 
@@ -554,17 +557,15 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     // Output broadening (shg.py:433-436): radius as scipy.ndimage (int(4 sigma + 0.5)); a radius of 0 is the
     // identity.  Dense sweeps with radius <= 64 take the fused kernel K3, everything else K2 -> K1 slab by slab.
-    // SSHG_K3=0 forces the two-pass path (tests compare both).
+    // Option "k3" = 0 forces the two-pass path (tests compare both).
+    const sshg_options& opt = ctx->opt;                  // test / tuning switches (sshg_ctx_set_option); -1 = automatic
     bool sparse = 4 * p->nP < 64;
-    if (const char* env = getenv("SSHG_K2_SPARSE")) sparse = atoi(env) != 0;
+    if (opt.k2_sparse >= 0) sparse = opt.k2_sparse != 0;
     const long long radius = sigma_out > 1e-15 ? (long long)(4.0 * sigma_out + 0.5) : 0;
     SSHG_REQUIRE(radius < (1LL << 28), "sshg_yield: sigma_out %g is too large", sigma_out);
     bool fused = radius >= 1 && radius <= BLUR_RMAX && !sparse;
-    // EXPERIMENT: SSHG_K2_HARMONIC=1 sends un-broadened dense sweeps through K3 with radius 0
-    // (harmonic sweep, 7 instead of 10 FP64 instructions per point, node segments re-evaluated by the fix-up kernel)
-    if (radius == 0 && !sparse && getenv("SSHG_K2_HARMONIC") && atoi(getenv("SSHG_K2_HARMONIC")) != 0) fused = true;
     if (p->phys.flags & SSHG_FLAG_STRICT_BROADENING) fused = false;
-    if (const char* env = getenv("SSHG_K3")) fused = fused && atoi(env) != 0;
+    if (opt.k3 == 0) fused = false;
     const bool two_pass = radius >= 1 && !fused;
 
     void* tab;
@@ -585,12 +586,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // config-5 shards they reach 0.95-0.97 of the HBM peak where 256-thread CTAs reach 0.89-0.92 (shorter
     // tail, more CTAs to interleave), and they tie on the full cube.  Sweeps with few rows per column
     // (config 4: P = 1) are bound by the column setup and run 256-thread CTAs (1.55 ms against 1.96 ms).
-    // SSHG_K2_NT=64|256 overrides (tuning).
+    // Option "k2_nt" = 64 | 256 overrides (tuning).
     int nt = (4 * p->nP >= 64) ? NT_SMALL : NT_BIG;
-    if (const char* env = getenv("SSHG_K2_NT")) {
-        if (atoi(env) == NT_SMALL) nt = NT_SMALL;
-        else if (atoi(env) == NT_BIG) nt = NT_BIG;
-    }
+    if (opt.k2_nt == NT_SMALL || opt.k2_nt == NT_BIG) nt = opt.k2_nt;
     a.n_tiles = (int)((p->nE + nt * EPT - 1) / (nt * EPT));
     a.n_seg = 1;
     a.ph = make_physics(p->phys);
@@ -605,7 +603,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
 
     // Sweeps with few azimuths per column go through the sparse-phi kernel (phi-contracted chi2,
-    // thickness loop inside the thread).  SSHG_K2_SPARSE=0|1 overrides (tests run both kernels).
+    // thickness loop inside the thread).  option "k2_sparse" = 0 | 1 overrides (tests run both kernels).
     SparseArgs sa{};
     if (sparse) {
         void* dX;
@@ -620,11 +618,11 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         sa.nE = p->nE; sa.nP = p->nP; sa.nDs = a.nDs; sa.t0 = a.t0; sa.d0 = a.d0;
         sa.n_tiles = (int)((p->nE + SNT - 1) / SNT);
         sa.ph = a.ph;
-        // uniformly spaced thicknesses -> phase factors by recurrence (SSHG_K2_NO_RECURRENCE disables)
+        // uniformly spaced thicknesses -> phase factors by recurrence (option "k2_recurrence" = 0 disables)
         void* dinfo;
         if (int rc = sshg_scratch(ctx, SCR_XPHI + 1, 16, &dinfo)) return rc;
         thick_uniform_kernel<<<1, 256, 0, ctx->stream>>>(a.thick_nm, p->nD, (double*)dinfo,
-                                                       getenv("SSHG_K2_NO_RECURRENCE") ? 0 : 1);
+                                                       opt.k2_recurrence == 0 ? 0 : 1);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         sa.dinfo = (const double*)dinfo;
@@ -632,42 +630,39 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     BlurArgs ba{};
     size_t blur_smem = 0;
-    // Tile width and shared-memory plan of K3.  A CTA needs wf[2 R + 2] + raw[46][tile + 2 R]; once the FIRs are
-    // done only blur[46][tile] of that is live and the phi table chunks use everything behind it.  256-energy
-    // tiles (128 threads) halve the halo overhead and measured 0.94 of the HBM peak against 0.89 on a 46-theta
-    // shard of config 5 -- as long as two of them fit on an SM (radius <= 28); beyond that 128-energy tiles
-    // (3 .. 2 CTAs/SM).  The allocation is grown up to the occupancy's share of the SM so that the table chunks
-    // are as long as possible (each chunk costs two CTA-wide barriers).  SSHG_K3_NT=64|128 overrides (tuning).
+    // Tile width and shared-memory plan of K3.  A CTA holds wf[2 R + 2] + cols[20][S] + raw[13][S] (S = tile + 2 R) and
+    // the phi table (12 doubles per item) behind them; what does not fit is staged in chunks, polarisation by
+    // polarisation.  256-energy tiles (128 threads, register-limited to 2 CTAs/SM) halve the halo overhead of
+    // 128-energy tiles and fit twice on an SM for every fused radius (R = 64: 101 KB + 11 KB of table), so they are
+    // used whenever the axis is longer than one narrow tile.  Option "k3_nt" = 64 | 128 overrides (tests run both).
     int blur_nt = NT_BLUR, blur_per_sm = 1;
     if (fused) {
         const size_t sm_bytes = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
-        auto need = [&](int nt) { return (size_t)(2 * radius + 2 + (size_t)NA * (nt * EPT + 2 * radius)) * sizeof(double); };
+        auto fixed = [&](int nt) { return (size_t)blur_fixed_doubles((int)radius, nt * EPT + 2 * (int)radius) * sizeof(double); };
+        auto need = [&](int nt) { return fixed(nt) + (size_t)blur_chunk_doubles(32) * sizeof(double); };
         auto share = [&](int per_sm) { return sm_bytes / per_sm - 1024; };     // 1 KB per CTA is reserved by the system
-        const bool wide_fits2 = need(NT_BLUR_WIDE) <= share(2);
-        if (wide_fits2 && p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
-        if (const char* env = getenv("SSHG_K3_NT")) {
-            if (atoi(env) == NT_BLUR) blur_nt = NT_BLUR;
-            else if (atoi(env) == NT_BLUR_WIDE && need(NT_BLUR_WIDE) <= cta_max) blur_nt = NT_BLUR_WIDE;
-        }
-        const int reg_limit = blur_nt == NT_BLUR ? 4 : 2;                      // 212 registers per thread
+        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
+        if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE) blur_nt = opt.k3_nt;
+        SSHG_REQUIRE(need(blur_nt) <= cta_max, "sshg_yield: internal: K3 shared-memory plan");
+        const int reg_limit = blur_nt == NT_BLUR ? 3 : 2;                      // registers per thread (launch bounds)
         blur_per_sm = 1;
         for (int k = reg_limit; k >= 1; --k)
             if (need(blur_nt) <= share(k)) { blur_per_sm = k; break; }
-        if (blur_nt == NT_BLUR && blur_per_sm > 3) blur_per_sm = 3;            // more table, fewer barriers
         // grow the allocation to this occupancy's share, but not beyond what the whole table needs
-        const size_t live = (size_t)(2 * radius + 2 + (size_t)NA * blur_nt * EPT) * sizeof(double);
-        const size_t items_max = (size_t)p->nP;                                // un-paired grid: one item per phi
-        size_t total = live + items_max * 12 * sizeof(double);
+        const int items_all = (int)((p->nP + 31) / 32 * 32);                   // un-paired grid: one item per phi
+        size_t total = fixed(blur_nt) + (size_t)blur_chunk_doubles(items_all) * sizeof(double);
         if (total > share(blur_per_sm)) total = share(blur_per_sm);
-        if (total < need(blur_nt)) total = need(blur_nt);
         if (total > cta_max) total = cta_max;
-        blur_smem = total & ~(size_t)15;
+        int chunk = 32;                                                        // largest multiple of 32 that fits
+        while (chunk + 32 <= items_all && fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk + 32) * sizeof(double) <= total)
+            chunk += 32;
+        blur_smem = fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk) * sizeof(double);
         ba.radius = (int)radius;
         ba.S = blur_nt * EPT + 2 * (int)radius;
-        ba.chunk = (int)((blur_smem - live) / (12 * sizeof(double)));
-        SSHG_REQUIRE(ba.chunk >= 1 && blur_smem >= need(blur_nt), "sshg_yield: internal: K3 shared-memory plan");
-        if (radius >= 1) sshg_gaussian_taps(sigma_out, radius, ba.w);
-        else ba.w[0] = 1.0;
+        ba.chunk = chunk;
+        ba.fixup = opt.k3_fixup == 0 ? 0 : 1;
+        ba.phi_deg = (const double*)dphi;
+        sshg_gaussian_taps(sigma_out, radius, ba.w);
         if (blur_nt == NT_BLUR)
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
@@ -680,12 +675,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     // Short launches: a CTA that is left alone at the end of a launch still needs its full azimuthal sweep
     // (~40-75 us), and every CTA starts with a store-free setup phase.  Cutting the phi items of a column
-    // into segments (one CTA each, the setup is repeated) shortens both.  SSHG_NSEG overrides (tuning).
+    // into segments (one CTA each, the setup is repeated) shortens both.  option "nseg" overrides (tuning).
     auto pick_segments = [&](int64_t ctas, int per_sm, double below_waves) -> int {
-        if (const char* env = getenv("SSHG_NSEG")) {
-            const int v = atoi(env);
-            return v < 1 ? 1 : (v > 16 ? 16 : v);
-        }
+        if (opt.nseg >= 1) return opt.nseg;
         const double waves = (double)ctas / ((double)ctx->num_sms * per_sm);
         const long long items = p->nP - p->nP / 2;
         int ns = 1;
@@ -726,13 +718,8 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         ctx->launches++;
         return SSHG_OK;
     };
-    // K3: the same columns, broadened along the energy axis, in one pass; then the fix-up kernel re-evaluates the
-    // row segments K3 flagged (yield next to an azimuthal node) the strict way.  SSHG_K3_FIXUP=0 disables (tests).
-    const bool fixup = !(getenv("SSHG_K3_FIXUP") && atoi(getenv("SSHG_K3_FIXUP")) == 0);
-    const int fx_tiles = (int)((p->nE + FX_TILE - 1) / FX_TILE);
-    const size_t fx_smem = (size_t)(2 * radius + 2 + (size_t)(NCOL + 14 + FX_RB) * (FX_TILE + 2 * radius)) * sizeof(double);
-    if (fused && fixup)
-        SSHG_CUDA(cudaFuncSetAttribute(yield_blur_fixup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fx_smem));
+    // K3: the same columns, broadened along the energy axis, in one pass (rows next to an azimuthal node are
+    // re-evaluated the strict way inside the same CTA; option "k3_fixup" = 0 disables that: tests of the error bound).
     auto launch_blur = [&](int64_t c0, int64_t nc, double* dst, cudaStream_t st) -> int {
         BlurArgs b = ba;
         b.y = a;
@@ -743,20 +730,6 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.n_seg = pick_segments(nc * blur_tiles, blur_per_sm, 0.0);        // K3's setup (halo, harmonics, FIR) is too
                                                                             // heavy to repeat: measured slower (tuning only)
         SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
-        void *flags = nullptr, *work = nullptr;
-        const size_t n_blocks = (size_t)nc * fx_tiles;
-        const size_t flag_bytes = n_blocks * 4 * (size_t)p->nP, work_bytes = (1 + 2 * n_blocks) * sizeof(int);
-        if (fixup) {
-            SSHG_REQUIRE(n_blocks < (1ULL << 30), "sshg_yield: too many tiles for one launch");
-            if (int rc = sshg_scratch(ctx, 13, flag_bytes, &flags)) return rc;
-            if (int rc = sshg_scratch(ctx, 14, work_bytes, &work)) return rc;
-            SSHG_CUDA(cudaMemsetAsync(flags, 0, flag_bytes, st));
-            SSHG_CUDA(cudaMemsetAsync(work, 0, work_bytes, st));
-        }
-        b.flags = (unsigned char*)flags;
-        b.work = (int*)work;
-        b.fx_tiles = fx_tiles;
-        b.n_blocks = (int)n_blocks;
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
             yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
@@ -764,24 +737,6 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
             yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
-        if (fixup) {
-            SSHG_REQUIRE(nc * fx_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
-            FixArgs f{};
-            f.y = b.y;
-            f.y.n_tiles = fx_tiles;
-            f.y.n_seg = 1;
-            f.phi_deg = (const double*)dphi;
-            f.flags = (const unsigned char*)flags;
-            f.work = (const int*)work;
-            f.radius = ba.radius;
-            f.S = FX_TILE + 2 * ba.radius;
-            for (int k = 0; k <= ba.radius; ++k) f.w[k] = ba.w[k];
-            // a fixed grid walks the list of flagged blocks (its length is only known on the device)
-            const size_t fx_grid = n_blocks < (size_t)4 * ctx->num_sms ? n_blocks : (size_t)4 * ctx->num_sms;
-            yield_blur_fixup_kernel<<<(unsigned)fx_grid, FX_NT, fx_smem, st>>>(f);
-            SSHG_CUDA(cudaGetLastError());
-            ctx->launches++;
-        }
         return SSHG_OK;
     };
 

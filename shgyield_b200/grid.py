@@ -86,6 +86,8 @@ def yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi2, mref=True, co
         out = _lib.pinned_empty(shape) if pinned else np.empty(shape)
     elif out.shape != shape or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
         raise ValueError("out must be a C-contiguous float64 array of shape %s" % (shape,))
+    if out.size == 0:
+        return out                                  # empty shard (more ranks than thetas)
     _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), out.ctypes.data, _lib.HOST),
                ctx.lib)
     return out
@@ -102,7 +104,6 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
     import torch
     ctx = _lib.context(energy.device.index)
     s = stream if stream is not None else torch.cuda.current_stream(energy.device)
-    ctx.set_stream(s.cuda_stream)
     keep = []
     for t, dt in ((energy, torch.float64), (theta, torch.float64), (phi, torch.float64), (thick, torch.float64),
                   (eps1w, torch.complex128), (eps2w, torch.complex128), (chi2, torch.complex128)):
@@ -126,7 +127,14 @@ def yield_grid_device(energy, theta, phi, thick, eps1w, eps2w, chi2, out=None, m
         elif tuple(out.shape) != shape or out.dtype != torch.float64 or not out.is_contiguous() or not out.is_cuda:
             raise ValueError("out must be a contiguous float64 CUDA tensor of shape %s" % (shape,))
         dst = out.data_ptr()
-    _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), dst, _lib.DEVICE), ctx.lib)
+    if out is not None and out.numel() == 0:
+        return out                                  # empty shard (more ranks than thetas): nothing to compute
+    if p.t1 == p.t0 or p.d1 == p.d0:
+        return out
+    # queued on the caller's stream; the context returns to its own stream afterwards (ordered on the device), so it
+    # never keeps the handle of a stream the caller may drop, and host-array calls keep running on the own stream
+    with ctx.on_stream(s.cuda_stream):
+        _lib.check(ctx.lib.sshg_yield_broadened(ctx.handle, C.byref(p), float(sigma_out), dst, _lib.DEVICE), ctx.lib)
     return out
 
 
@@ -297,12 +305,14 @@ def broaden_energy_device(cube, sigma):
     """K1 along the energy (last, contiguous) axis of a device cube; returns a new tensor."""
     import torch
     ctx = _lib.context(cube.device.index)
-    ctx.set_stream(torch.cuda.current_stream(cube.device).cuda_stream)
     out = torch.empty_like(cube)
     n = cube.shape[-1]
+    if cube.numel() == 0:
+        return out
     rows = cube.numel() // n
-    _lib.check(ctx.lib.sshg_gauss1d(ctx.handle, cube.data_ptr(), out.data_ptr(), rows, n, n, 1, float(sigma),
-                                    _lib.DEVICE), ctx.lib)
+    with ctx.on_stream(torch.cuda.current_stream(cube.device).cuda_stream):
+        _lib.check(ctx.lib.sshg_gauss1d(ctx.handle, cube.data_ptr(), out.data_ptr(), rows, n, n, 1, float(sigma),
+                                        _lib.DEVICE), ctx.lib)
     return out
 
 

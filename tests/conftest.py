@@ -35,3 +35,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def libopt():
+    """Test / tuning switches of the library's process-wide context for the rest of the test -- libopt(k3=0,
+    k2_sparse=1) -- restored afterwards (sshg_ctx_set_option; the library reads no environment variables)."""
+    import contextlib
+    from shgyield_b200 import _lib
+    with contextlib.ExitStack() as stack:
+        yield lambda **kv: stack.enter_context(_lib.context().options(**kv))

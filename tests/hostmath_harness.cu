@@ -164,8 +164,9 @@ extern "C" int hostmath_sparse_walk(const sshg_points* p, long long e, double th
 // ---- K3 on the CPU: harmonic form of one (theta, thickness) column, broadened along the energy axis ----
 // p: a point list whose spectra columns are the energy axis (eidx unused); theta / thickness scalars;
 // phi: nP azimuths; w: r + 1 Gaussian taps (w[0] centre); out[pol][nP][nE].
-// strict_nodes: 1 = as the product (K3 + fix-up kernel): values below NODE_FRACTION of the column's amplitude bound flag
-// their (polarisation, row, 128-energy tile), which is then re-evaluated row-wise (|r|^2 per energy, FIR); 0 = K3 alone.
+// strict_nodes: 1 = as the product: a value below NODE_FRACTION of its column's amplitude bound flags its
+// (polarisation, row, 256-energy tile), which is then re-evaluated row-wise (|r|^2 per energy, FIR); 0 = the harmonic
+// sums alone.
 extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, double thick_nm, const double* phi_deg,
                                     long long nP, const double* w, int r, int strict_nodes, double* out) {
     Physics ph;
@@ -232,7 +233,7 @@ extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, doub
         coeffs_sp(c, chi, k);     for (int j = 0; j < 7; ++j) kk[(size_t)(2 * 7 + j) * nE + e] = k[j];
         coeffs_ss(c, chi, k);     for (int j = 0; j < 4; ++j) kk[(size_t)(3 * 7 + j) * nE + e] = k[j];
     }
-    const long long FXT = 128;                                  // FX_TILE of the kernel
+    const long long FXT = 256;                                  // energies per CTA of the kernel (wide tiles)
     for (long long ip = 0; ip < nP; ++ip) {
         double t[12], bb[6];
         phi_harmonics(phi_deg[ip], t);
@@ -246,10 +247,7 @@ extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, doub
                 double y = harmonic_yield(H, t, pol == 3);
                 if (strict_nodes) {
                     const double u = amplitude_bound(H, pol == 3);
-                    if (y < NODE_FRACTION * u) {
-                        if (y > DEEP_FRACTION * u) flag[(size_t)(e / FXT)] = 1;
-                        y = fmax(y, 0.0);
-                    }
+                    if (u < 1.0e300 && y < NODE_FRACTION * u) flag[(size_t)(e / FXT)] = 1;
                 }
                 out[((size_t)pol * nP + ip) * nE + e] = y;
             }

@@ -81,6 +81,18 @@ def main():
         ok = ok and part is None
     del part
 
+    # more ranks than thetas: the surplus ranks hold an empty shard, skip the kernel, and still take part in
+    # the collective construction of the peer cube, the barrier and the NCCL gather
+    kw1 = dict(kw, theta=[65.0])
+    assert grid.choose_shard_axis(1, 1, world) == "theta"
+    whole1 = grid.shgyield_grid(**kw1)["cube"]
+    for how in (True, "peer"):
+        part = grid.shgyield_grid(shard=(rank, world), gather=how, **kw1)["cube"]
+        torch.cuda.synchronize()
+        ok = ok and (bool(torch.equal(part, whole1)) if rank == 0 else part is None)
+    empty = grid.shgyield_grid(shard=(world - 1, world), **kw1)["cube"]
+    ok = ok and tuple(empty.shape) == (0,) + tuple(whole1.shape[1:])
+
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

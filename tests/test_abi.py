@@ -71,3 +71,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+
+
+def test_library_reads_no_environment():
+    """Tests and tuning drive the library through sshg_ctx_set_option; nothing in csrc/ may call getenv (a stray
+    environment variable must not change results or speed of a drop-in library)."""
+    csrc = os.path.join(util.REPO, "shgyield_b200", "csrc")
+    for f in os.listdir(csrc):
+        assert "getenv" not in open(os.path.join(csrc, f)).read(), f

@@ -2,13 +2,13 @@
 GPU parity tests of the broadened sweep (sshg_yield_broadened, K3): the yield cube with the output
 broadening of shgyield() (broad(., sigma_out) along the energy axis, reference shg.py:26-28, 433-436)
 computed in one pass, against the CPU oracle (un-broadened yields -> scipy-style gaussian filter row by
-row) and against the two-pass device path (K2 -> K1, SSHG_K3=0).
+row) and against the two-pass device path (K2 -> K1, library option "k3" = 0).
 
 Tolerance: tests/cases.py::parity_ok with rtol 1e-10 in the strict metric (element-wise wherever the yield is
 >= 1e-6 of the maximum).  The harmonic sum of K3 alone has an absolute error (a few 1e-15 of the column's
 maximum over phi, checked here as < 5e-14); the segments where that is not enough -- values below 1e-3 of the
-column's amplitude bound, i.e. next to an azimuthal node -- are flagged by K3 and re-evaluated row-wise by
-yield_blur_fixup_kernel, so the product holds the strict metric (SSHG_K3_FIXUP=0 shows K3 alone).
+column's amplitude bound, i.e. next to an azimuthal node -- are flagged by K3's sweep and re-evaluated row-wise
+inside the same CTA, so the product holds the strict metric (option "k3_fixup" = 0 shows the harmonic sums alone).
 """
 import os
 
@@ -68,25 +68,24 @@ BLUR_SHAPES = [
 @pytest.mark.parametrize("path", ["fused", "fused64", "fused128", "two_pass"])
 @pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0])
 @pytest.mark.parametrize("nE,theta,phi,thick", BLUR_SHAPES, ids=[str(i) for i in range(len(BLUR_SHAPES))])
-def test_broadened_sweep_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, thick, sigma, path):
+def test_broadened_sweep_matches_oracle(grid, consts, libopt, nE, theta, phi, thick, sigma, path):
     """radius 1, 5, 20 (the default sigma_out = 5) and 64 (the largest fused radius); K3 with the tile width
     the library picks and with 128- / 256-energy tiles forced."""
-    monkeypatch.setenv("SSHG_K3", "0" if path == "two_pass" else "1")
+    libopt(k3=0 if path == "two_pass" else 1)
     if path in ("fused64", "fused128"):
-        monkeypatch.setenv("SSHG_K3_NT", path[5:])
+        libopt(k3_nt=int(path[5:]))
     cfg = _small_cfg(nE, theta, phi, thick, seed=3)
     got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
     _check(got, _blurred_oracle(cfg, consts, sigma), path != "two_pass", (nE, sigma, path))
 
 
-def test_sparse_phi_sweeps_and_large_radii_take_the_two_pass_path(grid, consts, monkeypatch):
+def test_sparse_phi_sweeps_and_large_radii_take_the_two_pass_path(grid, consts):
     """P = 1 (config-4 shape) and sigma_out > 16: K2 / K2s -> K1 slab by slab; P = 1 forced through K3."""
     cfg = _small_cfg(300, np.arange(0, 90, 9.0), [30.0], np.arange(1.0, 31.0), seed=5)
     want = _blurred_oracle(cfg, consts, 5.0)
     _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, False, "sparse")
-    monkeypatch.setenv("SSHG_K2_SPARSE", "0")
-    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, True, "P=1 through K3")
-    monkeypatch.delenv("SSHG_K2_SPARSE")
+    with util.lib_options(k2_sparse=0):
+        _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, True, "P=1 through K3")
     cfg = _small_cfg(400, [30.0, 60.0], np.arange(0, 360, 30.0), [10.0], seed=6)
     _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=20.0), _blurred_oracle(cfg, consts, 20.0), False, "r=80")
     # a radius of 0 (sigma_out < 0.125) is the identity
@@ -123,7 +122,7 @@ def test_nan_sample_stays_within_the_radius(grid, consts):
     assert np.isnan(got[0, 0, 0, 0, 192:209]).all() and not np.isnan(got[0, 0, 0, 0, :192]).any()
 
 
-def test_broadened_device_host_and_two_pass_paths_agree(grid, consts, monkeypatch):
+def test_broadened_device_host_and_two_pass_paths_agree(grid, consts, libopt):
     """Device-resident output, the host slab pipeline (several slabs) and the two-pass path on a 472 MB cube."""
     import torch
     cfg = _small_cfg(4096, np.linspace(5, 85, 20), np.arange(0, 360, 2.0), [10.0], seed=6)
@@ -134,7 +133,7 @@ def test_broadened_device_host_and_two_pass_paths_agree(grid, consts, monkeypatc
     fused = run()
     host = grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0)
     assert np.array_equal(fused.cpu().numpy(), host)
-    monkeypatch.setenv("SSHG_K3", "0")
+    libopt(k3=0)
     two = run()
     torch.cuda.synchronize()
     top = float(two.max())
@@ -187,25 +186,24 @@ def test_config5_shard_broadened_full_rows_vs_oracle(grid, consts):
 
 @pytest.mark.parametrize("nseg", ["2", "3", "5", "16"])
 @pytest.mark.parametrize("sigma", [0.0, 2.0])
-def test_phi_segments_change_nothing(grid, consts, monkeypatch, nseg, sigma):
-    """Short launches cut the phi items of a column into segments, one CTA each (K2; K3 under SSHG_NSEG):
+def test_phi_segments_change_nothing(grid, consts, nseg, sigma):
+    """Short launches cut the phi items of a column into segments, one CTA each (K2; K3 under the option "nseg"):
     uneven splits, more segments than items, pairs + un-paired tail -- bitwise the un-segmented result."""
     for phi in (np.arange(0, 360, 2.5), np.linspace(0, 360, 41), np.linspace(0, 350, 7)):
         cfg = _small_cfg(300, [20.0, 70.0], phi, [10.0], seed=9)
-        monkeypatch.setenv("SSHG_NSEG", "1")
-        one = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
-        monkeypatch.setenv("SSHG_NSEG", nseg)
-        many = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
+        with util.lib_options(nseg=1):
+            one = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
+        with util.lib_options(nseg=int(nseg)):
+            many = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
         assert np.array_equal(one, many), (nseg, sigma, phi.size)
 
 
 @pytest.mark.parametrize("path", ["fused", "two_pass"])
 @pytest.mark.parametrize("mat", ["si111", "full"])
-def test_broadened_sweep_vs_reference_golden(grid, monkeypatch, mat, path):
+def test_broadened_sweep_vs_reference_golden(grid, libopt, mat, path):
     """shgyield_grid(sigma_out) against rows produced by the UNMODIFIED reference, shgyield() called once per
     (theta, phi) (tests/golden/ref_blur_rows.npz; phi includes points 0.02 deg from the C3v nodes of Si(111))."""
-    monkeypatch.setenv("SSHG_K3", "1" if path == "fused" else "0")
-    monkeypatch.setenv("SSHG_K2_SPARSE", "0")                            # 9 azimuths: K3 only when the dense path is forced
+    libopt(k3=1 if path == "fused" else 0, k2_sparse=0)                  # 9 azimuths: K3 only when the dense path is forced
     z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
     m1, m2, m3, chi2 = cases.MATERIALS[mat](cases.load_spectra())
     for sigma in cases.BLUR_SWEEP_SIGMAS:
@@ -284,19 +282,18 @@ def test_config3_config4_full_size_broadened(grid, tag):
     torch.cuda.empty_cache()
 
 
-def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metric(grid, monkeypatch):
-    """Si(111) rows 0.02 deg from the C3v nodes: without the fix-up kernel (SSHG_K3_FIXUP=0) K3 holds its absolute
-    bound; the fix-up re-evaluates the near-node segments and every row holds the strict metric."""
+def test_k3_alone_has_the_absolute_bound_and_the_fixup_restores_the_strict_metric(grid, libopt):
+    """Si(111) rows 0.02 deg from the C3v nodes: without the strict re-evaluation (option "k3_fixup" = 0) K3 holds its
+    absolute bound; with it the near-node rows are re-evaluated row-wise and every row holds the strict metric."""
     z = np.load(os.path.join(cases.GOLDEN_DIR, "ref_blur_rows.npz"))
     m1, m2, m3, chi2 = cases.si111_material(cases.load_spectra())
     want = z["si111_sigma5"]                                            # [T, 4, P, E]
     top = float(np.max(want))
     run = lambda: grid.shgyield_grid(z["energy"], m1, m2, m3, chi2, z["theta"], z["phi"], cases.BLUR_SWEEP_THICK,
                                      gamma=0, sigma_out=5.0, device=False)["cube"][:, 0]
-    monkeypatch.setenv("SSHG_K2_SPARSE", "0")                            # 9 azimuths: force the dense path (K3)
-    monkeypatch.setenv("SSHG_K3_FIXUP", "0")
-    alone = run()
-    monkeypatch.delenv("SSHG_K3_FIXUP")
+    libopt(k2_sparse=0)                                                  # 9 azimuths: force the dense path (K3)
+    with util.lib_options(k3_fixup=0):
+        alone = run()
     fixed = run()
     for k in range(4):
         colmax = np.maximum(np.max(want[:, k], axis=1, keepdims=True), 1e-12 * top)

@@ -57,3 +57,40 @@ def test_rad_amplitudes_match_oracle(shg):
             want = getattr(orc, name)(energy, e1, e2, ch, theta, phi, 10.0, mref, orc.SCIPY_1_18_CONSTANTS)
             assert got.shape == (3, 50)
             np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)), err_msg=name)
+
+
+def test_context_options_and_stream_handling():
+    """sshg_ctx_set_option: unknown keys / values fail, -1 restores the library's choice; a device call on a
+    temporary torch stream leaves the context on its own stream (the handle of a dropped stream is never kept)."""
+    import torch
+    from shgyield_b200 import _lib, grid
+    from shgyield_b200.synthetic import config5
+    ctx = _lib.context(0)
+    with pytest.raises(ValueError):
+        ctx.set_option("no_such_option", 1)
+    with pytest.raises(ValueError):
+        ctx.set_option("k3_nt", 96)
+    with pytest.raises(ValueError):
+        ctx.set_option("nseg", 17)
+    assert ctx.get_option("k3") is None
+    with ctx.options(k3=0, nseg=3):
+        assert ctx.get_option("k3") == 0 and ctx.get_option("nseg") == 3
+    assert ctx.get_option("k3") is None and ctx.get_option("nseg") is None
+
+    own = ctx.lib.sshg_ctx_stream(ctx.handle)
+    cfg = config5(n_energy=400, n_theta=3, n_phi=21)
+    dev = torch.device("cuda", 0)
+    d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg.items()}
+    args = (d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"])
+    ref = grid.yield_grid_device(*args)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        s = torch.cuda.Stream(dev)                      # a temporary stream, dropped after the call
+        with torch.cuda.stream(s):
+            got = grid.yield_grid_device(*args, sigma_out=0.0)
+        s.synchronize()
+        assert torch.equal(got, ref)
+        del s
+        assert ctx.lib.sshg_ctx_stream(ctx.handle) == own
+        host = grid.yield_grid_host(**cfg)             # the host-array path keeps working on the own stream
+        assert np.array_equal(host, ref.cpu().numpy())

@@ -61,16 +61,12 @@ def test_points_kernel_random(seed, n, mref, sn, zq):
        grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]),
        kernel=st.sampled_from(["dense", "sparse"]))
 def test_grid_kernel_random(seed, nE, nT, nD, grid_kind, kernel):
-    import os
     from shgyield_b200 import grid
-    os.environ["SSHG_K2_SPARSE"] = "1" if kernel == "sparse" else "0"
-    try:
-        _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind)
-    finally:
-        os.environ.pop("SSHG_K2_SPARSE", None)
+    with util.lib_options(k2_sparse=1 if kernel == "sparse" else 0):
+        _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel)
 
 
-def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind):
+def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel):
     rng = np.random.default_rng(seed)
     energy, eps1w, eps2w, chi = _spectra(rng, nE)
     theta = np.sort(rng.uniform(0, 90, nT))
@@ -87,7 +83,7 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind):
     for k, pol in enumerate(cases.POLS):
         w = np.broadcast_to(want[pol], (nT, nD, phi.size, nE))
         ok, msg = cases.parity_ok(got[:, :, k], w, rtol=1e-10, scale=scale)
-        assert ok, (seed, grid_kind, os.environ.get("SSHG_K2_SPARSE"), pol, msg)
+        assert ok, (seed, grid_kind, kernel, pol, msg)
 
 
 @settings(max_examples=20 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
@@ -109,13 +105,8 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     phi = {"paired": np.concatenate([base, base + 180.0]),
            "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
            "free": rng.uniform(0, 360, 2 * h + 1)}[grid_kind]
-    os.environ["SSHG_K3_NT"] = tiles
-    os.environ["SSHG_K2_SPARSE"] = "0"                     # fewer than 16 azimuths would otherwise take K2s -> K1
-    try:
+    with util.lib_options(k3_nt=int(tiles), k2_sparse=0):  # fewer than 16 azimuths would otherwise take K2s -> K1
         got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS, sigma_out=sigma)
-    finally:
-        os.environ.pop("SSHG_K3_NT", None)
-        os.environ.pop("SSHG_K2_SPARSE", None)
     raw = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
     want = np.stack([orc.gaussian_filter1d(np.broadcast_to(raw[p], (nT, nD, phi.size, nE)), sigma, axis=-1)
                      for p in cases.POLS], axis=2)

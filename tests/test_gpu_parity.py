@@ -195,10 +195,10 @@ GRID_SHAPES = [
 
 @pytest.mark.parametrize("kernel", ["auto", "dense", "sparse"])
 @pytest.mark.parametrize("nE,theta,phi,thick", GRID_SHAPES, ids=[str(i) for i in range(len(GRID_SHAPES))])
-def test_grid_kernel_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, thick, kernel):
+def test_grid_kernel_matches_oracle(grid, consts, libopt, nE, theta, phi, thick, kernel):
     """Every shape through the dense (harmonic, phi-pair) kernel and the sparse-phi kernel."""
     if kernel != "auto":
-        monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
+        libopt(k2_sparse=1 if kernel == "sparse" else 0)
     cfg = _small_cfg(nE, theta, phi, thick)
     got = grid.yield_grid_host(**cfg, consts=consts)
     want = _oracle_cube(cfg, consts)
@@ -210,8 +210,8 @@ def test_grid_kernel_matches_oracle(grid, consts, monkeypatch, nE, theta, phi, t
 
 @pytest.mark.parametrize("kernel", ["dense", "sparse"])
 @pytest.mark.parametrize("kw", [dict(mref=False), dict(sinc_normalized=False), dict(zzz_phi_quirk=False)])
-def test_grid_kernel_switches(grid, consts, monkeypatch, kw, kernel):
-    monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
+def test_grid_kernel_switches(grid, consts, libopt, kw, kernel):
+    libopt(k2_sparse=1 if kernel == "sparse" else 0)
     cfg = _small_cfg(200, [15.0, 70.0], np.arange(0, 360, 20.0), [10.0, 55.0], seed=4)
     got = grid.yield_grid_host(**cfg, consts=consts, **kw)
     want = _oracle_cube(cfg, consts, **kw)
@@ -221,9 +221,9 @@ def test_grid_kernel_switches(grid, consts, monkeypatch, kw, kernel):
 
 
 @pytest.mark.parametrize("kernel", ["dense", "sparse"])
-def test_grid_shards_are_bitwise_slices(grid, consts, monkeypatch, kernel):
+def test_grid_shards_are_bitwise_slices(grid, consts, libopt, kernel):
     """Sharding changes no arithmetic: every shard equals the slice of the full cube bit for bit."""
-    monkeypatch.setenv("SSHG_K2_SPARSE", "1" if kernel == "sparse" else "0")
+    libopt(k2_sparse=1 if kernel == "sparse" else 0)
     cfg = _small_cfg(300, np.linspace(0, 90, 11), np.arange(0, 360, 10.0), [4.0, 9.0, 14.0], seed=2)
     full = grid.yield_grid_host(**cfg, consts=consts)
     for world in (2, 4, 8):
@@ -233,6 +233,10 @@ def test_grid_shards_are_bitwise_slices(grid, consts, monkeypatch, kernel):
             assert np.array_equal(part, full[lo:hi])
     lo, hi = grid.shard_bounds(3, 2, 1)
     assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, d_range=(lo, hi)), full[:, lo:hi])
+    # more ranks than thetas: the surplus ranks hold an empty shard, which is a legal no-op
+    lo, hi = grid.shard_bounds(11, 16, 13)
+    assert lo == hi == 11
+    assert grid.yield_grid_host(**cfg, consts=consts, t_range=(lo, hi)).shape == (0, 3, 4, 36, 300)
 
 
 def test_grid_device_and_host_paths_agree(grid, consts):

@@ -63,6 +63,38 @@ def _gather_worker(rank, world, port, axis, q):
         dist.destroy_process_group()
 
 
+def _surplus_worker(rank, world, port, q):
+    """world 3, two thetas: rank 2 holds an empty shard and still takes part in the gather."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        nT, nD, nP, nE = 2, 1, 3, 4
+        full = torch.arange(nT * nD * 4 * nP * nE, dtype=torch.float64).reshape(nT, nD, 4, nP, nE)
+        lo, hi = grid.shard_bounds(nT, world, rank)
+        slab = full[lo:hi].clone()
+        got = grid.gather_slabs(slab, nT, nD, (rank, world, "theta"))
+        ok = (bool(torch.equal(got, full)) if rank == 0 else got is None) and (hi - lo == 0) == (rank == 2)
+        everywhere = grid.gather_slabs(slab, nT, nD, (rank, world, "theta"), all_ranks=True)
+        q.put((rank, ok and bool(torch.equal(everywhere, full))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_slabs_gloo_more_ranks_than_thetas():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_surplus_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+    assert res == [(0, True), (1, True), (2, True)]
+    assert grid.choose_shard_axis(2, 1, 3) == "theta"
+
+
 @pytest.mark.parametrize("axis", ["theta", "thick"])
 def test_gather_slabs_gloo_world2(axis):
     ctx = mp.get_context("spawn")

@@ -28,3 +28,11 @@ def pack_chi(chi: dict, n: int) -> np.ndarray:
     for i, k in enumerate(cases.CHI2_KEYS):
         out[i] = np.broadcast_to(np.asarray(chi[k], dtype=np.complex128), (n,))
     return out
+
+
+def lib_options(**kv):
+    """`with util.lib_options(k3=0, k2_sparse=1): ...` -- test / tuning switches of the process-wide context
+    (sshg_ctx_set_option; the library reads no environment variables), restored on exit."""
+    from shgyield_b200 import _lib
+    return _lib.context().options(**kv)
+

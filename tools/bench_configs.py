@@ -38,10 +38,12 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--only-k1", action="store_true")
     ap.add_argument("--only-k3", action="store_true")
+    ap.add_argument("--only-configs", action="store_true", help="configs 3 and 4 only")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
     consts = shg.physical_constants()
+    ctx = _lib.context(0)
     m1, m2, m3, chi2 = cases.si111_material()
 
     # ---- configs 3 and 4: Si(111) material, device resident; prep (K1, spline, rotate) timed apart -----
@@ -54,32 +56,35 @@ def main():
              put(eps1w), put(eps2w), put(chi_rot)]
         T, D, P, E = axes["theta"].size, axes["thick"].size, axes["phi"].size, axes["energy"].size
         out = torch.empty((T, D, 4, P, E), dtype=torch.float64, device=dev)
-        for nt in ("64", "256"):
-            os.environ["SSHG_K2_NT"] = nt
-            med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
+        for nt in (64, 256):
+            with ctx.options(k2_nt=nt):
+                med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
             print(json.dumps({"case": tag, "k2_threads": nt, "k2_ms_median": med, "k2_ms_best": best}), flush=True)
-        os.environ.pop("SSHG_K2_NT", None)
         med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts), args.reps)
         pts = out.numel()
         flops = 28.0 * pts + 1000.0 * E * T * D
         print(json.dumps({"case": tag, "shape_TDPE": [T, D, P, E], "points": pts, "k2_ms_median": med, "k2_ms_best": best,
                           "points_per_s": pts / (med * 1e-3), "store_gbs": 8e-9 * pts / (med * 1e-3),
                           "alg_fp64_tflops": flops / (med * 1e-3) / 1e12, "host_prep_ms": prep_ms}), flush=True)
+        for sigma in (5.0, 12.0):                   # the API's default output broadening (K3 for config 3, K2s -> K1 for config 4)
+            med, best = timed(lambda: grid.yield_grid_device(*d, out=out, consts=consts, sigma_out=sigma), args.reps)
+            print(json.dumps({"case": tag, "sigma_out": sigma, "ms_median": med, "ms_best": best,
+                              "points_per_s": pts / (med * 1e-3), "store_gbs": 8e-9 * pts / (med * 1e-3)}), flush=True)
         del out
+
+    if args.only_configs:
+        return
 
     # ---- config-5 theta shards (what one of 8 / 4 ranks computes), both CTA sizes of K2 ----------------
     cfg = config5()
     dd = {k: put(v) for k, v in cfg.items()}
     for nth in (() if (args.only_k1 or args.only_k3) else (23, 46)):
         out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
-        for nt in ("64", "256", None):
-            if nt is None:
-                os.environ.pop("SSHG_K2_NT", None)
-            else:
-                os.environ["SSHG_K2_NT"] = nt
-            med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"], dd["eps1w"],
-                                                            dd["eps2w"], dd["chi2"], out=out, consts=consts,
-                                                            t_range=(0, nth)), args.reps)
+        for nt in (64, 256, None):
+            with ctx.options(k2_nt=nt):
+                med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"],
+                                                                dd["eps1w"], dd["eps2w"], dd["chi2"], out=out, consts=consts,
+                                                                t_range=(0, nth)), args.reps)
             print(json.dumps({"case": "config5_shard_%dtheta" % nth, "k2_threads": nt or "auto", "ms_median": med,
                               "ms_best": best, "store_gbs": 8e-9 * out.numel() / (med * 1e-3)}), flush=True)
         del out
@@ -90,15 +95,15 @@ def main():
         out = torch.empty((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
         for sigma in (2.0, 5.0, 12.0):
             for k3 in ("1", "0"):
-                os.environ["SSHG_K3"] = k3
-                med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"],
-                                                                dd["eps1w"], dd["eps2w"], dd["chi2"], out=out, consts=consts,
-                                                                t_range=(0, nth), sigma_out=sigma), args.reps)
+                with ctx.options(k3=int(k3)):
+                    med, best = timed(lambda: grid.yield_grid_device(dd["energy"], dd["theta"], dd["phi"], dd["thick"],
+                                                                    dd["eps1w"], dd["eps2w"], dd["chi2"], out=out,
+                                                                    consts=consts, t_range=(0, nth), sigma_out=sigma),
+                                      args.reps)
                 print(json.dumps({"case": "config5_shard_%dtheta_sigma_out%g" % (nth, sigma),
                                   "path": "K3 fused" if k3 == "1" else "K2 -> K1 two-pass", "ms_median": med, "ms_best": best,
                                   "points_per_s": out.numel() / (med * 1e-3),
                                   "store_gbs": 8e-9 * out.numel() / (med * 1e-3)}), flush=True)
-        os.environ.pop("SSHG_K3", None)
         del out
     if args.only_k3:
         return

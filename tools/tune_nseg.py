@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Tuning run: phi-segment count (SSHG_NSEG) of K2 / K3 on short launches (config 3, config-5 shards)."""
+"""Tuning run: phi-segment count (library option "nseg") of K2 / K3 on short launches (config 3, config-5 shards)."""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from shgyield_b200 import grid, shg  # noqa: E402
+from shgyield_b200 import _lib, grid, shg  # noqa: E402
 from shgyield_b200.synthetic import config5  # noqa: E402
 from tests import cases  # noqa: E402
 from tools.bench_configs import timed  # noqa: E402
@@ -31,11 +31,8 @@ for tag, args, t_range, shape in (("config3", c3, None, (90, 1, 4, 360, 2000)), 
     out = torch.empty(shape, dtype=torch.float64, device=dev)
     for sigma in (0.0, 5.0):
         for ns in segs:
-            if ns == "auto":
-                os.environ.pop("SSHG_NSEG", None)
-            else:
-                os.environ["SSHG_NSEG"] = ns
-            med, best = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 7)
+            with _lib.context(0).options(nseg=None if ns == "auto" else int(ns)):
+                med, best = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 7)
             print(json.dumps({"case": tag, "sigma_out": sigma, "nseg": ns, "ms_median": round(med, 4), "ms_best": round(best, 4),
                               "store_gbs": round(8e-9 * out.numel() / (med * 1e-3))}), flush=True)
     del out
