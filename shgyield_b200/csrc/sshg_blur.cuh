@@ -34,7 +34,7 @@
 constexpr int NT_BLUR = 64;                     // 128-energy tiles (short energy axes)
 constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 64
 constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
-constexpr int FX_RB = 8;                        // flagged rows re-evaluated together
+constexpr int FX_RB = 12;                       // flagged rows re-evaluated together (rowbuf aliases raw: <= NH)
 #ifndef SSHG_SWEEP_SB
 #define SSHG_SWEEP_SB 16
 #endif
@@ -46,18 +46,18 @@ struct BlurArgs {
     const double* phi_deg;                      // [nP] (strict re-evaluation of flagged rows)
     int radius;
     int S;                                      // staged energies per CTA = 2 NT + 2 radius
-    int chunk;                                  // phi items per table chunk, a multiple of 32
+    int chunk;                                  // phi items per table chunk
     int fixup;                                  // 1: re-evaluate the rows next to azimuthal nodes (0: tests of the bound)
     double w[BLUR_RMAX + 1];                    // Gaussian taps, w[0] centre
 };
 
 // shared memory of a CTA, in doubles (the host plans with the same function)
-__host__ __device__ constexpr int blur_flag_words(int chunk) { return chunk / 32 + 1; }   // per part; +1: a mask may straddle
+__host__ __device__ constexpr int blur_flag_words(int chunk) { return chunk / 32 + 2; }   // per part; a mask may straddle words
 __host__ __device__ constexpr int blur_fixed_doubles(int radius, int S) {
     return 2 * radius + 2 + (NCOL + NH) * S + FX_RB * 6;
 }
-// a chunk of the phi table: 12 doubles per item, in front of it the two bitmaps (2 x words x 4 B, padded to 16 B)
-__host__ __device__ constexpr int blur_chunk_doubles(int chunk) { return chunk * 12 + (blur_flag_words(chunk) + 1) / 2 * 2; }
+// a chunk of the phi table: 12 doubles per item, in front of it four bitmaps (flagged / strict rows x two parts; 4 x words x 4 B)
+__host__ __device__ constexpr int blur_chunk_doubles(int chunk) { return chunk * 12 + 2 * blur_flag_words(chunk); }
 
 __global__ void phi_harm_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
                                       int allow_pairs) {
@@ -241,7 +241,7 @@ __device__ __forceinline__ Column parked_column(const double* cols, int S, int i
 }
 
 // shared memory: wf[2 R + 2] | cols[NCOL][S] | raw[NH][S] (rowbuf[FX_RB][S] during (D)) | pb[FX_RB][6] |
-//                flag bitmaps fl[2][chunk / 32 + 1] | tabs[chunk][12]
+//                bitmaps fl[2][chunk / 32 + 1], st[2][chunk / 32 + 1] | tabs[chunk][12]
 template <int NT>
 __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
     extern __shared__ double smem[];
@@ -252,13 +252,14 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
     double* cols = wf + 2 * R + 2;              // [NCOL][S] parked columns, struct of arrays
     double* raw = cols + NCOL * S;              // [NH][S] harmonic spectra of the current polarisation
     double* pb = raw + NH * S;                  // [FX_RB][6] phi basis of the rows being re-evaluated
-    unsigned* fl = reinterpret_cast<unsigned*>(pb + FX_RB * 6);      // [2][FLW]
+    unsigned* fl = reinterpret_cast<unsigned*>(pb + FX_RB * 6);      // [2][FLW] flagged rows, then [2][FLW] strict rows
     double* tabs = smem + blur_fixed_doubles(R, S) + (blur_chunk_doubles(CH) - CH * 12);     // [CH][12]
 
     const long long blk = blockIdx.x;
     const int tile = (int)(blk % a.n_tiles);
-    const int seg = (int)((blk / a.n_tiles) % a.n_seg);
-    const long long lcol = blk / a.n_tiles / a.n_seg;
+    const int n_seg = a.n_seg;
+    const int seg = (int)((blk / a.n_tiles) % n_seg);
+    const long long lcol = blk / a.n_tiles / n_seg;
     const long long col = a.col0 + lcol;
     const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
     const int tid = threadIdx.x;
@@ -301,7 +302,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
     const bool vec = a.vec_ok != 0;
     const long long rows_per_pol = a.nP * nE;
     double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
-    const long long seg_len = (items + a.n_seg - 1) / a.n_seg;
+    const long long seg_len = (items + n_seg - 1) / n_seg;
     const long long seg_lo = seg * seg_len, seg_hi = min(items, (seg + 1) * seg_len);
     const bool one_chunk = seg_hi - seg_lo <= CH;               // the whole table of this CTA fits: staged once
     const int INT_LOWEST = (int)0x80000000;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             const int n_items = (int)min((long long)CH, seg_hi - base);
             if (!one_chunk || pol == 0)         // (every thread is past the previous chunk: barrier at the end of the loop)
                 for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
-            for (int i = tid; i < 2 * FLW; i += NT) fl[i] = 0u;
+            for (int i = tid; i < 4 * FLW; i += NT) fl[i] = 0u;     // flagged rows and (D)'s strict rows
             __syncthreads();
             const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
             const int n_single = n_items - n_pair;
@@ -374,12 +375,54 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             }
             __syncthreads();                    // bitmap complete; nobody reads raw or this chunk's table any more
 
-            // ---- (D) flagged rows, FX_RB at a time.  The bitmap is the same for every thread: uniform control flow.
+            // ---- (D) flagged rows.  The bitmaps are the same for every thread: uniform control flow.
+            // First every thread looks at its own two values of each flagged row again (the arithmetic of the sweep: the
+            // same bits): a value in the band (DEEP, NODE) * U marks the row in the second bitmap `st`; negative rounding
+            // noise (exact symmetry zeros) is stored again as 0.  Rows marked in `st` are then re-evaluated the
+            // reference's way, FX_RB rows at a time; rows that were flagged only by exact zeros are done.
             if (!b.fixup) continue;
+            unsigned* st = fl + 2 * FLW;        // [2][FLW], cleared with fl
+            {
+                double thr0 = 0.0, thr1 = 0.0;  // NODE_FRACTION * U of this thread's energies (computed on first use)
+                bool have_thr = false;
+#pragma unroll 1
+                for (int wi = 0; wi < 2 * FLW; ++wi) {
+                    unsigned bits = fl[wi];
+                    unsigned mine = 0u;
+#pragma unroll 1
+                    while (bits) {
+                        const int bp = __ffs(bits) - 1;
+                        bits &= bits - 1;
+                        if (!active) continue;
+                        const int part = wi >= FLW ? 1 : 0;
+                        const int item = (wi - part * FLW) * 32 + bp;
+                        if (!have_thr) {
+                            thr0 = NODE_FRACTION * amplitude_bound(A0, pol == 3);
+                            thr1 = valid1 ? NODE_FRACTION * amplitude_bound(A1, pol == 3) : 0.0;
+                            have_thr = true;
+                        }
+                        double ye0, ye1, yo0, yo1;
+                        if (pol == 3) harm_item<true>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
+                        else harm_item<false>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
+                        const double y0 = part == 1 ? ye0 - yo0 : ye0 + yo0, y1 = part == 1 ? ye1 - yo1 : ye1 + yo1;
+                        const double band = DEEP_FRACTION / NODE_FRACTION;
+                        if (((y0 < thr0) & (y0 > band * thr0)) | (valid1 & (y1 < thr1) & (y1 > band * thr1))) {
+                            mine |= 1u << bp;
+                        } else if ((y0 < 0.0) | (valid1 & (y1 < 0.0))) {
+                            const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
+                            double* dst = out_col + (pol * a.nP + row) * nE;
+                            if (vec) store2t<true>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+                            else store2t<false>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+                        }
+                    }
+                    if (mine) atomicOr(st + wi, mine);
+                }
+            }
+            __syncthreads();                    // `st` complete
             int rows[FX_RB], nb = 0;
 #pragma unroll 1
             for (int wi = 0; wi <= 2 * FLW; ++wi) {
-                unsigned bits = wi < 2 * FLW ? fl[wi] : 0u;
+                unsigned bits = wi < 2 * FLW ? st[wi] : 0u;
                 const bool last = wi == 2 * FLW;
 #pragma unroll 1
                 while (bits || (last && nb > 0)) {
@@ -430,20 +473,19 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                         }
                     }
                     __syncthreads();
-                    // -- ... filtered along E (centre tap, then the pairs from the farthest inwards) and stored
+                    // -- ... filtered along E (four rows at a time: one LDS.128 feeds 4 FMAs) and stored
                     if (active) {
 #pragma unroll 1
-                        for (int q = 0; q < nb; ++q) {
-                            const double* x = rowbuf + q * S + tid * EPT;       // x[0 .. 2 R + 1]
-                            double o0 = x[R] * wf[R], o1 = x[R + 1] * wf[R];
-                            for (int j = R; j >= 1; --j) {
-                                const double w = wf[R + j];
-                                o0 = fma(x[R - j] + x[R + j], w, o0);
-                                o1 = fma(x[R + 1 - j] + x[R + 1 + j], w, o1);
-                            }
-                            double* dst = out_col + (pol * a.nP + (long long)rows[q]) * nE;
-                            if (vec) store2t<true>(dst, o0, o1, valid1);
-                            else store2t<false>(dst, o0, o1, valid1);
+                        for (int q0 = 0; q0 < nb; q0 += 4) {
+                            double o0[4], o1[4];
+                            fir_pair<4>(rowbuf + q0 * S + tid * EPT, S, R, wf, o0, o1);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (q0 + q < nb) {
+                                    double* dst = out_col + (pol * a.nP + (long long)rows[q0 + q]) * nE;
+                                    if (vec) store2t<true>(dst, o0[q], o1[q], valid1);
+                                    else store2t<false>(dst, o0[q], o1[q], valid1);
+                                }
                         }
                     }
                     __syncthreads();            // rowbuf and pb are free again

@@ -337,18 +337,24 @@ SSHG_HD void phi_harmonics(double phi_deg, double t[12]) {
     }
 }
 
-// U = |C0| + sum_q sqrt(C_q^2 + S_q^2) >= max over phi of the harmonic sum.  The rounding error of that sum is
+// U = |C0| + sum_q (|C_q| + |S_q|) >= |C0| + sum_q sqrt(C_q^2 + S_q^2) >= max over phi of the harmonic sum.  The rounding error of that sum is
 // <= 5e-14 U, so a value below NODE_FRACTION * U (the yield next to an azimuthal node, or an exact symmetry zero,
 // where the sum returns rounding noise of either sign) is no longer accurate to 1e-10 relative: K3 flags its row
 // and re-evaluates it the reference's way (|r|^2 per energy, then the FIR).  With 1e-3 everything that is NOT
 // flagged keeps an element-wise error below 5e-11.
 constexpr double NODE_FRACTION = 1e-3;
+// A flagged row whose values are all below DEEP_FRACTION * U is an exact node (a symmetry zero; the reference returns
+// ~1e-32 of the maximum there, K3 rounding noise of ~1e-15 U, stored as max(noise, 0)).  It is not re-evaluated:
+// U <= 13 max_phi y, so such a value is below 1.3e-7 of the maximum of any array that contains its column, i.e. outside
+// the element-wise part of the parity metric, and the `1e-10 * max` part holds with four orders to spare.
+constexpr double DEEP_FRACTION = 1e-8;
 
 SSHG_HD double amplitude_bound(const double* H, bool odd_only) {
+    // |C| + |S| >= sqrt(C^2 + S^2): a bound that needs no square roots (at most sqrt(2) above the tight one)
     double u = fabs(H[0]);
 #pragma unroll
     for (int j = 0; j < 6; ++j)
-        if (!odd_only || j < 3) u += sqrt(fma(H[1 + 2 * j], H[1 + 2 * j], H[2 + 2 * j] * H[2 + 2 * j]));
+        if (!odd_only || j < 3) u += fabs(H[1 + 2 * j]) + fabs(H[2 + 2 * j]);
     return u;
 }
 

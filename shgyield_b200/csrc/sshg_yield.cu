@@ -649,13 +649,12 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         for (int k = reg_limit; k >= 1; --k)
             if (need(blur_nt) <= share(k)) { blur_per_sm = k; break; }
         // grow the allocation to this occupancy's share, but not beyond what the whole table needs
-        const int items_all = (int)((p->nP + 31) / 32 * 32);                   // un-paired grid: one item per phi
+        const int items_all = (int)p->nP;                                      // un-paired grid: one item per phi
         size_t total = fixed(blur_nt) + (size_t)blur_chunk_doubles(items_all) * sizeof(double);
         if (total > share(blur_per_sm)) total = share(blur_per_sm);
         if (total > cta_max) total = cta_max;
-        int chunk = 32;                                                        // largest multiple of 32 that fits
-        while (chunk + 32 <= items_all && fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk + 32) * sizeof(double) <= total)
-            chunk += 32;
+        int chunk = 32;                                                        // as many items as fit
+        while (chunk < items_all && fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk + 1) * sizeof(double) <= total) ++chunk;
         blur_smem = fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk) * sizeof(double);
         ba.radius = (int)radius;
         ba.S = blur_nt * EPT + 2 * (int)radius;
@@ -727,8 +726,11 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.out = dst;
         b.y.n_tiles = blur_tiles;
         b.y.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
-        b.y.n_seg = pick_segments(nc * blur_tiles, blur_per_sm, 0.0);        // K3's setup (halo, harmonics, FIR) is too
-                                                                            // heavy to repeat: measured slower (tuning only)
+        // K3's setup (halo, harmonics, FIR) is too heavy to repeat: cutting the phi items of a column into segments
+        // measured slower, and so did cutting only the items of the last, partial wave of a short launch (config 3:
+        // 0.495 against 0.501 ms, config-5 shards 1 % slower: profiles/r02_k3_quick_tail_split.jsonl).  Option "nseg"
+        // cuts every item (tests).
+        b.y.n_seg = opt.nseg >= 1 ? opt.nseg : 1;
         SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)

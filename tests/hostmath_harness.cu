@@ -164,9 +164,9 @@ extern "C" int hostmath_sparse_walk(const sshg_points* p, long long e, double th
 // ---- K3 on the CPU: harmonic form of one (theta, thickness) column, broadened along the energy axis ----
 // p: a point list whose spectra columns are the energy axis (eidx unused); theta / thickness scalars;
 // phi: nP azimuths; w: r + 1 Gaussian taps (w[0] centre); out[pol][nP][nE].
-// strict_nodes: 1 = as the product: a value below NODE_FRACTION of its column's amplitude bound flags its
-// (polarisation, row, 256-energy tile), which is then re-evaluated row-wise (|r|^2 per energy, FIR); 0 = the harmonic
-// sums alone.
+// strict_nodes: 1 = as the product: a value between DEEP_FRACTION and NODE_FRACTION of its column's amplitude bound
+// flags its (polarisation, row, 256-energy tile), which is then re-evaluated row-wise (|r|^2 per energy, FIR), values
+// below DEEP_FRACTION (exact symmetry zeros) are stored as max(noise, 0); 0 = the harmonic sums alone.
 extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, double thick_nm, const double* phi_deg,
                                     long long nP, const double* w, int r, int strict_nodes, double* out) {
     Physics ph;
@@ -247,7 +247,10 @@ extern "C" int hostmath_blur_column(const sshg_points* p, double theta_deg, doub
                 double y = harmonic_yield(H, t, pol == 3);
                 if (strict_nodes) {
                     const double u = amplitude_bound(H, pol == 3);
-                    if (u < 1.0e300 && y < NODE_FRACTION * u) flag[(size_t)(e / FXT)] = 1;
+                    if (u < 1.0e300 && y < NODE_FRACTION * u) {
+                        if (y > DEEP_FRACTION * u) flag[(size_t)(e / FXT)] = 1;   // next to a node: the tile's row is re-evaluated
+                        else y = fmax(y, 0.0);                                    // exact node: rounding noise, never negative
+                    }
                 }
                 out[((size_t)pol * nP + ip) * nE + e] = y;
             }

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Quick timing of the fused broadened sweep (K3) on the cases that steer its tuning: config 3 (Si(111), short launch,
+symmetry nodes), config-5 shards (random chi2, long launches).  One JSON line per case.
+
+    python tools/k3_quick.py [tag]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from shgyield_b200 import _lib, grid, shg  # noqa: E402
+from shgyield_b200.synthetic import config5  # noqa: E402
+from tests import cases  # noqa: E402
+from tools.bench_configs import timed  # noqa: E402
+
+tag = sys.argv[1] if len(sys.argv) > 1 else ""
+dev = torch.device("cuda", 0)
+put = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+consts = shg.physical_constants()
+m1, m2, m3, chi2 = cases.si111_material()
+axes = cases.config3_axes()
+eps1w, eps2w, chi_rot, thick = shg._prepare(axes["energy"], m1, m2, m3, chi2, axes["thick"], axes["gamma"], 0.0, 0.0, "3-layer")
+c3 = [put(axes["energy"]), put(axes["theta"]), put(axes["phi"]), put(np.atleast_1d(thick).astype(float)), put(eps1w),
+      put(eps2w), put(chi_rot)]
+cfg = config5()
+dd = {k: put(v) for k, v in cfg.items()}
+c5 = [dd[k] for k in ("energy", "theta", "phi", "thick", "eps1w", "eps2w", "chi2")]
+for name, args, t_range, shape in (("config3", c3, None, (90, 1, 4, 360, 2000)), ("c5_23theta", c5, (0, 23), (23, 1, 4, 721, 20000)),
+                                   ("c5_46theta", c5, (0, 46), (46, 1, 4, 721, 20000))):
+    out = torch.empty(shape, dtype=torch.float64, device=dev)
+    for sigma in (0.0, 2.0, 5.0, 12.0):
+        med, best = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 9)
+        with _lib.context(0).options(nseg=1):       # the same without cutting the tail of the launch into phi segments
+            med1, best1 = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 9)
+        print(json.dumps({"tag": tag, "case": name, "sigma_out": sigma, "ms_median": round(med, 4), "ms_best": round(best, 4),
+                          "store_gbs": round(8e-9 * out.numel() / (med * 1e-3)), "ms_median_nseg1": round(med1, 4)}), flush=True)
+    del out
