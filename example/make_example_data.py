@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Writes the Si(111)(1x1):H example spectra as text files (the formats `loadeps` / `loadshg` read)
-from the fixture tests/golden/si111_spectra.npz, next to example/si111-input.yml:
+from example/si111_spectra.npz (the raw file columns of the example material), next to example/si111-input.yml:
 
     python example/make_example_data.py [target_dir]
     python shgyield.py example/si111-input.yml
@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def write(target=HERE):
-    z = np.load(os.path.join(os.path.dirname(HERE), "tests", "golden", "si111_spectra.npz"))
+    z = np.load(os.path.join(HERE, "si111_spectra.npz"))
     e = z["energy"]
     for sub in ("chi1-linear", "chi2-nonlinear"):
         os.makedirs(os.path.join(target, sub), exist_ok=True)

@@ -149,14 +149,7 @@ BLUR_SWEEP_GAMMA = {"si111": 0, "full": 33}
 
 
 # ---- sampled points of the large grids (configs 3, 4, 5 of BASELINE.json) --------------------
-def config3_axes():
-    return dict(energy=np.linspace(0.005, 10.0, 2000), theta=np.arange(0, 90, dtype=np.float64),
-                phi=np.arange(0, 360, dtype=np.float64), thick=np.array([10.0]), gamma=0)
-
-
-def config4_axes():
-    return dict(energy=0.01 * np.arange(1, 1001), theta=np.arange(0, 90, dtype=np.float64),
-                phi=np.array([30.0]), thick=np.arange(1, 101, dtype=np.float64), gamma=0)
+from shgyield_b200.synthetic import config3_axes, config4_axes  # noqa: E402,F401  (one definition for tests and bench)
 
 
 def sample_indices(shape, n, seed):

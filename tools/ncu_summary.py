@@ -2,7 +2,10 @@
 """Summarises ncu artefacts brought back in gpurun_out/ into small text files for profiles/.
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv           > profiles/rNN_launches.txt
-    python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [kernel-regex] > profiles/rNN_kernel.txt
+    python tools/ncu_summary.py full gpurun_out/prof.ncu-rep [kernel-regex] [alg_bytes=N] > profiles/rNN_kernel.txt
+
+alg_bytes=N adds the line `algorithmic_bytes byte N` (the algorithmic bytes of the captured launch), which
+bench.py reads together with the dram__bytes lines for `roofline.traffic`.
 """
 import csv
 import io
@@ -44,7 +47,7 @@ def launches(path):
         print("%-70s %6d %14.0f %8.4f %12.0f" % (k[:70], cnt[k], v, v / s, v / cnt[k]))
 
 
-def full(path, pattern=None):
+def full(path, pattern=None, alg_bytes=None):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -57,6 +60,8 @@ def full(path, pattern=None):
             if k in hdr:
                 i = hdr.index(k)
                 print("%-75s %-14s %s" % (k, units[i], r[i]))
+        if alg_bytes is not None:
+            print("%-75s %-14s %s" % ("algorithmic_bytes", "byte", alg_bytes))
         print()
 
 
@@ -64,4 +69,7 @@ if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
     else:
-        full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+        rest = sys.argv[3:]
+        alg = next((a.split("=", 1)[1] for a in rest if a.startswith("alg_bytes=")), None)
+        pat = next((a for a in rest if not a.startswith("alg_bytes=")), None)
+        full(sys.argv[2], pat, alg)
