@@ -44,7 +44,9 @@ typedef enum {
     SSHG_ENOMEM = -3    /* host or device allocation failed (MemoryError)  */
 } sshg_status;
 
-enum { SSHG_HOST = 0, SSHG_IN_DEVICE = 1, SSHG_OUT_DEVICE = 2, SSHG_DEVICE = 3 };
+enum { SSHG_HOST = 0, SSHG_IN_DEVICE = 1, SSHG_OUT_DEVICE = 2, SSHG_DEVICE = 3,
+       SSHG_SPECTRA_DEVICE = 4 /* sshg_yield_points_broadened: energy_eV, eps1w, eps2w, chi2 are device pointers (spectra
+                                  prepared once and kept resident), the point arrays and `out` are host pointers */ };
 
 /* polarisation order of every output: index 0..3 = pp, ps, sp, ss
  * (first letter = incoming 1w field, second = outgoing 2w field; reference shg.py:433-436) */
@@ -145,6 +147,11 @@ SSHG_API int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value);
 SSHG_API int sshg_ctx_get_option(sshg_ctx* ctx, const char* key, int64_t* value);
 SSHG_API int sshg_host_alloc(void** ptr, int64_t bytes);  /* page-locked host memory for fast D2H    */
 SSHG_API int sshg_host_free(void* ptr);
+/* host array -> device memory obtained from sshg_device_alloc (synchronous): prepared spectra that stay resident */
+SSHG_API int sshg_upload(sshg_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes);
+/* 64-bit content hash of a host buffer (xxHash64 construction, ~10 GB/s): the key under which the Python layer
+ * keeps prepared spectra, so that an array modified IN PLACE is noticed (reference to-do, shg.py:11-12) */
+SSHG_API uint64_t sshg_hash64(const void* data, int64_t bytes, uint64_t seed);
 
 /* ---- the gather of the yield cube without a collective: peer memory over NVLink ----------------
  * north_star's one exchange step is the gather of the theta slabs onto one GPU.  Instead of computing a
@@ -169,6 +176,12 @@ SSHG_API int sshg_ipc_close(sshg_ctx* ctx, void* dev_ptr);
 SSHG_API int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_t rows, int64_t n,
                  int64_t row_stride, int64_t elem_stride, double sigma, int where);
 
+/* The same along EVERY axis of a C-contiguous N-D array of extents shape[ndim] -- what broad() does to an N-D result
+ * (scipy.ndimage.gaussian_filter(data, sigma), shg.py:26-28): one pass per axis on the device, the array crosses PCIe
+ * once each way. */
+SSHG_API int sshg_gauss_nd(sshg_ctx* ctx, const double* in, double* out, int32_t ndim, const int64_t* shape, double sigma,
+                  int where);
+
 /* ---- in-plane rotation of chi2: replaces rotate (shg.py:63-134).
  * chi_in / chi_out: [18][nE][2]; gamma_deg as passed to shgyield().  xxy_quirk = 1 keeps the
  * reference's sign on the chi_yyy contribution to chi_xxy (shg.py:92). */
@@ -191,6 +204,14 @@ SSHG_API int sshg_broaden_resample(sshg_ctx* ctx, const double* x, const double*
  * contraction + |Gamma r|^2 (shg.py:137-378, 428-436).  */
 SSHG_API int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int where);
 SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
+/* The tail of shgyield() for a point list that is the C-order flattening of a NumPy broadcast of extents shape[ndim]
+ * (prod(shape) = p->n): the four yields, then broad(., sigma_out) along every axis of the [shape] array
+ * (shg.py:428-436); out[pol][n].  `where` = SSHG_HOST, SSHG_SPECTRA_DEVICE, or SSHG_DEVICE.  Host calls with resident
+ * spectra (the interactive call shapes of the reference's GUI, gui.py:286-330) upload the point arrays in one copy
+ * from page-locked staging memory and replay a CUDA graph (copy in, yield kernel, FIR passes, copy out) that is
+ * recorded the first time a (shape, sigma_out, physics, spectra) combination is seen; option "graphs" = 0 disables. */
+SSHG_API int sshg_yield_points_broadened(sshg_ctx* ctx, const sshg_points* p, double sigma_out, int32_t ndim,
+                                const int64_t* shape, double* out, int where);
 /* The same sweep with the output broadening of shgyield() (broad(., sigma_out) on every yield spectrum,
  * shg.py:26-28, 433-436; sigma_out in SAMPLES of the energy axis, 5.0 is the reference's default):
  * out[t][d][pol][p][:] = gaussian_filter(yield[t][d][pol][p][:], sigma_out) with scipy.ndimage's taps,

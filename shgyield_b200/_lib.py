@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libsshg.so")
 
 SSHG_OK, SSHG_EINVAL, SSHG_ECUDA, SSHG_ENOMEM = 0, -1, -2, -3
-HOST, IN_DEVICE, OUT_DEVICE, DEVICE = 0, 1, 2, 3
+HOST, IN_DEVICE, OUT_DEVICE, DEVICE, SPECTRA_DEVICE = 0, 1, 2, 3, 4
 ABI_VERSION = 2
 FLAG_RADIANS = 1
 FLAG_STRICT_BROADENING = 2
@@ -64,6 +64,8 @@ SYMBOLS = {
     "sshg_ctx_get_option": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "sshg_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64]),
     "sshg_host_free": (C.c_int, [C.c_void_p]),
+    "sshg_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
+    "sshg_hash64": (C.c_uint64, [C.c_void_p, C.c_int64, C.c_uint64]),
     "sshg_device_alloc": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int64]),
     "sshg_device_free": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sshg_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p]),
@@ -71,6 +73,7 @@ SYMBOLS = {
     "sshg_ipc_close": (C.c_int, [C.c_void_p, C.c_void_p]),
     "sshg_gauss1d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                C.c_double, C.c_int]),
+    "sshg_gauss_nd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_double, C.c_int]),
     "sshg_rotate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int]),
     "sshg_spline_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p,
                                        C.c_int64, C.c_void_p, C.c_int]),
@@ -79,6 +82,8 @@ SYMBOLS = {
     "sshg_yield": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_void_p, C.c_int]),
     "sshg_yield_broadened": (C.c_int, [C.c_void_p, C.POINTER(Problem), C.c_double, C.c_void_p, C.c_int]),
     "sshg_yield_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
+    "sshg_yield_points_broadened": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
+                                              C.c_int]),
     "sshg_fresnel": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int]),
     "sshg_multiref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(Physics), C.c_void_p, C.c_int64, C.c_int]),

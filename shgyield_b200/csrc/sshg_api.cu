@@ -49,6 +49,7 @@ int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out) {
             return SSHG_ENOMEM;
         }
         ctx->scratch_bytes[slot] = cap;
+        ctx->epoch++;
     }
     *out = ctx->scratch[slot];
     return SSHG_OK;
@@ -139,6 +140,10 @@ void sshg_ctx_destroy(sshg_ctx* ctx) {
         if (ctx->ev_done[k]) cudaEventDestroy(ctx->ev_done[k]);
         if (ctx->ev_copied[k]) cudaEventDestroy(ctx->ev_copied[k]);
     }
+    for (int k = 0; k < SSHG_NGRAPH; ++k)
+        if (ctx->graphs[k].exec) cudaGraphExecDestroy(ctx->graphs[k].exec);
+    if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+    if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -231,6 +236,56 @@ int sshg_host_free(void* ptr) {
     if (!ptr) return SSHG_OK;
     SSHG_CUDA(cudaFreeHost(ptr));
     return SSHG_OK;
+}
+
+int sshg_upload(sshg_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {
+    SSHG_REQUIRE(ctx && dst_dev && src_host && bytes > 0, "sshg_upload: bad argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    SSHG_CUDA(cudaMemcpyAsync(dst_dev, src_host, (size_t)bytes, cudaMemcpyHostToDevice, ctx->stream));
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SSHG_OK;
+}
+
+// xxHash64 construction (Y. Collet's public specification): four 64-bit lanes over 32-byte stripes, merged and
+// avalanched.  Host code; used as a content key, not for security.
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+uint64_t sshg_hash64(const void* data, int64_t bytes, uint64_t seed) {
+    const uint64_t P1 = 11400714785074694791ull, P2 = 14029467366897019727ull, P3 = 1609587929392839161ull,
+                   P4 = 9650029242287828579ull, P5 = 2870177450012600261ull;
+    if (!data || bytes <= 0) return seed ^ P5;
+    const unsigned char* p = (const unsigned char*)data;
+    const unsigned char* end = p + bytes;
+    auto rd64 = [](const unsigned char* q) { uint64_t v; memcpy(&v, q, 8); return v; };
+    auto round = [&](uint64_t acc, uint64_t in) { return rotl64(acc + in * P2, 31) * P1; };
+    uint64_t h;
+    if (bytes >= 32) {
+        uint64_t v1 = seed + P1 + P2, v2 = seed + P2, v3 = seed, v4 = seed - P1;
+        const unsigned char* limit = end - 32;
+        do {
+            v1 = round(v1, rd64(p));
+            v2 = round(v2, rd64(p + 8));
+            v3 = round(v3, rd64(p + 16));
+            v4 = round(v4, rd64(p + 24));
+            p += 32;
+        } while (p <= limit);
+        h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        auto merge = [&](uint64_t acc, uint64_t v) { return (acc ^ round(0, v)) * P1 + P4; };
+        h = merge(h, v1); h = merge(h, v2); h = merge(h, v3); h = merge(h, v4);
+    } else {
+        h = seed + P5;
+    }
+    h += (uint64_t)bytes;
+    while (p + 8 <= end) {
+        h = rotl64(h ^ round(0, rd64(p)), 27) * P1 + P4;
+        p += 8;
+    }
+    while (p < end) {
+        h = rotl64(h ^ (*p * P5), 11) * P1;
+        ++p;
+    }
+    h ^= h >> 33; h *= P2; h ^= h >> 29; h *= P3; h ^= h >> 32;
+    return h;
 }
 
 // ---- peer memory for the store-through gather (include/sshg.h) ---------------------------------------

@@ -215,17 +215,25 @@ constexpr int GPT = 4;           // outputs per thread
 constexpr int GTILE = GT * GPT;  // outputs per CTA
 
 // smem: [GTILE + 2r] samples, then [r + 1] taps (w[0] = centre)
+// Row `row` starts at (row / inner_rows) * outer_stride + (row % inner_rows) * row_stride: filtering a middle axis of an
+// N-D array (rows = outer x inner signals) is one launch; plain row lists pass inner_rows = rows.
+__device__ __forceinline__ long long row_start(long long row, long long inner_rows, long long outer_stride, long long row_stride) {
+    return (row / inner_rows) * outer_stride + (row % inner_rows) * row_stride;
+}
+
 __global__ void __launch_bounds__(GT) gauss_tiled_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                          const double* __restrict__ taps, long long rows,
                                                          long long n, long long row_stride, long long elem_stride,
+                                                         long long inner_rows, long long outer_stride,
                                                          int r, int tiles_per_row) {
     extern __shared__ double sm[];
     double* xs = sm;
     double* ws = sm + GTILE + 2 * r;
     const long long row = blockIdx.x / tiles_per_row;
     const long long i0 = (long long)(blockIdx.x % tiles_per_row) * GTILE;
-    const double* src = in + row * row_stride;
-    double* dst = out + row * row_stride;
+    const long long start = row_start(row, inner_rows, outer_stride, row_stride);
+    const double* src = in + start;
+    double* dst = out + start;
     const int span = GTILE + 2 * r;
     for (int k = threadIdx.x; k < span; k += GT) {
         long long i = i0 - r + k;
@@ -257,22 +265,25 @@ __global__ void __launch_bounds__(GT) gauss_tiled_kernel(const double* __restric
 // Fallback for radii whose halo does not fit in shared memory.
 __global__ void gauss_direct_kernel(const double* __restrict__ in, double* __restrict__ out,
                                     const double* __restrict__ taps, long long rows, long long n,
-                                    long long row_stride, long long elem_stride, long long r) {
+                                    long long row_stride, long long elem_stride, long long inner_rows,
+                                    long long outer_stride, long long r) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= rows * n) return;
     const long long row = g / n, i = g % n;
-    const double* src = in + row * row_stride;
+    const long long start = row_start(row, inner_rows, outer_stride, row_stride);
+    const double* src = in + start;
     double acc = src[i * elem_stride] * taps[0];
     for (long long j = r; j >= 1; --j)
         acc = fma(src[reflect(i - j, n) * elem_stride] + src[reflect(i + j, n) * elem_stride], taps[j], acc);
-    out[row * row_stride + i * elem_stride] = acc;
+    out[start + i * elem_stride] = acc;
 }
 
 __global__ void copy_strided_kernel(const double* __restrict__ in, double* __restrict__ out, long long rows,
-                                    long long n, long long row_stride, long long elem_stride) {
+                                    long long n, long long row_stride, long long elem_stride, long long inner_rows,
+                                    long long outer_stride) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= rows * n) return;
-    const long long off = (g / n) * row_stride + (g % n) * elem_stride;
+    const long long off = row_start(g / n, inner_rows, outer_stride, row_stride) + (g % n) * elem_stride;
     out[off] = in[off];
 }
 
@@ -296,10 +307,18 @@ void sshg_gaussian_taps(double sigma, long long r, double* w) {
 // Device-level filter: din / dout are device pointers; queued on ctx->stream.
 int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                       int64_t elem_stride, double sigma) {
+    return sshg_gauss_device_ex(ctx, din, dout, rows, n, row_stride, elem_stride, rows, 0, sigma);
+}
+
+// The same with the row addressing of an N-D axis: row k starts at (k / inner_rows) * outer_stride +
+// (k % inner_rows) * row_stride.
+int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
+                         int64_t elem_stride, int64_t inner_rows, int64_t outer_stride, double sigma) {
     const long long total = (long long)rows * n;
+    const bool plain = inner_rows >= rows;                  // rows are row_stride apart: the contiguous kernels apply
     if (!(sigma > 1e-15)) {
         copy_strided_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(din, dout, rows, n, row_stride,
-                                                                                   elem_stride);
+                                                                                   elem_stride, inner_rows, outer_stride);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
@@ -323,7 +342,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         ctx->tap_sigma = sigma;
         ctx->tap_ptr = dw;
     }
-    if (elem_stride == 1 && ctx->opt.k1_generic != 1) {
+    if (elem_stride == 1 && plain && ctx->opt.k1_generic != 1) {
         switch (r) {                               // radii with a compile-time specialisation
 #define SSHG_FIXED(R_) case R_: return launch_fixed<R_>(ctx, din, dout, rows, n, row_stride, ctx->tap_host);
             SSHG_FIXED(4) SSHG_FIXED(6) SSHG_FIXED(8) SSHG_FIXED(10) SSHG_FIXED(12) SSHG_FIXED(14) SSHG_FIXED(16)
@@ -334,7 +353,7 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
     }
     const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;
-    if (elem_stride == 1 && smem_stream <= SMEM_CAP) {
+    if (elem_stride == 1 && plain && smem_stream <= SMEM_CAP) {
         const int tiles = (int)((n + STILE - 1) / STILE);
         SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
         SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
@@ -345,10 +364,12 @@ int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t ro
         SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
         SSHG_CUDA(cudaFuncSetAttribute(gauss_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
         gauss_tiled_kernel<<<(unsigned)(rows * tiles), GT, smem_tiled, ctx->stream>>>(din, dout, (const double*)dw, rows, n,
-                                                                                    row_stride, elem_stride, (int)r, tiles);
+                                                                                    row_stride, elem_stride, inner_rows,
+                                                                                    outer_stride, (int)r, tiles);
     } else {
         gauss_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(din, dout, (const double*)dw, rows, n,
-                                                                                   row_stride, elem_stride, r);
+                                                                                   row_stride, elem_stride, inner_rows,
+                                                                                   outer_stride, r);
     }
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -375,6 +396,69 @@ extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_
         if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
     }
     if (int rc = sshg_gauss_device(ctx, (const double*)din, (double*)dout, rows, n, row_stride, elem_stride, sigma)) return rc;
+    if (!out_dev) {
+        SSHG_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return SSHG_OK;
+}
+
+// Every axis of a C-contiguous N-D array, as scipy.ndimage.gaussian_filter(data, sigma) does it (broad(), shg.py:26-28,
+// on an N-D result): one pass per axis, ping-pong between `out` and one scratch buffer, the array crosses PCIe once
+// each way.  `lead` leading axes are NOT filtered (the four polarisations of a yield stack).  All on the device.
+int sshg_gauss_nd_device(sshg_ctx* ctx, const double* din, double* dout, int lead, int ndim, const int64_t* shape,
+                         double sigma) {
+    int64_t total = 1;
+    for (int a = 0; a < ndim; ++a) total *= shape[a];
+    const int passes = ndim - lead;
+    if (passes <= 0 || !(sigma > 1e-15) || total == 0) {
+        if (total) SSHG_CUDA(cudaMemcpyAsync(dout, din, (size_t)total * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        return SSHG_OK;
+    }
+    void* tmp = nullptr;
+    if (passes > 1) {
+        if (int rc = sshg_scratch(ctx, SCR_ND, (size_t)total * 8, &tmp)) return rc;
+    }
+    // the last pass must land in dout: passes alternate dout / tmp backwards from there
+    const double* src = din;
+    for (int k = 0; k < passes; ++k) {
+        const int a = lead + k;
+        double* dst = ((passes - 1 - k) % 2 == 0) ? dout : (double*)tmp;
+        int64_t outer = 1, inner = 1;
+        for (int j = 0; j < a; ++j) outer *= shape[j];
+        for (int j = a + 1; j < ndim; ++j) inner *= shape[j];
+        const int64_t n = shape[a];
+        int rc;
+        if (inner == 1) rc = sshg_gauss_device(ctx, src, dst, outer, n, n, 1, sigma);
+        else rc = sshg_gauss_device_ex(ctx, src, dst, outer * inner, n, 1, inner, inner, n * inner, sigma);
+        if (rc) return rc;
+        src = dst;
+    }
+    return SSHG_OK;
+}
+
+extern "C" int sshg_gauss_nd(sshg_ctx* ctx, const double* in, double* out, int32_t ndim, const int64_t* shape, double sigma,
+                             int where) {
+    SSHG_TRACE("sshg_gauss_nd");
+    SSHG_REQUIRE(ctx && in && out && (shape || ndim == 0), "sshg_gauss_nd: null argument");
+    SSHG_REQUIRE(in != out, "sshg_gauss_nd: in-place filtering is not supported");
+    SSHG_REQUIRE(ndim >= 0 && ndim <= 16, "sshg_gauss_nd: ndim must be in 0 .. 16 (got %d)", (int)ndim);
+    SSHG_REQUIRE(sigma >= 0.0 && isfinite(sigma), "sshg_gauss_nd: sigma must be finite and >= 0 (got %g)", sigma);
+    int64_t total = 1;
+    for (int a = 0; a < ndim; ++a) {
+        SSHG_REQUIRE(shape[a] > 0, "sshg_gauss_nd: extents must be positive");
+        total *= shape[a];
+    }
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const int in_dev = (where & SSHG_IN_DEVICE) != 0, out_dev = (where & SSHG_OUT_DEVICE) != 0;
+    const size_t bytes = (size_t)total * 8;
+    const void* din = in;
+    if (int rc = sshg_stage_in(ctx, 10, in, bytes, in_dev, &din)) return rc;
+    void* dout = out;
+    if (!out_dev) {
+        if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
+    }
+    if (int rc = sshg_gauss_nd_device(ctx, (const double*)din, (double*)dout, 0, ndim, shape, sigma)) return rc;
     if (!out_dev) {
         SSHG_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         SSHG_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -16,12 +16,17 @@ struct sshg_trace_range {
 };
 #define SSHG_TRACE(name) sshg_trace_range sshg_trace_range_(name)
 
-#define SSHG_NSCRATCH 24
+#define SSHG_NSCRATCH 32
 #define SSHG_TAP_HOST 64
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
 #define SCR_SPLFAC 17    // spline elimination coefficients of the last axis (cached)
 #define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel (slot 19: thickness-axis info)
 #define SCR_BROAD 16     // broadened rows handed from K1 to the spline kernels
+#define SCR_ND 21        // ping-pong buffer of the N-D Gaussian filter
+#define SCR_PTS_IN 22    // small point-list calls: theta | phi | thick | eidx, one upload
+#define SCR_PTS_Y 23     // ... un-broadened yields [4][n]
+#define SCR_PTS_OUT 24   // ... broadened yields [4][n]
+#define SCR_SPLTAB 25    // spline: cyclic-reduction coefficient tables of the cached axis
 
 // Test / tuning switches of a context (sshg_ctx_set_option, include/sshg.h); -1 = the library decides.
 struct sshg_options {
@@ -34,6 +39,25 @@ struct sshg_options {
     int nseg;           // phi segments per column (1 .. 16)
     int k1_generic;     // 1: never use the fixed-radius FIR kernels
     int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
+};
+
+// A recorded small call: copy in -> yield_points_kernel -> FIR passes -> copy out, keyed on everything the recorded
+// kernel arguments depend on.
+#define SSHG_NGRAPH 4
+struct sshg_small_key {
+    int64_t n, nE;
+    int32_t ndim;
+    int64_t shape[8];
+    double sigma_out;
+    sshg_physics phys;
+    const void *energy, *eps1w, *eps2w, *chi2;      // resident spectra
+    uint64_t epoch;
+};
+struct sshg_small_graph {
+    sshg_small_key key;
+    cudaGraphExec_t exec;       // null: slot free
+    uint64_t used;              // LRU stamp
+    int launches;               // kernels per replay
 };
 
 struct sshg_ctx {
@@ -56,6 +80,14 @@ struct sshg_ctx {
     // growable device scratch buffers (inputs copied from the host, staged outputs)
     void* scratch[SSHG_NSCRATCH];
     size_t scratch_bytes[SSHG_NSCRATCH];
+    uint64_t epoch;             // bumped whenever a scratch or staging buffer moves: recorded graphs of older epochs are stale
+    // small point-list calls (sshg_yield_points_broadened): page-locked staging + recorded CUDA graphs
+    void* pin_in;
+    void* pin_out;
+    size_t pin_in_bytes, pin_out_bytes;
+    sshg_small_graph graphs[SSHG_NGRAPH];
+    uint64_t graph_clock;
+    int64_t graph_replays;
 };
 
 void sshg_set_error(const char* fmt, ...);
@@ -79,6 +111,10 @@ int sshg_scratch(sshg_ctx* ctx, int slot, size_t bytes, void** out);   // grows 
 // Device-level stages (all pointers on the device, queued on ctx->stream)
 int sshg_gauss_device(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                       int64_t elem_stride, double sigma);
+int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
+                         int64_t elem_stride, int64_t inner_rows, int64_t outer_stride, double sigma);
+int sshg_gauss_nd_device(sshg_ctx* ctx, const double* din, double* dout, int lead, int ndim, const int64_t* shape,
+                         double sigma);
 int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
                        int64_t nq, double* dout, int* dflag, uint64_t axis_hash);
 

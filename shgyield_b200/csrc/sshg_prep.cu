@@ -10,7 +10,7 @@
 //  * sshg_spline_resample replaces spline/splineC/splineEPS (shg.py:38-55, 423-424):
 //    InterpolatedUnivariateSpline(x, y, ext=2) is FITPACK's interpolating cubic spline with
 //    knots x[2:-2], i.e. the unique not-a-knot cubic interpolant.  It is computed here from its
-//    second derivatives (tridiagonal system, Thomas algorithm, one thread per signal) and
+//    second derivatives (tridiagonal system, parallel cyclic reduction, one CTA per signal) and
 //    evaluated piecewise.
 #include "sshg_internal.h"
 
@@ -63,177 +63,126 @@ __global__ void rotate_kernel(const double2* __restrict__ in, double2* __restric
 }
 
 // ---- spline -------------------------------------------------------------------------------
-// Not-a-knot cubic spline through its second derivatives M: tridiagonal system in M_1..M_{n-2}
-// (Thomas algorithm).  The elimination coefficients depend on the axis x only, so they are
-// factored once per axis by one thread (`spline_factor_kernel`; cached in the context while the
-// same axis keeps coming) and every signal then needs two short first-order recurrences
-// (`spline_solve_kernel`, one thread per signal, FMA-latency bound).
+// Not-a-knot cubic spline through its second derivatives M: a tridiagonal, diagonally dominant system in
+// M_1..M_{n-2}, solved by PARALLEL CYCLIC REDUCTION -- ceil(log2 m) levels, every unknown updated by every level, all
+// threads of a CTA busy (the Thomas recurrences of round 1 ran on one thread: 0.36 ms per axis + 63 us per launch).
 //
-// fac layout, m = n - 2:  cp[m] | inv[m] | low[m] | ih[n-1]   (ih[i] = 1 / (x[i+1] - x[i]))
-__global__ void spline_factor_kernel(const double* __restrict__ x, double* __restrict__ fac, long long n) {
-    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// Rows are kept normalised (diagonal 1):  A_i x_{i-s} + x_i + C_i x_{i+s} = D_i.  One level with stride s replaces
+// row i by  row_i - A_i row_{i-s} - C_i row_{i+s},  renormalised:
+//     beta = 1 - A_i C_{i-s} - C_i A_{i+s},   A' = -A_i A_{i-s} / beta,   C' = -C_i C_{i+s} / beta,
+//     D'   = (D_i - A_i D_{i-s} - C_i D_{i+s}) / beta
+// (neighbours outside 0..m-1 do not exist: their A_i / C_i is 0).  After L levels (2^L >= m) the rows are decoupled and
+// x = D.  A, C and 1/beta depend on the axis only: `spline_pcr_factor_kernel` tabulates them once per axis (cached in
+// the context while the same axis keeps coming), and a signal then costs 2 FMAs + 1 multiply per unknown and level.
+//
+// tab layout, m = n - 2, L levels:  ib0[m] | ih[n-1] | per level l: A[m] | C[m] | ib[m]      (ih[i] = 1 / (x[i+1] - x[i]))
+__host__ __device__ inline int pcr_levels(long long m) {
+    int L = 0;
+    while ((1LL << L) < m) ++L;
+    return L;
+}
+__host__ __device__ inline long long pcr_tab_doubles(long long n) { return (n - 2) + (n - 1) + 3LL * pcr_levels(n - 2) * (n - 2); }
+
+__global__ void __launch_bounds__(1024) spline_pcr_factor_kernel(const double* __restrict__ x, double* __restrict__ tab,
+                                                                 long long n) {
     const long long m = n - 2;
-    double* cp = fac;
-    double* inv = fac + m;
-    double* low = fac + 2 * m;
-    double* ih = fac + 3 * m;
+    const int L = pcr_levels(m);
+    double* ib0 = tab;
+    double* ih = tab + m;
+    double* lev = ih + (n - 1);
     const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
     const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
-    double cprev = 0.0;
-    for (long long i = 0; i < m; ++i) {
+    // level 0: the rows of the not-a-knot system, normalised by their diagonal
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
         const double hl = x[i + 1] - x[i], hr = x[i + 2] - x[i + 1];
         double lower = hl, diag = 2.0 * (hl + hr), upper = hr;
         if (i == 0) {                           // not-a-knot at x_1: M_0 = (1 + q0) M_1 - q0 M_2
             diag += hl * (1.0 + q0);
             upper -= hl * q0;
+            lower = 0.0;
         }
         if (i == m - 1) {                       // not-a-knot at x_{n-2}
             diag += hr * (1.0 + q1);
             lower -= hr * q1;
+            upper = 0.0;
         }
-        const double den = (i == 0) ? diag : diag - lower * cprev;
-        const double r = 1.0 / den;
-        cprev = upper * r;
-        cp[i] = cprev;
-        inv[i] = r;
-        low[i] = (i == 0) ? 0.0 : lower;
+        if (m == 1) lower = 0.0;
+        const double r = 1.0 / diag;
+        ib0[i] = r;
         ih[i] = 1.0 / hl;
         if (i == m - 1) ih[i + 1] = 1.0 / hr;
+        if (L > 0) {
+            lev[i] = lower * r;                 // A of level 0
+            lev[m + i] = upper * r;             // C of level 0
+        }
+    }
+    for (int l = 0; l < L; ++l) {
+        __syncthreads();                        // one CTA: the global writes of the previous level are visible
+        const long long s = 1LL << l;
+        double* A = lev + 3LL * l * m;
+        double* C = A + m;
+        double* ib = C + m;
+        double* An = A + 3 * m;                 // level l + 1
+        double* Cn = An + m;
+        for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+            const double a = A[i], c = C[i];
+            const bool lo = i - s >= 0, hi = i + s < m;
+            const double beta = 1.0 - (lo ? a * C[i - s] : 0.0) - (hi ? c * A[i + s] : 0.0);
+            const double r = 1.0 / beta;
+            ib[i] = r;
+            if (l + 1 < L) {
+                An[i] = lo ? -(a * A[i - s]) * r : 0.0;
+                Cn[i] = hi ? -(c * C[i + s]) * r : 0.0;
+            }
+        }
     }
 }
 
-// One CTA per signal, everything in shared memory (3 m doubles: 48 KB for the 2001-sample spectra).
-// All threads form a_i = rhs_i * inv_i, b_i = low_i * inv_i in parallel; thread 0 then runs the two
-// first-order recurrences  d_i = a_i - b_i d_{i-1}  and  M_{i+1} = d_i - cp_i M_{i+2}  as dependent
-// FMAs fed from shared memory (global loads inside the chain cost ~500 cycles per step).
-// y, M: [rows][n].
-__global__ void __launch_bounds__(128) spline_solve_smem_kernel(const double* __restrict__ x,
-                                                                const double* __restrict__ y,
-                                                                const double* __restrict__ fac,
-                                                                double* __restrict__ M, long long n) {
+// One CTA per signal; D ping-pongs between two buffers of m doubles: shared memory when it fits (`in_smem`), else the
+// global scratch `dbuf` [rows][2][m].  y, M: [rows][n].
+__global__ void __launch_bounds__(512) spline_pcr_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
+                                                               const double* __restrict__ tab, double* __restrict__ M,
+                                                               double* __restrict__ dbuf, long long n, int in_smem) {
     extern __shared__ double sp[];
-    const int m = (int)(n - 2);
-    double* A = sp;
-    double* B = sp + m;
-    double* CP = sp + 2 * m;
-    const double* cp = fac;
-    const double* inv = fac + m;
-    const double* low = fac + 2 * m;
-    const double* ih = fac + 3 * m;
+    const long long m = n - 2;
+    const int L = pcr_levels(m);
+    const double* ib0 = tab;
+    const double* ih = tab + m;
+    const double* lev = ih + (n - 1);
     const double* yr = y + (long long)blockIdx.x * n;
     double* Mr = M + (long long)blockIdx.x * n;
-    for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    double* cur = in_smem ? sp : dbuf + (long long)blockIdx.x * 2 * m;
+    double* nxt = cur + m;
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) {
         const double y0 = yr[i], y1 = yr[i + 1], y2 = yr[i + 2];
-        const double rhs = 6.0 * ((y2 - y1) * ih[i + 1] - (y1 - y0) * ih[i]);
-        const double r = inv[i];
-        A[i] = rhs * r;
-        B[i] = low[i] * r;
-        CP[i] = cp[i];
+        cur[i] = 6.0 * ((y2 - y1) * ih[i + 1] - (y1 - y0) * ih[i]) * ib0[i];
+    }
+    for (int l = 0; l < L; ++l) {
+        __syncthreads();
+        const long long s = 1LL << l;
+        const double* A = lev + 3LL * l * m;
+        const double* C = A + m;
+        const double* ib = C + m;
+        for (long long i = threadIdx.x; i < m; i += blockDim.x) {
+            double d = cur[i];
+            if (i - s >= 0) d = fma(-A[i], cur[i - s], d);
+            if (i + s < m) d = fma(-C[i], cur[i + s], d);
+            nxt[i] = d * ib[i];
+        }
+        double* t = cur;
+        cur = nxt;
+        nxt = t;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        // software-pipelined in batches of 8: the loads of the next batch are issued before the
-        // dependent FMA chain of the current one, so the chain never waits for shared memory
-        constexpr int W = 8;
-        double d = 0.0;
-        {
-            double a[W], b[W], an[W], bn[W];
-            int i = 0;
-            if (m >= W) {
-#pragma unroll
-                for (int k = 0; k < W; ++k) { a[k] = A[k]; b[k] = B[k]; }
-            }
-            for (; i + W <= m; i += W) {
-                const bool more = i + 2 * W <= m;
-                if (more) {
-#pragma unroll
-                    for (int k = 0; k < W; ++k) { an[k] = A[i + W + k]; bn[k] = B[i + W + k]; }
-                }
-#pragma unroll
-                for (int k = 0; k < W; ++k) { d = fma(-b[k], d, a[k]); a[k] = d; }
-#pragma unroll
-                for (int k = 0; k < W; ++k) A[i + k] = a[k];
-#pragma unroll
-                for (int k = 0; k < W; ++k) { a[k] = an[k]; b[k] = bn[k]; }
-            }
-            for (; i < m; ++i) {
-                d = fma(-B[i], d, A[i]);
-                A[i] = d;
-            }
-        }
-        double next = d;                        // M_{n-2} = d_{m-1}; A[i] becomes M_{i+1}
-        {
-            double a[W], c[W], an[W], cn[W];
-            int i = m - 2;                      // next index to process, going down
-            if (i - (W - 1) >= 0) {
-#pragma unroll
-                for (int k = 0; k < W; ++k) { a[k] = A[i - k]; c[k] = CP[i - k]; }
-            }
-            for (; i - (W - 1) >= 0; i -= W) {
-                const bool more = i - (2 * W - 1) >= 0;
-                if (more) {
-#pragma unroll
-                    for (int k = 0; k < W; ++k) { an[k] = A[i - W - k]; cn[k] = CP[i - W - k]; }
-                }
-#pragma unroll
-                for (int k = 0; k < W; ++k) { next = fma(-c[k], next, a[k]); a[k] = next; }
-#pragma unroll
-                for (int k = 0; k < W; ++k) A[i - k] = a[k];
-#pragma unroll
-                for (int k = 0; k < W; ++k) { a[k] = an[k]; c[k] = cn[k]; }
-            }
-            for (; i >= 0; --i) {
-                next = fma(-CP[i], next, A[i]);
-                A[i] = next;
-            }
-        }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < m; i += blockDim.x) Mr[i + 1] = A[i];
+    for (long long i = threadIdx.x; i < m; i += blockDim.x) Mr[i + 1] = cur[i];
     if (threadIdx.x == 0) {
         const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
         const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
-        Mr[0] = (1.0 + q0) * A[0] - q0 * A[1];
-        Mr[n - 1] = (1.0 + q1) * A[m - 1] - q1 * A[m - 2];
+        const double m1 = cur[0], m2 = m > 1 ? cur[1] : cur[0];
+        const double ml = cur[m - 1], mk = m > 1 ? cur[m - 2] : cur[m - 1];
+        Mr[0] = (1.0 + q0) * m1 - q0 * m2;
+        Mr[n - 1] = (1.0 + q1) * ml - q1 * mk;
     }
-}
-
-// Fallback for axes too long for shared memory: one thread per signal, dp in global scratch
-// [m][rows] (thread-contiguous).
-__global__ void spline_solve_kernel(const double* __restrict__ x, const double* __restrict__ y,
-                                    const double* __restrict__ fac, double* __restrict__ M, double* __restrict__ dp,
-                                    long long rows, long long n) {
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= rows) return;
-    const long long m = n - 2;
-    const double* cp = fac;
-    const double* inv = fac + m;
-    const double* low = fac + 2 * m;
-    const double* ih = fac + 3 * m;
-    const double* yr = y + r * n;
-    double* Mr = M + r * n;
-    double dprev = 0.0;
-    double s_lo = (yr[1] - yr[0]) * ih[0];      // slope of the interval left of node i + 1
-#pragma unroll 8
-    for (long long i = 0; i < m; ++i) {
-        const double s_hi = (yr[i + 2] - yr[i + 1]) * ih[i + 1];
-        const double rhs = 6.0 * (s_hi - s_lo);
-        s_lo = s_hi;
-        const double rr = inv[i];
-        dprev = fma(-(low[i] * rr), dprev, rhs * rr);
-        dp[i * rows + r] = dprev;
-    }
-    double next = dprev;                        // M_{n-2}
-    Mr[m] = next;
-#pragma unroll 8
-    for (long long i = m - 2; i >= 0; --i) {
-        next = fma(-cp[i], next, dp[i * rows + r]);
-        Mr[i + 1] = next;
-    }
-    const double q0 = (x[1] - x[0]) / (x[2] - x[1]);
-    const double q1 = (x[n - 1] - x[n - 2]) / (x[n - 2] - x[n - 3]);
-    Mr[0] = (1.0 + q0) * Mr[1] - q0 * Mr[2];
-    Mr[n - 1] = (1.0 + q1) * Mr[n - 2] - q1 * Mr[n - 3];
 }
 
 __global__ void spline_eval_kernel(const double* __restrict__ x, const double* __restrict__ y,
@@ -347,28 +296,32 @@ extern "C" int sshg_spline_resample(sshg_ctx* ctx, const double* x, const double
 // Second derivatives + evaluation, all pointers on the device; *dflag is set when a query is out of range.
 int sshg_spline_device(sshg_ctx* ctx, const double* dx, const double* dy, int64_t rows, int64_t n, const double* dq,
                        int64_t nq, double* dout, int* dflag, uint64_t axis_hash) {
-    void *dM, *ddp, *dfac;
+    void *dM, *dtab;
+    const long long m = n - 2;
     if (int rc = sshg_scratch(ctx, 13, (size_t)rows * n * 8, &dM)) return rc;
-    if (int rc = sshg_scratch(ctx, 14, (size_t)rows * n * 8, &ddp)) return rc;
-    if (int rc = sshg_scratch(ctx, SCR_SPLFAC, (size_t)(4 * n) * 8, &dfac)) return rc;
+    if (int rc = sshg_scratch(ctx, SCR_SPLTAB, (size_t)pcr_tab_doubles(n) * 8, &dtab)) return rc;
     SSHG_CUDA(cudaMemsetAsync(dflag, 0, 4, ctx->stream));
-    // the factorisation is reused while the same axis (same host bytes) keeps coming
-    if (!(axis_hash != 0 && ctx->spl_hash == axis_hash && ctx->spl_n == n && ctx->spl_ptr == dfac)) {
-        spline_factor_kernel<<<1, 32, 0, ctx->stream>>>(dx, (double*)dfac, n);
+    // the coefficient tables are reused while the same axis (same host bytes) keeps coming
+    if (!(axis_hash != 0 && ctx->spl_hash == axis_hash && ctx->spl_n == n && ctx->spl_ptr == dtab)) {
+        spline_pcr_factor_kernel<<<1, 1024, 0, ctx->stream>>>(dx, (double*)dtab, n);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         ctx->spl_hash = axis_hash;
         ctx->spl_n = n;
-        ctx->spl_ptr = dfac;
+        ctx->spl_ptr = dtab;
     }
-    const size_t solve_smem = (size_t)3 * (n - 2) * 8;
-    if (solve_smem <= 200 * 1024 && rows < (1LL << 31)) {
-        SSHG_CUDA(cudaFuncSetAttribute(spline_solve_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        spline_solve_smem_kernel<<<(unsigned)rows, 128, solve_smem, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM, n);
+    SSHG_REQUIRE(rows < (1LL << 31), "sshg_spline_resample: too many rows");
+    const size_t solve_smem = (size_t)2 * m * 8;
+    void* dbuf = nullptr;
+    const int in_smem = solve_smem <= 200 * 1024;
+    if (in_smem) {
+        SSHG_CUDA(cudaFuncSetAttribute(spline_pcr_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     } else {
-        spline_solve_kernel<<<(unsigned)((rows + 31) / 32), 32, 0, ctx->stream>>>(dx, dy, (const double*)dfac, (double*)dM,
-                                                                                (double*)ddp, rows, n);
+        if (int rc = sshg_scratch(ctx, 14, (size_t)rows * 2 * m * 8, &dbuf)) return rc;
     }
+    spline_pcr_solve_kernel<<<(unsigned)rows, 512, in_smem ? solve_smem : 0, ctx->stream>>>(dx, dy, (const double*)dtab,
+                                                                                          (double*)dM, (double*)dbuf, n,
+                                                                                          in_smem);
     SSHG_CUDA(cudaGetLastError());
     const long long total = (long long)rows * nq;
     spline_eval_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(dx, dy, (const double*)dM, rows, n, dq,

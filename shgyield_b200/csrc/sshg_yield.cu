@@ -446,6 +446,15 @@ __global__ void __launch_bounds__(128) yield_points_kernel(const PointArgs a) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n) return;
     const long long e = a.eidx[i], nE = a.nE;
+    if (e < 0 || e >= nE) {                     // device-resident index lists are not validated on the host
+        const double bad = nan("");
+#pragma unroll
+        for (int pol = 0; pol < 4; ++pol) {
+            if (AMP) reinterpret_cast<double2*>(a.out)[pol * a.n + i] = make_double2(bad, bad);
+            else a.out[pol * a.n + i] = bad;
+        }
+        return;
+    }
     const double to_rad = a.ph.radians ? 1.0 : (3.141592653589793 / 180.0);
     double st, ct;
     sincos(a.theta_deg[i] * to_rad, &st, &ct);
@@ -864,4 +873,187 @@ extern "C" int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* ou
 
 extern "C" int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where) {
     return points_impl(ctx, p, out, where, true);
+}
+
+// ---- the tail of shgyield() for small broadcasts: yields of a point list + broad(., sigma_out) along every axis --------
+// (reference shg.py:428-436; the interactive call shapes of gui.py:286-330).  With resident spectra the call is one
+// upload of the packed point arrays from page-locked memory, the yield kernel, one FIR pass per axis and one download,
+// recorded as a CUDA graph the first time a (shape, sigma_out, physics, spectra) combination is seen and replayed after.
+namespace {
+
+int grow_pinned(sshg_ctx* ctx, void** buf, size_t* have, size_t bytes) {
+    if (*have >= bytes) return SSHG_OK;
+    if (*buf) {
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+        SSHG_CUDA(cudaFreeHost(*buf));
+        *buf = nullptr;
+        *have = 0;
+    }
+    size_t cap = bytes < 65536 ? 65536 : bytes + bytes / 2;
+    cudaError_t e = cudaMallocHost(buf, cap);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        sshg_set_error("pinned host allocation of %zu bytes failed: %s", cap, cudaGetErrorString(e));
+        return SSHG_ENOMEM;
+    }
+    *have = cap;
+    ctx->epoch++;
+    return SSHG_OK;
+}
+
+// the device part: everything between the upload of the point arrays and the download of the result
+int small_call_enqueue(sshg_ctx* ctx, const PointArgs& a, double sigma_out, int ndim, const int64_t* shape, double* d_y,
+                       double* d_out, int* n_launches) {
+    const size_t n = (size_t)a.n;
+    PointArgs k = a;
+    const bool blur = sigma_out > 1e-15 && ndim > 0;
+    k.out = blur ? d_y : d_out;
+    yield_points_kernel<false><<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(k);
+    SSHG_CUDA(cudaGetLastError());
+    ctx->launches++;
+    *n_launches = 1;
+    if (blur) {
+        int64_t full[9];
+        full[0] = 4;
+        for (int j = 0; j < ndim; ++j) full[1 + j] = shape[j];
+        const int64_t before = ctx->launches;
+        if (int rc = sshg_gauss_nd_device(ctx, d_y, d_out, 1, ndim + 1, full, sigma_out)) return rc;
+        *n_launches += (int)(ctx->launches - before);
+    }
+    return SSHG_OK;
+}
+
+}  // namespace
+
+extern "C" int sshg_yield_points_broadened(sshg_ctx* ctx, const sshg_points* p, double sigma_out, int32_t ndim,
+                                           const int64_t* shape, double* out, int where) {
+    SSHG_TRACE("sshg_yield_points_broadened");
+    SSHG_REQUIRE(ctx && p && out && (shape || ndim == 0), "sshg_yield_points_broadened: null argument");
+    SSHG_REQUIRE(p->n > 0 && p->nE > 0, "sshg_yield_points_broadened: n and nE must be positive");
+    SSHG_REQUIRE(ndim >= 0 && ndim <= 8, "sshg_yield_points_broadened: ndim must be in 0 .. 8 (got %d)", (int)ndim);
+    SSHG_REQUIRE(sigma_out >= 0.0 && isfinite(sigma_out), "sshg_yield_points_broadened: sigma_out must be finite and >= 0 (got %g)",
+                 sigma_out);
+    SSHG_REQUIRE(where == SSHG_HOST || where == SSHG_SPECTRA_DEVICE || where == SSHG_DEVICE,
+                 "sshg_yield_points_broadened: where must be SSHG_HOST, SSHG_SPECTRA_DEVICE or SSHG_DEVICE");
+    int64_t prod = 1;
+    for (int j = 0; j < ndim; ++j) {
+        SSHG_REQUIRE(shape[j] > 0, "sshg_yield_points_broadened: extents must be positive");
+        prod *= shape[j];
+    }
+    SSHG_REQUIRE(prod == p->n, "sshg_yield_points_broadened: prod(shape) = %lld but n = %lld", (long long)prod, (long long)p->n);
+    SSHG_REQUIRE(p->energy_eV && p->eidx && p->theta_deg && p->phi_deg && p->thick_nm && p->eps1w && p->eps2w && p->chi2,
+                 "sshg_yield_points_broadened: null input array");
+    if (int rc = check_physics(p->phys)) return rc;
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)p->n, nE = (size_t)p->nE;
+    const bool all_dev = where == SSHG_DEVICE, spectra_dev = all_dev || where == SSHG_SPECTRA_DEVICE;
+
+    PointArgs a{};
+    a.n = p->n;
+    a.nE = p->nE;
+    a.ph = make_physics(p->phys);
+    const void* d;
+    if (int rc = sshg_stage_in(ctx, 0, p->eps1w, 3 * nE * 16, spectra_dev, &d)) return rc;
+    a.eps1w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 1, p->eps2w, 3 * nE * 16, spectra_dev, &d)) return rc;
+    a.eps2w = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 2, p->chi2, SSHG_NCHI * nE * 16, spectra_dev, &d)) return rc;
+    a.chi = (const double2*)d;
+    if (int rc = sshg_stage_in(ctx, 3, p->energy_eV, nE * 8, spectra_dev, &d)) return rc;
+    a.energy = (const double*)d;
+    SSHG_REQUIRE(((uintptr_t)a.eps1w | (uintptr_t)a.eps2w | (uintptr_t)a.chi) % 16 == 0,
+                 "sshg_yield_points_broadened: complex device arrays must be 16-byte aligned");
+
+    void *d_y = nullptr, *d_out = out;
+    if (int rc = sshg_scratch(ctx, SCR_PTS_Y, 4 * n * 8, &d_y)) return rc;
+    if (all_dev) {                              // everything resident: queue and return
+        a.theta_deg = p->theta_deg; a.phi_deg = p->phi_deg; a.thick_nm = p->thick_nm; a.eidx = (const long long*)p->eidx;
+        int nl;
+        return small_call_enqueue(ctx, a, sigma_out, ndim, shape, (double*)d_y, out, &nl);
+    }
+    for (size_t i = 0; i < n; ++i)
+        SSHG_REQUIRE(p->eidx[i] >= 0 && p->eidx[i] < p->nE, "sshg_yield_points_broadened: eidx[%zu] = %lld out of range", i,
+                     (long long)p->eidx[i]);
+
+    // point arrays: theta | phi | thick | eidx packed in page-locked memory, ONE upload; result through page-locked memory
+    void* d_in;
+    if (int rc = sshg_scratch(ctx, SCR_PTS_IN, 4 * n * 8, &d_in)) return rc;
+    if (int rc = sshg_scratch(ctx, SCR_PTS_OUT, 4 * n * 8, &d_out)) return rc;
+    if (int rc = grow_pinned(ctx, &ctx->pin_in, &ctx->pin_in_bytes, 4 * n * 8)) return rc;
+    if (int rc = grow_pinned(ctx, &ctx->pin_out, &ctx->pin_out_bytes, 4 * n * 8)) return rc;
+    double* hin = (double*)ctx->pin_in;
+    memcpy(hin, p->theta_deg, n * 8);
+    memcpy(hin + n, p->phi_deg, n * 8);
+    memcpy(hin + 2 * n, p->thick_nm, n * 8);
+    memcpy(hin + 3 * n, p->eidx, n * 8);
+    a.theta_deg = (const double*)d_in;
+    a.phi_deg = (const double*)d_in + n;
+    a.thick_nm = (const double*)d_in + 2 * n;
+    a.eidx = (const long long*)((const double*)d_in + 3 * n);
+
+    auto enqueue_all = [&](int* nl) -> int {
+        SSHG_CUDA(cudaMemcpyAsync(d_in, ctx->pin_in, 4 * n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (int rc = small_call_enqueue(ctx, a, sigma_out, ndim, shape, (double*)d_y, (double*)d_out, nl)) return rc;
+        SSHG_CUDA(cudaMemcpyAsync(ctx->pin_out, d_out, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        return SSHG_OK;
+    };
+
+    // ---- replay, or run directly and record for the next call -------------------------------------------------
+    const bool graphable = spectra_dev && ctx->opt.graphs != 0 && n <= (1u << 16) && ctx->stream == ctx->own_stream;
+    sshg_small_key key;
+    memset(&key, 0, sizeof(key));
+    key.n = p->n; key.nE = p->nE; key.ndim = ndim;
+    for (int j = 0; j < ndim; ++j) key.shape[j] = shape[j];
+    key.sigma_out = sigma_out;
+    key.phys = p->phys;
+    key.energy = a.energy; key.eps1w = a.eps1w; key.eps2w = a.eps2w; key.chi2 = a.chi;
+    key.epoch = ctx->epoch;
+    sshg_small_graph* hit = nullptr;
+    if (graphable)
+        for (int k = 0; k < SSHG_NGRAPH; ++k)
+            if (ctx->graphs[k].exec && memcmp(&ctx->graphs[k].key, &key, sizeof(key)) == 0) hit = &ctx->graphs[k];
+    if (hit) {
+        hit->used = ++ctx->graph_clock;
+        SSHG_CUDA(cudaGraphLaunch(hit->exec, ctx->stream));
+        ctx->launches += hit->launches;
+        ctx->graph_replays++;
+    } else {
+        int nl = 0;
+        if (int rc = enqueue_all(&nl)) return rc;
+    }
+    SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(out, ctx->pin_out, 4 * n * 8);
+    if (hit || !graphable) return SSHG_OK;
+
+    // first sighting: every buffer the sequence touches now exists at its final size and the taps are resident, so the
+    // same sequence can be captured (capture executes nothing).  A failure here only means "no graph": the result is out.
+    if (key.epoch != ctx->epoch) return SSHG_OK;      // a buffer moved during the direct run; record next time
+    sshg_small_graph* slot = &ctx->graphs[0];
+    for (int k = 0; k < SSHG_NGRAPH; ++k) {
+        if (!ctx->graphs[k].exec) { slot = &ctx->graphs[k]; break; }
+        if (ctx->graphs[k].used < slot->used) slot = &ctx->graphs[k];
+    }
+    if (slot->exec) {
+        cudaGraphExecDestroy(slot->exec);
+        slot->exec = nullptr;
+    }
+    const int64_t launches_before = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess) {
+        int nl = 0;
+        const int rc = enqueue_all(&nl);
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc == SSHG_OK && e == cudaSuccess && graph && key.epoch == ctx->epoch &&
+            cudaGraphInstantiate(&slot->exec, graph, 0) == cudaSuccess) {
+            slot->key = key;
+            slot->used = ++ctx->graph_clock;
+            slot->launches = nl;
+        } else {
+            slot->exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    (void)cudaGetLastError();
+    ctx->launches = launches_before;                 // nothing ran during the capture
+    return SSHG_OK;
 }

@@ -35,15 +35,21 @@ POLS = ("pp", "ps", "sp", "ss")
 GRID_MIN_POINTS = 4096
 
 
+_CONSTANTS = None
+
+
 def physical_constants() -> dict:
     """The four constants the reference reads from scipy.constants at run time
     (reference shg.py:181,194,429-430); read from the same SciPy so results do not drift."""
-    from scipy import constants
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore")
-        return {"h_eVs": constants.value("Planck constant in eV s"),
-                "hbar_eVs": constants.value("Planck constant over 2 pi in eV s"),
-                "eps0": constants.epsilon_0, "c": constants.c}
+    global _CONSTANTS
+    if _CONSTANTS is None:
+        from scipy import constants
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            _CONSTANTS = {"h_eVs": constants.value("Planck constant in eV s"),
+                          "hbar_eVs": constants.value("Planck constant over 2 pi in eV s"),
+                          "eps0": constants.epsilon_0, "c": constants.c}
+    return dict(_CONSTANTS)
 
 
 def _physics(consts, mref=True, sinc_normalized=True, zzz_phi_quirk=True, flags=0) -> _lib.Physics:
@@ -55,21 +61,13 @@ def _physics(consts, mref=True, sinc_normalized=True, zzz_phi_quirk=True, flags=
 # ---------------------------------------------------------------------------------------------
 # K1: Gaussian broadening  (reference shg.py:26-35)
 # ---------------------------------------------------------------------------------------------
-def _gauss_axis(ctx, arr: np.ndarray, sigma: float, axis: int) -> np.ndarray:
-    """One axis of scipy.ndimage.gaussian_filter on a C-contiguous float64 array."""
+def _gauss_nd(ctx, arr: np.ndarray, sigma: float) -> np.ndarray:
+    """scipy.ndimage.gaussian_filter(arr, sigma) on a C-contiguous float64 array: every axis, one library call (the
+    array is uploaded once, filtered axis by axis on the device and copied back once)."""
     out = np.empty_like(arr)
-    n = arr.shape[axis]
-    inner = int(np.prod(arr.shape[axis + 1:], dtype=np.int64))
-    outer = int(np.prod(arr.shape[:axis], dtype=np.int64))
-    lib = ctx.lib
-    if inner == 1:
-        _lib.check(lib.sshg_gauss1d(ctx.handle, arr.ctypes.data, out.ctypes.data, outer, n, n, 1, float(sigma),
-                                    _lib.HOST), lib)
-    else:
-        blk = n * inner * arr.itemsize
-        for o in range(outer):
-            _lib.check(lib.sshg_gauss1d(ctx.handle, arr.ctypes.data + o * blk, out.ctypes.data + o * blk, inner, n,
-                                        1, inner, float(sigma), _lib.HOST), lib)
+    shape = (C.c_int64 * max(arr.ndim, 1))(*arr.shape)
+    _lib.check(ctx.lib.sshg_gauss_nd(ctx.handle, arr.ctypes.data, out.ctypes.data, arr.ndim, shape, float(sigma), _lib.HOST),
+               ctx.lib)
     return out
 
 
@@ -82,9 +80,12 @@ def broad(data, sigma):
         return arr.copy()                       # a 0-d input stays 0-d, like scipy's gaussian_filter
     arr = np.ascontiguousarray(arr)
     ctx = _lib.context()
-    for ax in range(arr.ndim):
-        arr = _gauss_axis(ctx, arr, sigma, ax)
-    return arr
+    if arr.ndim == 1:
+        out = np.empty_like(arr)
+        _lib.check(ctx.lib.sshg_gauss1d(ctx.handle, arr.ctypes.data, out.ctypes.data, 1, arr.size, arr.size, 1, sigma,
+                                        _lib.HOST), ctx.lib)
+        return out
+    return _gauss_nd(ctx, arr, sigma)
 
 
 def broadC(data, sigma):
@@ -281,55 +282,175 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
 
 
 # ---------------------------------------------------------------------------------------------
-# Optional reuse of the prepared spectra between calls.  The reference re-runs broadening, splines and
-# the rotation on every call and lists "avoid running unless changed" as a to-do (shg.py:11-12); its GUI
-# calls shgyield() twice per slider tick with the same material.  Opt-in, because a cache keyed on object
-# identity cannot see arrays that are modified in place.
+# Reuse of the prepared spectra between calls.  The reference re-runs broadening, splines and the rotation on
+# every call and lists "avoid running unless changed" as a to-do (shg.py:11-12); its GUI calls shgyield() twice
+# per slider tick with the same material (gui.py:286-330).  Here the broadened / resampled / averaged / rotated
+# spectra of the last few distinct (material CONTENT, energy values, gamma, sigma_eps, sigma_chi, mode) combinations
+# stay resident on the device.  The key is a 64-bit hash of the bytes of every array (sshg_hash64, ~10 GB/s), so an
+# array modified in place is a different key: the cache is transparent and on by default.
 # ---------------------------------------------------------------------------------------------
-_PREPARE_CACHE = None           # None: off; else an OrderedDict
+_PREPARE_CACHE = None           # OrderedDict: key -> _Prepared (created on first use); False: switched off
 _PREPARE_CACHE_SIZE = 8
 
 
 def cache_prepared(enable: bool = True, size: int = 8):
-    """Keep the broadened / resampled / averaged / rotated spectra of the last `size` distinct
-    (material objects, energy values, gamma, sigma_eps, sigma_chi, mode) combinations, so that calls
-    that only change theta / phi / thick / sigma_out / mref skip K1, the splines and the rotation.
-    The material dicts are held (by reference) while cached; arrays modified IN PLACE are not noticed
-    -- call cache_prepared(False) or pass new objects."""
+    """Switches the reuse of prepared spectra on (default) or off and sets how many distinct combinations are kept.
+    Switching drops (and frees on the device) everything that is cached."""
     global _PREPARE_CACHE, _PREPARE_CACHE_SIZE
-    from collections import OrderedDict
-    _PREPARE_CACHE = OrderedDict() if enable else None
+    if _PREPARE_CACHE:
+        for ent in _PREPARE_CACHE.values():
+            ent.release()
+    for (cid, _), pool in list(_FREE_BLOCKS.items()):
+        for ctx in list(_lib._contexts.values()):
+            if id(ctx) == cid and ctx.handle:
+                for ptr in pool:
+                    ctx.lib.sshg_device_free(ctx.handle, C.c_void_p(ptr))
+    _FREE_BLOCKS.clear()
+    _PREPARE_CACHE = None if enable else False
     _PREPARE_CACHE_SIZE = max(1, int(size))
 
 
+_FREE_BLOCKS: dict = {}         # device blocks of evicted entries, by size: a miss reuses one instead of cudaMalloc / cudaFree
+
+
+class _Prepared:
+    """eps(w), eps(2w) [3, nE] and the rotated chi2 [18, nE] of one prepared combination: host arrays plus one resident
+    device block  energy | eps1w | eps2w | chi2  (16-byte aligned parts)."""
+
+    def __init__(self, e_flat, eps1w, eps2w, chi_rot):
+        self.eps1w, self.eps2w, self.chi_rot = eps1w, eps2w, chi_rot
+        self.nE = int(e_flat.size)
+        self.ctx = None
+        self.dev = 0
+        if self.nE == 0:
+            return
+        try:
+            ctx = _lib.context()
+        except RuntimeError:
+            return
+        pad = (self.nE + 1) // 2 * 2
+        nbytes = 8 * pad + 16 * 24 * self.nE
+        pool = _FREE_BLOCKS.get((id(ctx), nbytes))
+        if pool:
+            ptr = C.c_void_p(pool.pop())
+        else:
+            ptr = C.c_void_p()
+            _lib.check(ctx.lib.sshg_device_alloc(ctx.handle, C.byref(ptr), nbytes), ctx.lib)
+        self.ctx, self.dev, self.nbytes = ctx, int(ptr.value), nbytes
+        block = np.zeros(nbytes // 8)
+        block[:self.nE] = e_flat
+        block[pad:] = np.concatenate([eps1w.ravel(), eps2w.ravel(), chi_rot.ravel()]).view(np.float64)
+        try:
+            _lib.check(ctx.lib.sshg_upload(ctx.handle, ptr, block.ctypes.data, nbytes), ctx.lib)
+        except Exception:
+            self.release()
+            raise
+        self.d_energy = self.dev
+        self.d_eps1w = self.dev + 8 * pad
+        self.d_eps2w = self.d_eps1w + 16 * 3 * self.nE
+        self.d_chi = self.d_eps2w + 16 * 3 * self.nE
+
+    def release(self, keep: bool = False):
+        """Frees the device block, or (keep) parks it for the next entry of the same size."""
+        if self.dev and self.ctx is not None and self.ctx.handle:
+            pool = _FREE_BLOCKS.setdefault((id(self.ctx), self.nbytes), [])
+            if keep and len(pool) < 4:
+                pool.append(self.dev)
+            else:
+                self.ctx.lib.sshg_device_free(self.ctx.handle, C.c_void_p(self.dev))
+        self.dev = 0
+
+    def __del__(self):
+        try:
+            self.release(keep=True)
+        except Exception:
+            pass
+
+
+def _content_key(e_arr, mats, gamma, sigma_eps, sigma_chi, mode):
+    """Hashable key of everything _prepare() depends on, by CONTENT.  Raises TypeError for inputs it cannot key."""
+    lib = _lib.load()
+    seen = {}
+
+    def arr_key(a):
+        k = seen.get(id(a))
+        if k is None:
+            b = np.ascontiguousarray(a)
+            k = (b.dtype.str, b.shape, int(lib.sshg_hash64(b.ctypes.data, b.nbytes, 0)))
+            seen[id(a)] = k
+        return k
+
+    parts = [arr_key(e_arr), float(gamma), float(sigma_eps), float(sigma_chi), str(mode)]
+    for m in mats:
+        row = []
+        for name, v in m.items():
+            if isinstance(v, dict):
+                row.append((name, arr_key(v["energy"]), arr_key(v["data"])))
+            elif isinstance(v, np.ndarray):
+                row.append((name, arr_key(v)))
+            else:
+                row.append((name, complex(v)))
+        parts.append(tuple(row))
+    return tuple(parts)
+
+
 def _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode):
-    if _PREPARE_CACHE is None:
-        return _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode)
-    try:
-        key = (id(eps_m1), id(eps_m2), id(eps_m3), id(chi2), e_arr.shape, e_arr.tobytes(), float(gamma),
-               float(sigma_eps), float(sigma_chi), str(mode))
-    except (TypeError, ValueError):
-        return _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode)
-    hit = _PREPARE_CACHE.get(key)
-    if hit is None:
-        eps1w, eps2w, chi_rot, thick_eff = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
-                                                    sigma_chi, mode)
-        # the references keep the ids in the key alive and unique
-        _PREPARE_CACHE[key] = (eps1w, eps2w, chi_rot, (eps_m1, eps_m2, eps_m3, chi2))
+    """(_Prepared, effective thick) for this call; prepared spectra are reused by content (see above)."""
+    global _PREPARE_CACHE
+    key = None
+    if _PREPARE_CACHE is not False:
+        try:
+            key = _content_key(e_arr, (eps_m1, eps_m2, eps_m3, chi2), gamma, sigma_eps, sigma_chi, mode)
+        except (TypeError, ValueError, KeyError, AttributeError):
+            key = None                          # unusual inputs: prepare afresh (and fail exactly like the reference)
+    if key is not None:
+        if _PREPARE_CACHE is None:
+            from collections import OrderedDict
+            _PREPARE_CACHE = OrderedDict()
+        hit = _PREPARE_CACHE.get(key)
+        if hit is not None:
+            _PREPARE_CACHE.move_to_end(key)
+            if mode in ("fresnel", "2-layer"):
+                thick = 0                       # reference shg.py:414
+            return hit, thick
+    eps1w, eps2w, chi_rot, thick_eff = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi,
+                                                mode)
+    ent = _Prepared(e_arr.ravel(), eps1w, eps2w, chi_rot)
+    if key is not None:
+        _PREPARE_CACHE[key] = ent
         while len(_PREPARE_CACHE) > _PREPARE_CACHE_SIZE:
-            _PREPARE_CACHE.popitem(last=False)
-        return eps1w, eps2w, chi_rot, thick_eff
-    _PREPARE_CACHE.move_to_end(key)
-    eps1w, eps2w, chi_rot, _ = hit
-    if mode in ("fresnel", "2-layer"):
-        thick = 0                                   # reference shg.py:414
-    return eps1w, eps2w, chi_rot, thick
+            _PREPARE_CACHE.popitem(last=False)[1].release(keep=True)
+    return ent, thick_eff
 
 
 def _axes_of(shape, ndim):
     """Axes (in the ndim-dimensional broadcast result) along which an operand of `shape` varies."""
     pad = (1,) * (ndim - len(shape)) + tuple(shape)
     return tuple(i for i, s in enumerate(pad) if s != 1)
+
+
+def _points_tail(prep, e_arr, t_arr, p_arr, d_arr, shape, n, sigma_out, mref, consts):
+    """Yields of the flattened broadcast + broad(., sigma_out) along every axis in ONE library call
+    (sshg_yield_points_broadened; resident spectra, packed upload, CUDA-graph replay).  Returns [4, n]."""
+    ctx = _lib.context()
+    eidx = np.ascontiguousarray(np.broadcast_to(np.arange(e_arr.size, dtype=np.int64).reshape(e_arr.shape), shape)).ravel()
+    bc = lambda a: np.ascontiguousarray(np.broadcast_to(a, shape), dtype=np.float64).ravel()
+    th, ph, dd = bc(t_arr), bc(p_arr), bc(d_arr)
+    out = np.empty((4, n))
+    if prep.dev:
+        where = _lib.SPECTRA_DEVICE
+        en, e1, e2, ch = prep.d_energy, prep.d_eps1w, prep.d_eps2w, prep.d_chi
+    else:
+        where = _lib.HOST
+        e_flat = np.ascontiguousarray(e_arr, dtype=np.float64).ravel()
+        en, e1, e2, ch = e_flat.ctypes.data, prep.eps1w.ctypes.data, prep.eps2w.ctypes.data, prep.chi_rot.ctypes.data
+    p = _lib.Points(n=n, nE=e_arr.size, energy_eV=en, eidx=eidx.ctypes.data, theta_deg=th.ctypes.data,
+                    phi_deg=ph.ctypes.data, thick_nm=dd.ctypes.data, eps1w=e1, eps2w=e2, chi2=ch,
+                    phys=_physics(consts, mref))
+    shp = (C.c_int64 * max(len(shape), 1))(*shape)
+    _lib.check(ctx.lib.sshg_yield_points_broadened(ctx.handle, C.byref(p), float(sigma_out), len(shape), shp,
+                                                   out.ctypes.data, where), ctx.lib)
+    return out
 
 
 def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0, sigma_chi=0.0,
@@ -342,8 +463,7 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     """
     consts = physical_constants()
     e_arr = np.asarray(energy, dtype=np.float64)
-    eps1w, eps2w, chi_rot, thick = _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps,
-                                                   sigma_chi, mode)
+    prep, thick = _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode)
     if not mref:
         thick = 0.0               # the reference never touches `thick` without multiple reflections (shg.py:179, 192),
                                   # so its shape does not enter the broadcast of the result either
@@ -351,14 +471,15 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     shape = np.broadcast_shapes(e_arr.shape, t_arr.shape, p_arr.shape, d_arr.shape)
     ndim = len(shape)
     n = int(np.prod(shape, dtype=np.int64))
-    res = None
+    sigma_out = float(sigma_out)
+    stack = None
     if n >= GRID_MIN_POINTS:
         ax = [_axes_of(a.shape, ndim) for a in (t_arr, d_arr, p_arr, e_arr)]       # cube order T, D, P, E
         flat = [a for axes in ax for a in axes]
         if len(set(flat)) == len(flat):                                             # outer-product structure
             from .grid import yield_grid_host
-            cube = yield_grid_host(e_arr.ravel(), t_arr.ravel(), p_arr.ravel(), d_arr.ravel(), eps1w, eps2w, chi_rot,
-                                   mref=mref, consts=consts)                       # [T, D, 4, P, E]
+            cube = yield_grid_host(e_arr.ravel(), t_arr.ravel(), p_arr.ravel(), d_arr.ravel(), prep.eps1w, prep.eps2w,
+                                   prep.chi_rot, mref=mref, consts=consts)          # [T, D, 4, P, E]
             missing = [i for i in range(ndim) if i not in flat]                     # axes of extent 1
             order = flat + missing
             blocks = [tuple(shape[i] for i in axes) for axes in ax]
@@ -366,22 +487,22 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
             for k in range(4):
                 r = cube[:, :, k].reshape(sum(blocks, ()) + (1,) * len(missing))
                 res.append(np.ascontiguousarray(np.transpose(r, np.argsort(order))).reshape(shape))
-    if res is None:
-        if n:
+            stack = np.ascontiguousarray(np.stack(res))                             # [4, *shape]
+            # output broadening (reference shg.py:433-436): scalar sigma blurs every axis, like scipy's gaussian_filter
+            if sigma_out > 1e-15 and ndim:
+                ctx = _lib.context()
+                stack = np.stack([_gauss_nd(ctx, np.ascontiguousarray(stack[k]), sigma_out) for k in range(4)])
+    if stack is None:
+        if n and ndim <= 8:
+            stack = _points_tail(prep, e_arr, t_arr, p_arr, d_arr, shape, n, sigma_out, mref, consts).reshape((4,) + shape)
+        elif n:                                     # more than 8 broadcast axes: yields, then the filter
             eidx = np.broadcast_to(np.arange(e_arr.size, dtype=np.int64).reshape(e_arr.shape), shape).ravel()
             bc = lambda a: np.broadcast_to(a, shape).ravel()
-            y = yield_points(e_arr.ravel(), eidx, bc(t_arr), bc(p_arr), bc(d_arr), eps1w, eps2w, chi_rot, mref=mref,
-                             consts=consts)
+            y = yield_points(e_arr.ravel(), eidx, bc(t_arr), bc(p_arr), bc(d_arr), prep.eps1w, prep.eps2w, prep.chi_rot,
+                             mref=mref, consts=consts)
+            stack = np.stack([broad(y[k].reshape(shape), sigma_out) for k in range(4)])
         else:
-            y = np.empty((4, 0))
-        res = [y[k].reshape(shape) for k in range(4)]
-    # output broadening (reference shg.py:433-436): the four arrays are filtered together, one K1 launch
-    # per axis of the result (scalar sigma blurs every axis, like scipy's gaussian_filter)
-    stack = np.ascontiguousarray(np.stack([np.asarray(r, dtype=np.float64) for r in res]))       # [4, *shape]
-    if float(sigma_out) > 1e-15 and stack.ndim > 1 and stack.size:
-        ctx = _lib.context()
-        for ax in range(1, stack.ndim):
-            stack = _gauss_axis(ctx, stack, float(sigma_out), ax)
+            stack = np.empty((4,) + shape)
     out = {"energy": energy, "phi": phi}
     for k, pol in enumerate(POLS):
         out[pol] = np.array(stack[k])             # own array per polarisation (0-d stays a 0-d ndarray)

@@ -79,3 +79,42 @@ def test_library_reads_no_environment():
     csrc = os.path.join(util.REPO, "shgyield_b200", "csrc")
     for f in os.listdir(csrc):
         assert "getenv" not in open(os.path.join(csrc, f)).read(), f
+
+
+def test_content_hash(lib):
+    """sshg_hash64 (the key of the prepared-spectra cache): deterministic, sensitive to every byte and to the length,
+    fine with unaligned tails; ~GB/s so that hashing a material costs tens of microseconds."""
+    import time
+    rng = np.random.default_rng(0)
+    buf = rng.integers(0, 256, 100003, dtype=np.uint8)
+    h = lambda a, n=None, seed=0: int(lib.sshg_hash64(a.ctypes.data, a.nbytes if n is None else n, seed))
+    base = h(buf)
+    assert base == h(buf.copy()) and base != h(buf, seed=1)
+    seen = {base}
+    for pos in (0, 1, 31, 32, 33, 50000, 100002):
+        mod = buf.copy()
+        mod[pos] ^= 1
+        seen.add(h(mod))
+    for n in (0, 1, 7, 8, 31, 32, 33, 100002):
+        seen.add(h(buf, n))
+    assert len(seen) == 1 + 7 + 8
+    big = np.zeros(1 << 22, dtype=np.float64)
+    t0 = time.perf_counter()
+    h(big)
+    assert big.nbytes / (time.perf_counter() - t0) > 1e9
+
+
+def test_content_key_of_the_prepared_cache(lib):
+    """The cache key sees values, not object identity: equal copies give the same key, an in-place change another."""
+    from shgyield_b200 import shg
+    e = np.linspace(0, 20, 2001)
+    mk = lambda: {"xx": {"energy": e.copy(), "data": np.cos(e) + 1j * np.sin(e)}, "yy": 2.5, "zz": np.full(5, 1.0 + 2j)}
+    m, chi = mk(), {"xxx": {"energy": e, "data": e * 1j}, "zzz": 0}
+    key = lambda mm: shg._content_key(np.linspace(1, 2, 11), (mm, mm, mm, chi), 90, 0.0, 0.0, "3-layer")
+    k0 = key(m)
+    assert key(mk()) == k0
+    m["xx"]["data"][100] += 1e-12
+    assert key(m) != k0
+    assert shg._content_key(np.linspace(1, 2, 11), (mk(), mk(), mk(), chi), 90, 0.0, 0.5, "3-layer") != k0
+    with pytest.raises(TypeError):
+        shg._content_key(np.linspace(1, 2, 11), ({"xx": None},), 90, 0.0, 0.0, "3-layer")

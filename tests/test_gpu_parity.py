@@ -435,20 +435,26 @@ def test_config5_full_theta_rows_vs_oracle(grid, consts):
 
 
 def test_prepared_cache_is_transparent(shg, spectra):
-    """cache_prepared(): same results bit for bit, a hit when only angles / thickness / sigma_out change,
-    a miss when sigma_eps, gamma, the energies or the material objects change."""
+    """The reuse of prepared spectra (on by default, keyed on CONTENT): same results bit for bit as without it, a hit
+    when only angles / thickness / sigma_out change or when an equal copy of the material comes in, a miss when
+    sigma_eps, gamma, the energies or the VALUES of a spectrum change -- including a change made in place."""
+    from shgyield_b200 import _lib
     m1, m2, m3, chi2 = cases.full_tensor_material(spectra)
+    chi2 = {k: ({"energy": v["energy"], "data": v["data"].copy()} if isinstance(v, dict) else v) for k, v in chi2.items()}
     kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, thick=10, gamma=25, sigma_eps=2.0, sigma_chi=1.0)
+    polar_phi = np.arange(0.0, 360.0, 45.0).reshape(8, 1)
+    ctx = _lib.context()
+    shg.cache_prepared(False)
     base = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)
-    other = shg.shgyield(cases.E_C1, theta=40, phi=np.arange(0.0, 360.0, 45.0).reshape(8, 1), sigma_out=0.0, **kw)
-    ctx_launches = lambda: __import__("shgyield_b200._lib", fromlist=["x"]).context().launches
+    other = shg.shgyield(cases.E_C1, theta=40, phi=polar_phi, sigma_out=0.0, **kw)
+    f0 = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
     shg.cache_prepared(True)
     try:
         a = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)            # miss: fills the cache
-        n0 = ctx_launches()
+        n0 = ctx.launches
         b = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)            # hit
-        n1 = ctx_launches()
-        c = shg.shgyield(cases.E_C1, theta=40, phi=np.arange(0.0, 360.0, 45.0).reshape(8, 1), sigma_out=0.0, **kw)
+        n1 = ctx.launches
+        c = shg.shgyield(cases.E_C1, theta=40, phi=polar_phi, sigma_out=0.0, **kw)
         assert n1 - n0 == 2                                                          # yield kernel + output FIR only
         for pol in cases.POLS:
             assert np.array_equal(a[pol], base[pol]) and np.array_equal(b[pol], base[pol])
@@ -457,14 +463,69 @@ def test_prepared_cache_is_transparent(shg, spectra):
         shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, sigma_eps=3.0))
         shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, gamma=26))
         shg.shgyield(cases.E_C1[:-1], theta=65, phi=30, sigma_out=5, **kw)
-        shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, chi2=dict(chi2)))
+        assert len(shg._PREPARE_CACHE) == 4
+        # an equal COPY of the material is the same content: a hit
+        copy = {k: ({"energy": v["energy"].copy(), "data": v["data"].copy()} if isinstance(v, dict) else v) for k, v in chi2.items()}
+        shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **dict(kw, chi2=copy))
+        assert len(shg._PREPARE_CACHE) == 4
+        # a spectrum modified IN PLACE must miss, and the result must be the one of the modified material
+        saved = chi2["xxx"]["data"][150:170].copy()
+        chi2["xxx"]["data"][150:170] *= 1.5
+        d = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)
         assert len(shg._PREPARE_CACHE) == 5
+        shg.cache_prepared(False)
+        d0 = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, **kw)
+        shg.cache_prepared(True)
+        assert any(not np.array_equal(d[pol], base[pol]) for pol in cases.POLS)
+        for pol in cases.POLS:
+            assert np.array_equal(d[pol], d0[pol])
+        chi2["xxx"]["data"][150:170] = saved
         f = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
         g = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
         for pol in cases.POLS:
-            assert np.array_equal(f[pol], g[pol])
+            assert np.array_equal(f[pol], g[pol]) and np.array_equal(f[pol], f0[pol])
     finally:
-        shg.cache_prepared(False)
-    f0 = shg.shgyield(cases.E_C1, theta=65, phi=30, sigma_out=5, mode="fresnel", **kw)
+        shg.cache_prepared(True)                                                     # the default
+
+
+def test_small_calls_replay_a_graph_with_the_same_bits(shg, spectra):
+    """The reference GUI's two call shapes (gui.py:286-330: 361-phi polar plot, 126-energy spectrum with sigma_out):
+    after the first call of a shape the library replays a recorded CUDA graph; results are bit for bit those of the
+    kernel-by-kernel path (option "graphs" = 0) and match the reference-generated goldens."""
+    from shgyield_b200 import _lib
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, theta=65, thick=10, gamma=0)
+    ctx = _lib.context()
+    shapes = (dict(energy=1.7, phi=np.arange(0, 361), sigma_out=0.0), dict(energy=cases.E_C1, phi=30, sigma_out=5))
+    with ctx.options(graphs=0):
+        plain = [shg.shgyield(**s, **kw) for s in shapes]
+    first = [shg.shgyield(**s, **kw) for s in shapes]                  # runs kernel by kernel, records
+    n0 = ctx.launches
+    again = [shg.shgyield(**s, **kw) for s in shapes]                  # replays
+    assert ctx.launches - n0 == 1 + 2                                  # polar: yield kernel; spectrum: yield kernel + FIR
+    moved = shg.shgyield(energy=cases.E_C1, phi=31.5, sigma_out=5, **dict(kw, theta=40))     # same shape, new angles: replay
+    with ctx.options(graphs=0):
+        moved0 = shg.shgyield(energy=cases.E_C1, phi=31.5, sigma_out=5, **dict(kw, theta=40))
     for pol in cases.POLS:
-        assert np.array_equal(f[pol], f0[pol])
+        for a, b, c in zip(plain, first, again):
+            assert np.array_equal(a[pol], b[pol]) and np.array_equal(a[pol], c[pol])
+        assert np.array_equal(moved[pol], moved0[pol])
+    gold = np.load(os.path.join(G, "ref_api_cases.npz"))
+    for name, res in (("polar", again[0]), ("c1_d10", again[1])):
+        sc = cases.case_scale(gold, name + "_")
+        for pol in cases.POLS:
+            ok, msg = cases.parity_ok(res[pol], gold[name + "_" + pol], rtol=RTOL, scale=sc)
+            assert ok, (name, pol, msg)
+
+
+def test_gauss_nd_matches_scipy(shg):
+    """broad() of an N-D array = scipy.ndimage.gaussian_filter over every axis, one library call (middle axes are
+    filtered in place on the device with outer x inner row addressing)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(12)
+    for shape, sigma in (((7, 5, 33), 1.3), ((4, 1, 9, 2), 0.8), ((3, 40), 5.0), ((2, 3, 4, 5, 6), 0.6), ((1, 1), 2.0)):
+        x = rng.normal(size=shape)
+        want = ndimage.gaussian_filter(x, sigma)
+        got = shg.broad(x, sigma)
+        assert got.shape == want.shape
+        assert np.max(np.abs(got - want)) <= 4e-15 * max(1.0, np.max(np.abs(want))), (shape, sigma)
