@@ -135,8 +135,6 @@ SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by
  * value -1 restores the library's own choice.  Keys:
  *   "k2_sparse"     0 | 1     dense / sparse-phi yield kernel                 (default: by the number of azimuths)
  *   "k2_nt"         64 | 256  CTA width of the dense yield kernel
- *   "k2_bulk"       0 | 4 | 8 dense yield kernel: per-thread stores, or runs staged in shared memory and written by the
- *                             copy engine, 4 / 8 row pairs per batch                       (default 8)
  *   "k2_recurrence" 0 | 1     phase recurrence on uniform thickness axes      (default 1)
  *   "k3"            0 | 1     output broadening fused into the yield kernel   (default 1 where it applies)
  *   "k3_nt"         64 | 128  CTA width of the fused kernel

@@ -112,7 +112,7 @@ int sshg_ctx_create(int device, sshg_ctx** out) {
     }
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1};
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
@@ -181,7 +181,6 @@ const OptionKey kOptions[] = {
     {"nseg", &sshg_options::nseg, 1, 16, -1, -1},
     {"k1_generic", &sshg_options::k1_generic, 0, 1, -1, -1},
     {"graphs", &sshg_options::graphs, 0, 1, -1, -1},
-    {"k2_bulk", &sshg_options::k2_bulk, 0, 8, -1, -1},
 };
 const OptionKey* find_option(const char* key) {
     for (const OptionKey& o : kOptions)
@@ -196,8 +195,7 @@ int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value) {
     SSHG_REQUIRE(o, "sshg_ctx_set_option: unknown option '%s'", key);
     const bool ok = value == -1 || (o->only_a >= 0 ? (value == o->only_a || value == o->only_b)
                                                    : (value >= o->lo && value <= o->hi));
-    SSHG_REQUIRE(ok && !(strcmp(key, "k2_bulk") == 0 && value != -1 && value != 0 && value != 4 && value != 8),
-                 "sshg_ctx_set_option: value %lld is not allowed for '%s'", (long long)value, key);
+    SSHG_REQUIRE(ok, "sshg_ctx_set_option: value %lld is not allowed for '%s'", (long long)value, key);
     ctx->opt.*(o->field) = (int)value;
     return SSHG_OK;
 }

@@ -39,7 +39,6 @@ struct sshg_options {
     int nseg;           // phi segments per column (1 .. 16)
     int k1_generic;     // 1: never use the fixed-radius FIR kernels
     int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
-    int k2_bulk;        // 0 / 4 / 8: dense yield kernel with per-thread stores / bulk stores of 4 / 8 row pairs per batch
 };
 
 // A recorded small call: copy in -> yield_points_kernel -> FIR passes -> copy out, keyed on everything the recorded

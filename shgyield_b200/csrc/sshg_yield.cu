@@ -34,9 +34,6 @@ constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
 #ifndef SSHG_NSEG_WAVES
 #define SSHG_NSEG_WAVES 7.0
 #endif
-#ifndef SSHG_K2_BULK_DEFAULT
-#define SSHG_K2_BULK_DEFAULT 8
-#endif
 
 struct YieldArgs {
     const double2* eps1w;      // [3][nE]
@@ -299,244 +296,6 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
     }
 }
 
-
-// ---- K2 with bulk stores -----------------------------------------------------------------------------------------
-// The same kernel for store-dominated sweeps, with the stores taken off the threads: a warp stages its 512-byte run of
-// B consecutive (phi, phi + 180 deg) row pairs in shared memory (STS.128) and ONE lane hands the 2 B runs to the
-// asynchronous copy engine (cp.async.bulk shared -> global, one commit group per batch, two batches in flight).  On
-// K2's address pattern -- rows 160 KB apart -- that lifts the ceiling from 6.2 TB/s (per-thread st.global.cs.v2.f64)
-// to the 6.85 TB/s of a purely sequential store stream (profiles/r02_store_experiments.txt), because the memory system
-// sees whole runs arriving together instead of 16-byte pieces at the pace of each warp's arithmetic.  There is no
-// CTA-wide barrier: the phi table is read through L1 (17 KB, shared by all CTAs of the SM), polarisation-outer, so the
-// coefficients are assembled once per polarisation instead of once per table chunk.
-__device__ __forceinline__ void bulk_store_s2g(void* gdst, const void* ssrc, unsigned bytes) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-constexpr int WRUN = 64;                        // doubles per staged run: the 2 x 32 energies of a warp (512 B)
-
-// One warp's staging area: two slots of ROWS runs.
-template <int ROWS>
-struct WarpStage {
-    double* buf;                                // [2][ROWS][WRUN]
-    int slot, lane;
-    unsigned bytes;                             // valid bytes of a run (ragged end of the energy axis)
-    __device__ __forceinline__ void begin() {   // the slot about to be written has been read out by the copy engine
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-    }
-    __device__ __forceinline__ void put(int r, double y0, double y1) {
-        *reinterpret_cast<double2*>(buf + (slot * ROWS + r) * WRUN + lane * 2) = make_double2(y0, y1);
-    }
-    __device__ __forceinline__ void publish() { // generic-proxy writes -> visible to the async proxy, whole warp done
-        fence_proxy_async();
-        __syncwarp();
-    }
-    __device__ __forceinline__ void issue(int r, double* gdst) { bulk_store_s2g(gdst, buf + (slot * ROWS + r) * WRUN, bytes); }
-    __device__ __forceinline__ void end() {
-        if (lane == 0) bulk_commit();
-        slot ^= 1;
-    }
-};
-
-__device__ __forceinline__ void load_basis(const double* __restrict__ tab, long long item, double (&b)[6]) {
-    const double2* t = reinterpret_cast<const double2*>(tab) + 3 * item;         // shared memory, broadcast to the warp
-    const double2 v0 = t[0], v1 = t[1], v2 = t[2];
-    b[0] = v0.x; b[1] = v0.y; b[2] = v1.x; b[3] = v1.y; b[4] = v2.x; b[5] = v2.y;
-}
-
-// (C) with staged runs.  plo / phi_ / psg: the WARP's first energy of the first row of each kind; item0: first table item.
-template <int B, bool SS>
-__device__ __forceinline__ void sweep_bulk(const double (&kr0)[7], const double (&ki0)[7], const double (&kr1)[7],
-                                           const double (&ki1)[7], const double* __restrict__ tab, long long item0,
-                                           int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                           long long stride, WarpStage<2 * B>& st) {
-#pragma unroll 1
-    for (int i0 = 0; i0 < n_pair; i0 += B) {
-        const int nb = min(B, n_pair - i0);
-        st.begin();
-#pragma unroll 2
-        for (int i = 0; i < nb; ++i) {
-            double b[6];
-            load_basis(tab, item0 + i0 + i, b);
-            if (SS) {                           // odd part only: the row at phi + 180 deg equals the row at phi
-                const double r0 = fma(kr0[3], b[5], fma(kr0[2], b[4], fma(kr0[1], b[3], kr0[0] * b[2])));
-                const double j0 = fma(ki0[3], b[5], fma(ki0[2], b[4], fma(ki0[1], b[3], ki0[0] * b[2])));
-                const double r1 = fma(kr1[3], b[5], fma(kr1[2], b[4], fma(kr1[1], b[3], kr1[0] * b[2])));
-                const double j1 = fma(ki1[3], b[5], fma(ki1[2], b[4], fma(ki1[1], b[3], ki1[0] * b[2])));
-                st.put(i, fma(r0, r0, j0 * j0), fma(r1, r1, j1 * j1));
-            } else {
-                const double er0 = fma(kr0[2], b[1], fma(kr0[1], b[0], kr0[0]));
-                const double ei0 = fma(ki0[2], b[1], fma(ki0[1], b[0], ki0[0]));
-                const double or0 = fma(kr0[6], b[5], fma(kr0[5], b[4], fma(kr0[4], b[3], kr0[3] * b[2])));
-                const double oi0 = fma(ki0[6], b[5], fma(ki0[5], b[4], fma(ki0[4], b[3], ki0[3] * b[2])));
-                const double er1 = fma(kr1[2], b[1], fma(kr1[1], b[0], kr1[0]));
-                const double ei1 = fma(ki1[2], b[1], fma(ki1[1], b[0], ki1[0]));
-                const double or1 = fma(kr1[6], b[5], fma(kr1[5], b[4], fma(kr1[4], b[3], kr1[3] * b[2])));
-                const double oi1 = fma(ki1[6], b[5], fma(ki1[5], b[4], fma(ki1[4], b[3], ki1[3] * b[2])));
-                const double ar0 = er0 + or0, ai0 = ei0 + oi0, sr0 = er0 - or0, si0 = ei0 - oi0;
-                const double ar1 = er1 + or1, ai1 = ei1 + oi1, sr1 = er1 - or1, si1 = ei1 - oi1;
-                st.put(2 * i, fma(ar0, ar0, ai0 * ai0), fma(ar1, ar1, ai1 * ai1));
-                st.put(2 * i + 1, fma(sr0, sr0, si0 * si0), fma(sr1, sr1, si1 * si1));
-            }
-        }
-        st.publish();
-        if (st.lane == 0) {
-#pragma unroll 1
-            for (int i = 0; i < nb; ++i) {
-                st.issue(SS ? i : 2 * i, plo + (long long)(i0 + i) * stride);
-                st.issue(SS ? i : 2 * i + 1, phi_ + (long long)(i0 + i) * stride);
-            }
-        }
-        st.end();
-    }
-#pragma unroll 1
-    for (int i0 = 0; i0 < n_single; i0 += 2 * B) {         // the un-paired rows: one run per item
-        const int nb = min(2 * B, n_single - i0);
-        st.begin();
-#pragma unroll 2
-        for (int i = 0; i < nb; ++i) {
-            double b[6];
-            load_basis(tab, item0 + n_pair + i0 + i, b);
-            double r0, j0, r1, j1;
-            if (SS) {
-                r0 = fma(kr0[3], b[5], fma(kr0[2], b[4], fma(kr0[1], b[3], kr0[0] * b[2])));
-                j0 = fma(ki0[3], b[5], fma(ki0[2], b[4], fma(ki0[1], b[3], ki0[0] * b[2])));
-                r1 = fma(kr1[3], b[5], fma(kr1[2], b[4], fma(kr1[1], b[3], kr1[0] * b[2])));
-                j1 = fma(ki1[3], b[5], fma(ki1[2], b[4], fma(ki1[1], b[3], ki1[0] * b[2])));
-            } else {
-                r0 = fma(kr0[6], b[5], fma(kr0[5], b[4], fma(kr0[4], b[3], fma(kr0[3], b[2], fma(kr0[2], b[1], fma(kr0[1], b[0], kr0[0]))))));
-                j0 = fma(ki0[6], b[5], fma(ki0[5], b[4], fma(ki0[4], b[3], fma(ki0[3], b[2], fma(ki0[2], b[1], fma(ki0[1], b[0], ki0[0]))))));
-                r1 = fma(kr1[6], b[5], fma(kr1[5], b[4], fma(kr1[4], b[3], fma(kr1[3], b[2], fma(kr1[2], b[1], fma(kr1[1], b[0], kr1[0]))))));
-                j1 = fma(ki1[6], b[5], fma(ki1[5], b[4], fma(ki1[4], b[3], fma(ki1[3], b[2], fma(ki1[2], b[1], fma(ki1[1], b[0], ki1[0]))))));
-            }
-            st.put(i, fma(r0, r0, j0 * j0), fma(r1, r1, j1 * j1));
-        }
-        st.publish();
-        if (st.lane == 0) {
-#pragma unroll 1
-            for (int i = 0; i < nb; ++i) st.issue(i, psg + (long long)(i0 + i) * stride);
-        }
-        st.end();
-    }
-}
-
-constexpr int NT_BULK = 64;
-constexpr int BULK_TAB_ITEMS = 368;             // phi items of a CTA's segment held in shared memory (17.7 KB)
-constexpr size_t bulk_smem(int B) {
-    return (size_t)(EPT * NCOL * NT_BULK + (NT_BULK / 32) * 2 * 2 * B * WRUN + BULK_TAB_ITEMS * 6) * sizeof(double);
-}
-
-template <int B>
-__global__ void __launch_bounds__(NT_BULK, 6) yield_grid_bulk_kernel(const YieldArgs a) {
-    constexpr int NT = NT_BULK;
-    extern __shared__ __align__(128) double smem[];
-    double* cols = smem;                                   // [EPT][NCOL][NT]; every thread reads back only what it parked
-    double* tabs = smem + EPT * NCOL * NT + (NT / 32) * 2 * 2 * B * WRUN;      // [BULK_TAB_ITEMS][6]
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const long long blk = blockIdx.x;
-    const int tile = (int)(blk % a.n_tiles);
-    const int seg = (int)((blk / a.n_tiles) % a.n_seg);
-    const long long lcol = blk / a.n_tiles / a.n_seg;
-    const long long col = a.col0 + lcol;
-    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
-    const long long nE = a.nE;
-    const long long warp_e0 = ((long long)tile * NT + warp * 32) * EPT;
-    const bool warp_on = warp_e0 < nE;                      // a warp beyond the energy axis only keeps the barriers company
-    const long long e0 = warp_e0 + lane * EPT;
-    // lanes beyond the axis compute on its last energy (their part of a run is never copied out)
-    const long long ee[2] = {e0 < nE ? e0 : nE - 1, e0 + 1 < nE ? e0 + 1 : nE - 1};
-
-    // ---- (A) column setup, one energy at a time to keep register pressure down -------------
-    if (warp_on) {
-        double st, ct;
-        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
-        const double thick = a.thick_nm[a.d0 + dl];
-#pragma unroll 1
-        for (int k = 0; k < EPT; ++k) {
-            const long long e = ee[k];
-            cplx e1[3], e2[3];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                e1[m] = ldc(a.eps1w + m * nE + e);
-                e2[m] = ldc(a.eps2w + m * nE + e);
-            }
-            Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
-            double* d = cols + (k * NCOL) * NT + tid;
-            const cplx v[10] = {c.Gpp, c.Gps, c.Gsp, c.Gss, c.A, c.Bz, c.Q, c.a2, c.ab, c.b2};
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                d[(2 * j) * NT] = v[j].re;
-                d[(2 * j + 1) * NT] = v[j].im;
-            }
-        }
-    }
-    auto load_column = [&](int k) -> Column {
-        const double* d = cols + (k * NCOL) * NT + tid;
-        auto f = [&](int j) { return mk(d[(2 * j) * NT], d[(2 * j + 1) * NT]); };
-        Column c;
-        c.Gpp = f(0); c.Gps = f(1); c.Gsp = f(2); c.Gss = f(3);
-        c.A = f(4); c.Bz = f(5); c.Q = f(6);
-        c.a2 = f(7); c.ab = f(8); c.b2 = f(9);
-        return c;
-    };
-
-    WarpStage<2 * B> stg;
-    stg.buf = smem + EPT * NCOL * NT + warp * (2 * 2 * B * WRUN);
-    stg.slot = 0;
-    stg.lane = lane;
-    const long long valid = nE - warp_e0 < WRUN ? nE - warp_e0 : WRUN;
-    stg.bytes = (unsigned)((valid > 0 ? valid : 0) * 8);    // a multiple of 16: the launch requires an even nE
-
-    const long long H = (long long)a.tab[0];
-    const long long items = a.nP - H;
-    const long long rows_per_pol = a.nP * nE;
-    double* out_warp = a.out + lcol * 4 * rows_per_pol + warp_e0;
-    const long long seg_len = (items + a.n_seg - 1) / a.n_seg;
-    const long long seg_hi = min(items, (seg + 1) * seg_len);
-
-    // the phi table of the segment in chunks of BULK_TAB_ITEMS (one chunk for a paired 721-phi grid): two CTA-wide
-    // barriers per chunk, none inside the sweeps
-#pragma unroll 1
-    for (long long base = seg * seg_len; base < seg_hi; base += BULK_TAB_ITEMS) {
-        const int n_items = (int)min((long long)BULK_TAB_ITEMS, seg_hi - base);
-        __syncthreads();
-        for (int i = tid; i < n_items * 6; i += NT) tabs[i] = a.tab[2 + base * 6 + i];
-        __syncthreads();
-        if (!warp_on) continue;
-        const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
-        const int n_single = n_items - n_pair;
-#pragma unroll 1
-        for (int pol = 0; pol < 4; ++pol) {
-            double* prow = out_warp + pol * rows_per_pol;
-            double* plo = prow + base * nE;                          // row = item           (item < H)
-            double* phi_ = prow + (base + H) * nE;                   // row = item + H
-            double* psg = prow + (base + n_pair + H) * nE;           // row = item + H       (item >= H)
-            double kr[2][7], ki[2][7];
-#pragma unroll
-            for (int q = 0; q < EPT; ++q) {
-                const long long e = ee[q];
-                const Column c = load_column(q);
-                auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
-                cplx kk[7] = {};
-                if (pol == 0) coeffs_pp(c, chi, a.ph, kk);
-                else if (pol == 1) coeffs_ps(c, chi, kk);
-                else if (pol == 2) coeffs_sp(c, chi, kk);
-                else coeffs_ss(c, chi, kk);
-#pragma unroll
-                for (int j = 0; j < 7; ++j) { kr[q][j] = kk[j].re; ki[q][j] = kk[j].im; }
-            }
-            if (pol == 3) sweep_bulk<B, true>(kr[0], ki[0], kr[1], ki[1], tabs, 0, n_pair, n_single, plo, phi_, psg, nE, stg);
-            else sweep_bulk<B, false>(kr[0], ki[0], kr[1], ki[1], tabs, 0, n_pair, n_single, plo, phi_, psg, nE, stg);
-        }
-    }
-    if (warp_on && lane == 0) bulk_wait_read<0>();          // shared memory must outlive the copies that read it
-}
 
 #include "sshg_blur.cuh"   // K3: yield_blur_kernel (the sweep with the output broadening in one pass)
 
@@ -851,8 +610,6 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
                                    (int)grid_smem(NT_BIG, CHUNK_BIG)));
     SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
-    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_bulk_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(8)));
-    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_bulk_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bulk_smem(4)));
 
 
     // Sweeps with few azimuths per column go through the sparse-phi kernel (phi-contracted chi2,
@@ -962,14 +719,10 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.n_seg = pick_segments(nc * a.n_tiles, nt == NT_BIG ? 2 : 6, SSHG_NSEG_WAVES);
         SSHG_REQUIRE(nc * a.n_tiles * b.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
         const unsigned ctas = (unsigned)(nc * a.n_tiles * b.n_seg);
-        // store-dominated sweeps with 128-bit-aligned rows: the warps stage their runs and the copy engine writes them
-        // (option "k2_bulk" = 0 | 4 | 8: per-thread stores / row pairs per batch)
-        const int bulk = opt.k2_bulk >= 0 ? opt.k2_bulk : SSHG_K2_BULK_DEFAULT;
-        if (nt == NT_SMALL && b.vec_ok && bulk == 8)
-            yield_grid_bulk_kernel<8><<<ctas, NT_BULK, bulk_smem(8), st>>>(b);
-        else if (nt == NT_SMALL && b.vec_ok && bulk == 4)
-            yield_grid_bulk_kernel<4><<<ctas, NT_BULK, bulk_smem(4), st>>>(b);
-        else if (nt == NT_BIG)
+        // (Staging the warps' runs in shared memory and writing them with cp.async.bulk reaches the sequential-store
+        // peak on this address pattern in isolation, but costs resident warps in the real kernel and measured 1.6-1.8x
+        // slower: profiles/r02_store_experiments.txt, profiles/r02_k2_bulk_store_*.jsonl, DESIGN.md.)
+        if (nt == NT_BIG)
             yield_grid_kernel<NT_BIG, CHUNK_BIG><<<ctas, NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
         else
             yield_grid_kernel<NT_SMALL, CHUNK_SMALL><<<ctas, NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);

@@ -36,7 +36,7 @@ for name, args, t_range, shape in cases_:
     out = torch.empty(shape, dtype=torch.float64, device=dev)
     ref = None
     row = {"tag": tag, "case": name}
-    for bulk in (0, 4, 8, 0, 8):
+    for bulk in (0, 4, 8, 0, 8):  # NOTE: option removed from the library after the experiment (git history)
         with ctx.options(k2_bulk=bulk):
             med, best = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range), 7)
         key = "bulk%d" % bulk + ("_again" if ("bulk%d_ms" % bulk) in row else "")
