@@ -645,29 +645,32 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // polarisation.  256-energy tiles (128 threads, register-limited to 2 CTAs/SM) halve the halo overhead of
     // 128-energy tiles and fit twice on an SM for every fused radius (R = 64: 101 KB + 11 KB of table), so they are
     // used whenever the axis is longer than one narrow tile.  Option "k3_nt" = 64 | 128 overrides (tests run both).
-    int blur_nt = NT_BLUR, blur_per_sm = 1;
+    int blur_nt = NT_BLUR, blur_per_sm = 1, blur_te = NT_BLUR * EPT;          // threads and energies per CTA
     if (fused) {
         const size_t sm_bytes = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
-        auto fixed = [&](int nt) { return (size_t)blur_fixed_doubles((int)radius, nt * EPT + 2 * (int)radius) * sizeof(double); };
-        auto need = [&](int nt) { return fixed(nt) + (size_t)blur_chunk_doubles(32) * sizeof(double); };
+        // 256-energy tiles whenever the axis is longer than one narrow tile: by default one energy per thread (256 threads,
+        // 16 warps per SM); "k3_nt" = 128 selects the two-energies-per-thread kernel on the same tile (8 warps per SM)
+        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR1;
+        if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE || opt.k3_nt == NT_BLUR1) blur_nt = opt.k3_nt;
+        blur_te = blur_nt == NT_BLUR1 ? NT_BLUR1 : blur_nt * EPT;
+        auto fixed = [&]() { return (size_t)blur_fixed_doubles((int)radius, blur_te + 2 * (int)radius) * sizeof(double); };
+        auto need = [&]() { return fixed() + (size_t)blur_chunk_doubles(32) * sizeof(double); };
         auto share = [&](int per_sm) { return sm_bytes / per_sm - 1024; };     // 1 KB per CTA is reserved by the system
-        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
-        if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE) blur_nt = opt.k3_nt;
-        SSHG_REQUIRE(need(blur_nt) <= cta_max, "sshg_yield: internal: K3 shared-memory plan");
+        SSHG_REQUIRE(need() <= cta_max, "sshg_yield: internal: K3 shared-memory plan");
         const int reg_limit = blur_nt == NT_BLUR ? 3 : 2;                      // registers per thread (launch bounds)
         blur_per_sm = 1;
         for (int k = reg_limit; k >= 1; --k)
-            if (need(blur_nt) <= share(k)) { blur_per_sm = k; break; }
+            if (need() <= share(k)) { blur_per_sm = k; break; }
         // grow the allocation to this occupancy's share, but not beyond what the whole table needs
         const int items_all = (int)p->nP;                                      // un-paired grid: one item per phi
-        size_t total = fixed(blur_nt) + (size_t)blur_chunk_doubles(items_all) * sizeof(double);
+        size_t total = fixed() + (size_t)blur_chunk_doubles(items_all) * sizeof(double);
         if (total > share(blur_per_sm)) total = share(blur_per_sm);
         if (total > cta_max) total = cta_max;
         int chunk = 32;                                                        // as many items as fit
-        while (chunk < items_all && fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk + 1) * sizeof(double) <= total) ++chunk;
-        blur_smem = fixed(blur_nt) + (size_t)blur_chunk_doubles(chunk) * sizeof(double);
+        while (chunk < items_all && fixed() + (size_t)blur_chunk_doubles(chunk + 1) * sizeof(double) <= total) ++chunk;
+        blur_smem = fixed() + (size_t)blur_chunk_doubles(chunk) * sizeof(double);
         ba.radius = (int)radius;
-        ba.S = blur_nt * EPT + 2 * (int)radius;
+        ba.S = blur_te + 2 * (int)radius;
         ba.chunk = chunk;
         ba.fixup = opt.k3_fixup == 0 ? 0 : 1;
         ba.phi_deg = (const double*)dphi;
@@ -675,11 +678,13 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         if (blur_nt == NT_BLUR)
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
-        else
+        else if (blur_nt == NT_BLUR_WIDE)
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
+        else
+            SSHG_CUDA(cudaFuncSetAttribute(yield_blur1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
     }
-    const int blur_tiles = (int)((p->nE + blur_nt * EPT - 1) / (blur_nt * EPT));
+    const int blur_tiles = (int)((p->nE + blur_te - 1) / blur_te);
     SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
 
     // Short launches: a CTA that is left alone at the end of a launch still needs its full azimuthal sweep
@@ -748,8 +753,10 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
             yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
-        else
+        else if (blur_nt == NT_BLUR_WIDE)
             yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
+        else
+            yield_blur1_kernel<<<ctas, NT_BLUR1, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
