@@ -137,7 +137,7 @@ SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by
  *   "k2_nt"         64 | 256  CTA width of the dense yield kernel
  *   "k2_recurrence" 0 | 1     phase recurrence on uniform thickness axes      (default 1)
  *   "k3"            0 | 1     output broadening fused into the yield kernel   (default 1 where it applies)
- *   "k3_nt"         64 | 128 | 256  CTA width of the fused kernel (256: one energy per thread, the default on long axes)
+ *   "k3_nt"         64 | 128  CTA width of the fused kernel
  *   "k3_fixup"      0 | 1     strict re-evaluation next to azimuthal nodes    (default 1)   TEST ONLY
  *   "nseg"          1 .. 16   phi segments per column
  *   "k1_generic"    0 | 1     generic instead of fixed-radius FIR kernels     (default 0)

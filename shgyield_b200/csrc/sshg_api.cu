@@ -176,7 +176,7 @@ const OptionKey kOptions[] = {
     {"k2_nt", &sshg_options::k2_nt, 0, 0, 64, 256},
     {"k2_recurrence", &sshg_options::k2_recurrence, 0, 1, -1, -1},
     {"k3", &sshg_options::k3, 0, 1, -1, -1},
-    {"k3_nt", &sshg_options::k3_nt, 64, 256, -1, -1},
+    {"k3_nt", &sshg_options::k3_nt, 0, 0, 64, 128},
     {"k3_fixup", &sshg_options::k3_fixup, 0, 1, -1, -1},
     {"nseg", &sshg_options::nseg, 1, 16, -1, -1},
     {"k1_generic", &sshg_options::k1_generic, 0, 1, -1, -1},
@@ -195,8 +195,7 @@ int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value) {
     SSHG_REQUIRE(o, "sshg_ctx_set_option: unknown option '%s'", key);
     const bool ok = value == -1 || (o->only_a >= 0 ? (value == o->only_a || value == o->only_b)
                                                    : (value >= o->lo && value <= o->hi));
-    SSHG_REQUIRE(ok && !(strcmp(key, "k3_nt") == 0 && value != -1 && value != 64 && value != 128 && value != 256),
-                 "sshg_ctx_set_option: value %lld is not allowed for '%s'", (long long)value, key);
+    SSHG_REQUIRE(ok, "sshg_ctx_set_option: value %lld is not allowed for '%s'", (long long)value, key);
     ctx->opt.*(o->field) = (int)value;
     return SSHG_OK;
 }

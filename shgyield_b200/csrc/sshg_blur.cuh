@@ -496,323 +496,3 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
         }
     }
 }
-
-// ---- K3, one energy per thread (256-energy tiles, 256 threads) -------------------------------------------------------
-// K2 and K3 are bound by the latency of their dependent FMA chains: their throughput goes with the number of resident
-// warps until the HBM store stream saturates (profiles/r02_k2_bulk_store_*.jsonl: 12 -> 8 -> 6 warps per SM = 1.65 ->
-// 2.58 -> 2.95 ms).  The two-energies-per-thread kernel above holds 2 x 13 broadened harmonics per thread (~250
-// registers): 2 CTAs x 4 warps per SM.  Here a thread owns ONE energy: 13 harmonics, <= 128 registers, and the same
-// 256-energy tile is swept by 8 warps, 16 per SM, with the same shared-memory plan.  The FIR keeps its two-energy
-// form (one LDS.128 feeds 4 FMAs): the even lane of a pair filters both energies and hands the odd one its 13 results
-// by warp shuffles.  Stores are 64-bit; a warp still writes whole 128-byte lines (256 contiguous bytes per row).
-constexpr int NT_BLUR1 = 256;
-
-template <bool SS>
-__device__ __forceinline__ void harm_item1(const double* A, const double* __restrict__ tb, double& ye, double& yo) {
-    double t[12];
-#pragma unroll
-    for (int j = 0; j < (SS ? 3 : 6); ++j) {
-        const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
-        t[2 * j] = v.x;
-        t[2 * j + 1] = v.y;
-    }
-    ye = A[0];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) ye = fma(A[1 + j], t[j], ye);
-    yo = 0.0;
-    if (!SS) {
-        yo = A[7] * t[6];
-#pragma unroll
-        for (int j = 1; j < 6; ++j) yo = fma(A[7 + j], t[6 + j], yo);
-    }
-}
-
-template <bool SS, bool PAIR>
-__device__ __forceinline__ void sweep_part1(const double* A, const double* __restrict__ t, int n, int ibase, double* q0,
-                                            double* q1, long long stride, int h, unsigned* fl_lo, unsigned* fl_hi) {
-#pragma unroll 1
-    for (int i0 = 0; i0 < n; i0 += SWEEP_SB) {
-        const int nb = min(SWEEP_SB, n - i0);
-        unsigned mlo = 0u, mhi = 0u, bit = 1u;
-#pragma unroll 4
-        for (int i = 0; i < nb; ++i) {
-            double ye, yo;
-            harm_item1<SS>(A, t, ye, yo);
-            t += 12;
-            const double v = ye + yo;
-            __stcs(q0, v);
-            q0 += stride;
-            if (__double2hiint(v) < h) mlo |= bit;
-            if (PAIR) {
-                const double w = ye - yo;
-                __stcs(q1, w);
-                q1 += stride;
-                if (!SS) {
-                    if (__double2hiint(w) < h) mhi |= bit;
-                }
-            }
-            bit += bit;
-        }
-        if (SS && PAIR) mhi = mlo;
-        if (mlo | mhi) {
-            or_flag_bits(fl_lo, ibase + i0, mlo);
-            or_flag_bits(fl_hi, ibase + i0, mhi);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(NT_BLUR1, 2) yield_blur1_kernel(const __grid_constant__ BlurArgs b) {
-    constexpr int NT = NT_BLUR1;
-    extern __shared__ double smem[];
-    const YieldArgs& a = b.y;
-    const int R = b.radius, S = b.S, CH = b.chunk;
-    const int FLW = blur_flag_words(CH);
-    double* wf = smem;
-    double* cols = wf + 2 * R + 2;
-    double* raw = cols + NCOL * S;
-    double* pb = raw + NH * S;
-    unsigned* fl = reinterpret_cast<unsigned*>(pb + FX_RB * 6);
-    double* tabs = smem + blur_fixed_doubles(R, S) + (blur_chunk_doubles(CH) - CH * 12);
-
-    const long long blk = blockIdx.x;
-    const int tile = (int)(blk % a.n_tiles);
-    const int n_seg = a.n_seg;
-    const int seg = (int)((blk / a.n_tiles) % n_seg);
-    const long long lcol = blk / a.n_tiles / n_seg;
-    const long long col = a.col0 + lcol;
-    const int tl = (int)(col / a.nDs), dl = (int)(col % a.nDs);
-    const int tid = threadIdx.x, lane = tid & 31;
-    const long long nE = a.nE;
-    const long long tile_e0 = (long long)tile * NT;
-
-    for (int t = tid; t <= 2 * R; t += NT) wf[t] = b.w[t < R ? R - t : t - R];
-
-    // ---- (A) column setup of the staged energies (tile + halo), parked -----------------------------------
-    {
-        double st, ct;
-        sincos(a.theta_deg[a.t0 + tl] * (3.141592653589793 / 180.0), &st, &ct);
-        const double thick = a.thick_nm[a.d0 + dl];
-#pragma unroll 1
-        for (int i = tid; i < S; i += NT) {
-            const long long g = tile_e0 - R + i;
-            if (g >= nE + R) break;
-            const long long e = reflect_index(g, nE);
-            cplx e1[3], e2[3];
-#pragma unroll
-            for (int m = 0; m < 3; ++m) {
-                e1[m] = ldc(a.eps1w + m * nE + e);
-                e2[m] = ldc(a.eps2w + m * nE + e);
-            }
-            const Column c = column_setup(e1, e2, a.energy[e], st, ct, thick, a.ph);
-            const cplx v[10] = {c.Gpp, c.Gps, c.Gsp, c.Gss, c.A, c.Bz, c.Q, c.a2, c.ab, c.b2};
-#pragma unroll
-            for (int j = 0; j < 10; ++j) {
-                cols[(2 * j) * S + i] = v[j].re;
-                cols[(2 * j + 1) * S + i] = v[j].im;
-            }
-        }
-    }
-
-    const long long e0 = tile_e0 + tid;
-    const bool active = e0 < nE;
-    const long long H = (long long)a.tab[0];
-    const long long items = a.nP - H;
-    const long long rows_per_pol = a.nP * nE;
-    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
-    const long long seg_len = (items + n_seg - 1) / n_seg;
-    const long long seg_lo = seg * seg_len, seg_hi = min(items, (seg + 1) * seg_len);
-    const bool one_chunk = seg_hi - seg_lo <= CH;
-    const int INT_LOWEST = (int)0x80000000;
-
-#pragma unroll 1
-    for (int pol = 0; pol < 4; ++pol) {
-        // ---- (A') harmonic spectra of this polarisation for the staged energies ----------------------------
-        __syncthreads();
-#pragma unroll 1
-        for (int i = tid; i < S; i += NT) {
-            const long long g = tile_e0 - R + i;
-            if (g >= nE + R) break;
-            const long long e = reflect_index(g, nE);
-            const Column c = parked_column(cols, S, i);
-            auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
-            cplx kk[7];
-            coeffs_of(pol, c, chi, a.ph, kk);
-            double Hh[NH];
-            if (pol == 3) {
-                harmonics4(kk, Hh);
-#pragma unroll
-                for (int m = 0; m < NH_SS; ++m) raw[m * S + i] = Hh[m];
-            } else {
-                harmonics7(kk, Hh);
-#pragma unroll
-                for (int m = 0; m < NH; ++m) raw[m * S + i] = Hh[m];
-            }
-        }
-        __syncthreads();
-
-        // ---- (B) broadened harmonics: the even lane of a pair filters both energies, the odd lane receives its 13 ----
-        double A[NH];
-        {
-            // in two halves (7 + 6 spectra) to keep the accumulators of the pair within 128 registers
-            double A0[NH_SS], A1[NH_SS];
-            if ((tid & 1) == 0) fir_pair<NH_SS>(raw + tid, S, R, wf, A0, A1);   // window of the pair's first energy: 16-byte aligned
-#pragma unroll
-            for (int m = 0; m < NH_SS; ++m) {
-                const double other = __shfl_sync(0xffffffffu, A1[m], lane & ~1);
-                A[m] = (tid & 1) ? other : A0[m];
-            }
-            if (pol != 3) {
-                if ((tid & 1) == 0) fir_pair<NH - NH_SS>(raw + NH_SS * S + tid, S, R, wf, A0, A1);
-#pragma unroll
-                for (int m = 0; m < NH - NH_SS; ++m) {
-                    const double other = __shfl_sync(0xffffffffu, A1[m], lane & ~1);
-                    A[NH_SS + m] = (tid & 1) ? other : A0[m];
-                }
-            }
-        }
-        int h = INT_LOWEST;
-        if (b.fixup && active) {
-            const double u = amplitude_bound(A, pol == 3);
-            if (u < 1.0e300) h = __double2hiint(NODE_FRACTION * u);
-        }
-
-        // ---- (C) azimuthal sweep, (D) strict re-evaluation of the flagged rows, table chunk by chunk --------
-#pragma unroll 1
-        for (long long base = seg_lo; base < seg_hi; base += CH) {
-            const int n_items = (int)min((long long)CH, seg_hi - base);
-            if (!one_chunk || pol == 0)
-                for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
-            for (int i = tid; i < 4 * FLW; i += NT) fl[i] = 0u;
-            __syncthreads();
-            const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
-            const int n_single = n_items - n_pair;
-            if (active) {
-                double* prow = out_col + pol * rows_per_pol;
-                double* plo = prow + base * nE;
-                double* phi_ = prow + (base + H) * nE;
-                double* psg = prow + (base + n_pair + H) * nE;
-                if (pol == 3) {
-                    sweep_part1<true, true>(A, tabs, n_pair, 0, plo, phi_, nE, h, fl, fl + FLW);
-                    sweep_part1<true, false>(A, tabs + 12 * n_pair, n_single, n_pair, psg, nullptr, nE, h, fl, fl + FLW);
-                } else {
-                    sweep_part1<false, true>(A, tabs, n_pair, 0, plo, phi_, nE, h, fl, fl + FLW);
-                    sweep_part1<false, false>(A, tabs + 12 * n_pair, n_single, n_pair, psg, nullptr, nE, h, fl, fl + FLW);
-                }
-            }
-            __syncthreads();
-
-            // ---- (D) as in the two-energy kernel: band test per thread, then strict batches
-            if (!b.fixup) continue;
-            unsigned* st = fl + 2 * FLW;
-            {
-                double thr = 0.0;
-                bool have_thr = false;
-#pragma unroll 1
-                for (int wi = 0; wi < 2 * FLW; ++wi) {
-                    unsigned bits = fl[wi];
-                    unsigned mine = 0u;
-#pragma unroll 1
-                    while (bits) {
-                        const int bp = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        if (!active) continue;
-                        const int part = wi >= FLW ? 1 : 0;
-                        const int item = (wi - part * FLW) * 32 + bp;
-                        if (!have_thr) {
-                            thr = NODE_FRACTION * amplitude_bound(A, pol == 3);
-                            have_thr = true;
-                        }
-                        double ye, yo;
-                        if (pol == 3) harm_item1<true>(A, tabs + 12 * item, ye, yo);
-                        else harm_item1<false>(A, tabs + 12 * item, ye, yo);
-                        const double y = part == 1 ? ye - yo : ye + yo;
-                        const double band = DEEP_FRACTION / NODE_FRACTION;
-                        if ((y < thr) & (y > band * thr)) {
-                            mine |= 1u << bp;
-                        } else if (y < 0.0) {
-                            const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                            __stcs(out_col + (pol * a.nP + row) * nE, 0.0);
-                        }
-                    }
-                    if (mine) atomicOr(st + wi, mine);
-                }
-            }
-            __syncthreads();
-            int rows[FX_RB], nb = 0;
-#pragma unroll 1
-            for (int wi = 0; wi <= 2 * FLW; ++wi) {
-                unsigned bits = wi < 2 * FLW ? st[wi] : 0u;
-                const bool last = wi == 2 * FLW;
-#pragma unroll 1
-                while (bits || (last && nb > 0)) {
-                    if (bits) {
-                        const int bp = __ffs(bits) - 1;
-                        bits &= bits - 1;
-                        const int part = wi >= FLW ? 1 : 0;
-                        const int item = (wi - part * FLW) * 32 + bp;
-                        const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                        rows[nb++] = (int)row;
-                        if (nb < FX_RB) continue;
-                    }
-                    double* rowbuf = raw;
-                    if (tid < nb) phi_basis(b.phi_deg[rows[tid]], pb + tid * 6);
-                    __syncthreads();
-#pragma unroll 1
-                    for (int i = tid; i < S; i += NT) {
-                        const long long g = tile_e0 - R + i;
-                        if (g >= nE + R) break;
-                        const long long e = reflect_index(g, nE);
-                        const Column c = parked_column(cols, S, i);
-                        auto chi = [&](int r) { return ldc(a.chi + r * nE + e); };
-                        cplx kk[7];
-                        coeffs_of(pol, c, chi, a.ph, kk);
-#pragma unroll 1
-                        for (int q = 0; q < nb; ++q) {
-                            const double* bb = pb + q * 6;
-                            double re, im;
-                            if (pol == 3) {
-                                re = kk[0].re * bb[2];
-                                im = kk[0].im * bb[2];
-#pragma unroll
-                                for (int j = 1; j < 4; ++j) {
-                                    re = fma(kk[j].re, bb[j + 2], re);
-                                    im = fma(kk[j].im, bb[j + 2], im);
-                                }
-                            } else {
-                                re = kk[0].re;
-                                im = kk[0].im;
-#pragma unroll
-                                for (int j = 0; j < 6; ++j) {
-                                    re = fma(kk[j + 1].re, bb[j], re);
-                                    im = fma(kk[j + 1].im, bb[j], im);
-                                }
-                            }
-                            rowbuf[q * S + i] = fma(re, re, im * im);
-                        }
-                    }
-                    __syncthreads();
-                    // FIR with the arithmetic of fir_pair (ascending taps, absent taps skipped): even lanes filter
-                    // both energies of their pair, four rows at a time, and store both
-                    if ((tid & 1) == 0 && active) {
-                        const bool second = e0 + 1 < nE;
-#pragma unroll 1
-                        for (int q0 = 0; q0 < nb; q0 += 4) {
-                            double o0[4], o1[4];
-                            fir_pair<4>(rowbuf + q0 * S + tid, S, R, wf, o0, o1);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (q0 + q < nb) {
-                                    double* dst = out_col + (pol * a.nP + (long long)rows[q0 + q]) * nE;
-                                    __stcs(dst, o0[q]);
-                                    if (second) __stcs(dst + 1, o1[q]);
-                                }
-                        }
-                    }
-                    __syncthreads();
-                    nb = 0;
-                }
-            }
-            __syncthreads();
-        }
-    }
-}

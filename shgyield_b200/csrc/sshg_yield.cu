@@ -648,11 +648,12 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     int blur_nt = NT_BLUR, blur_per_sm = 1, blur_te = NT_BLUR * EPT;          // threads and energies per CTA
     if (fused) {
         const size_t sm_bytes = (size_t)228 * 1024, cta_max = (size_t)227 * 1024;
-        // 256-energy tiles whenever the axis is longer than one narrow tile: by default one energy per thread (256 threads,
-        // 16 warps per SM); "k3_nt" = 128 selects the two-energies-per-thread kernel on the same tile (8 warps per SM)
-        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR1;
-        if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE || opt.k3_nt == NT_BLUR1) blur_nt = opt.k3_nt;
-        blur_te = blur_nt == NT_BLUR1 ? NT_BLUR1 : blur_nt * EPT;
+        // 256-energy tiles (128 threads, two energies each) whenever the axis is longer than one narrow tile.  (One energy
+        // per thread -- 256 threads, 16 warps per SM instead of 8, 64-bit stores -- measured 12-18 % slower:
+        // profiles/r02_k3_one_energy_per_thread.jsonl.)
+        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
+        if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE) blur_nt = opt.k3_nt;
+        blur_te = blur_nt * EPT;
         auto fixed = [&]() { return (size_t)blur_fixed_doubles((int)radius, blur_te + 2 * (int)radius) * sizeof(double); };
         auto need = [&]() { return fixed() + (size_t)blur_chunk_doubles(32) * sizeof(double); };
         auto share = [&](int per_sm) { return sm_bytes / per_sm - 1024; };     // 1 KB per CTA is reserved by the system
@@ -678,11 +679,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         if (blur_nt == NT_BLUR)
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
-        else if (blur_nt == NT_BLUR_WIDE)
+        else
             SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)blur_smem));
-        else
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
     }
     const int blur_tiles = (int)((p->nE + blur_te - 1) / blur_te);
     SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
@@ -753,10 +752,8 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
         if (blur_nt == NT_BLUR)
             yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
-        else if (blur_nt == NT_BLUR_WIDE)
-            yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         else
-            yield_blur1_kernel<<<ctas, NT_BLUR1, blur_smem, st>>>(b);
+            yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;

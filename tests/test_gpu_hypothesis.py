@@ -89,7 +89,7 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel):
 @settings(max_examples=20 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 900), nT=st.integers(1, 3), nD=st.integers(1, 2),
        sigma=st.floats(0.13, 16.0), grid_kind=st.sampled_from(["paired", "paired_tail", "free"]),
-       tiles=st.sampled_from(["64", "128", "256"]))
+       tiles=st.sampled_from(["64", "128"]))
 def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     """K3 (yields broadened along E inside the kernel, both tile widths) on generated media / tensors /
     grids against the oracle's broad(yield, sigma_out) -- absolute bound of the harmonic form plus the
