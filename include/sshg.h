@@ -209,7 +209,7 @@ SSHG_API int sshg_yield_points(sshg_ctx* ctx, const sshg_points* p, double* out,
  * (shg.py:428-436); out[pol][n].  `where` = SSHG_HOST, SSHG_SPECTRA_DEVICE, or SSHG_DEVICE.  Host calls with resident
  * spectra (the interactive call shapes of the reference's GUI, gui.py:286-330) upload the point arrays in one copy
  * from page-locked staging memory and replay a CUDA graph (copy in, yield kernel, FIR passes, copy out) that is
- * recorded the first time a (shape, sigma_out, physics, spectra) combination is seen; option "graphs" = 0 disables. */
+ * recorded when a (shape, sigma_out, physics, spectra) combination comes the second time; option "graphs" = 0 disables. */
 SSHG_API int sshg_yield_points_broadened(sshg_ctx* ctx, const sshg_points* p, double sigma_out, int32_t ndim,
                                 const int64_t* shape, double* out, int where);
 /* The same sweep with the output broadening of shgyield() (broad(., sigma_out) on every yield spectrum,

@@ -86,6 +86,8 @@ struct sshg_ctx {
     void* pin_out;
     size_t pin_in_bytes, pin_out_bytes;
     sshg_small_graph graphs[SSHG_NGRAPH];
+    sshg_small_key seen[SSHG_NGRAPH];   // combinations that ran once: a graph is recorded when one of them comes again
+    int seen_valid[SSHG_NGRAPH], seen_next;
     uint64_t graph_clock;
     int64_t graph_replays;
 };

@@ -886,7 +886,7 @@ extern "C" int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, doubl
 // ---- the tail of shgyield() for small broadcasts: yields of a point list + broad(., sigma_out) along every axis --------
 // (reference shg.py:428-436; the interactive call shapes of gui.py:286-330).  With resident spectra the call is one
 // upload of the packed point arrays from page-locked memory, the yield kernel, one FIR pass per axis and one download,
-// recorded as a CUDA graph the first time a (shape, sigma_out, physics, spectra) combination is seen and replayed after.
+// recorded as a CUDA graph when a (shape, sigma_out, physics, spectra) combination comes a second time and replayed after.
 namespace {
 
 int grow_pinned(sshg_ctx* ctx, void** buf, size_t* have, size_t bytes) {
@@ -1033,9 +1033,25 @@ extern "C" int sshg_yield_points_broadened(sshg_ctx* ctx, const sshg_points* p, 
     memcpy(out, ctx->pin_out, 4 * n * 8);
     if (hit || !graphable) return SSHG_OK;
 
-    // first sighting: every buffer the sequence touches now exists at its final size and the taps are resident, so the
-    // same sequence can be captured (capture executes nothing).  A failure here only means "no graph": the result is out.
+    // Every buffer the sequence touches now exists at its final size and the taps are resident, so the same sequence can
+    // be captured (capture executes nothing).  Recording costs more than a call, so it waits for the SECOND sighting of a
+    // combination: a stream of ever-new combinations (a slider that changes the prepared spectra on every tick) never
+    // pays for it.  A failure here only means "no graph": the result is out.
     if (key.epoch != ctx->epoch) return SSHG_OK;      // a buffer moved during the direct run; record next time
+    {
+        bool seen_before = false;
+        for (int k = 0; k < SSHG_NGRAPH; ++k)
+            if (ctx->seen_valid[k] && memcmp(&ctx->seen[k], &key, sizeof(key)) == 0) {
+                seen_before = true;
+                ctx->seen_valid[k] = 0;
+            }
+        if (!seen_before) {
+            ctx->seen[ctx->seen_next] = key;
+            ctx->seen_valid[ctx->seen_next] = 1;
+            ctx->seen_next = (ctx->seen_next + 1) % SSHG_NGRAPH;
+            return SSHG_OK;
+        }
+    }
     sshg_small_graph* slot = &ctx->graphs[0];
     for (int k = 0; k < SSHG_NGRAPH; ++k) {
         if (!ctx->graphs[k].exec) { slot = &ctx->graphs[k]; break; }

@@ -240,6 +240,14 @@ def yield_points(energy, eidx, theta, phi, thick, eps1w, eps2w, chi2, mref=True,
 def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi, mode):
     """Reference shg.py:387-426: broaden, resample at E / 2E, average, map the mode, rotate.
     Returns (eps1w [3,nE], eps2w [3,nE], chi_rot [18,nE], thick) for the flattened energies."""
+    eps1w, eps2w, packed, thick = _resample_all(energy, eps_m1, eps_m2, eps_m3, chi2, thick, sigma_eps, sigma_chi, mode)
+    chi_rot = _rotate_packed(packed, float(gamma)) if packed.shape[1] else packed
+    return eps1w, eps2w, chi_rot, thick
+
+
+def _resample_all(energy, eps_m1, eps_m2, eps_m3, chi2, thick, sigma_eps, sigma_chi, mode):
+    """Everything of _prepare() that does not depend on gamma (shg.py:387-424): eps(w), eps(2w) [3, nE] and the
+    un-rotated chi2 [18, nE]."""
     energy = np.asarray(energy, dtype=np.float64)
     nE = energy.size
     # all spectra of the three media: one broaden + resample call (queries E and 2E)
@@ -277,8 +285,7 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
     packed = np.empty((18, nE), dtype=np.complex128)
     for i, k in enumerate(CHI2_KEYS):
         packed[i] = np.broadcast_to(np.asarray(chi_new[k], dtype=np.complex128), energy.shape).ravel()   # KeyError like the reference
-    chi_rot = _rotate_packed(packed, float(gamma)) if nE else packed
-    return eps1w, eps2w, chi_rot, thick
+    return eps1w, eps2w, packed, thick
 
 
 # ---------------------------------------------------------------------------------------------
@@ -291,6 +298,7 @@ def _prepare(energy, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigm
 # ---------------------------------------------------------------------------------------------
 _PREPARE_CACHE = None           # OrderedDict: key -> _Prepared (created on first use); False: switched off
 _PREPARE_CACHE_SIZE = 8
+_RESAMPLE_CACHE: dict = {}      # key without gamma -> (eps1w, eps2w, un-rotated chi2, thick): host arrays
 
 
 def cache_prepared(enable: bool = True, size: int = 8):
@@ -308,6 +316,7 @@ def cache_prepared(enable: bool = True, size: int = 8):
     _FREE_BLOCKS.clear()
     _PREPARE_CACHE = None if enable else False
     _PREPARE_CACHE_SIZE = max(1, int(size))
+    _RESAMPLE_CACHE.clear()
 
 
 _FREE_BLOCKS: dict = {}         # device blocks of evicted entries, by size: a miss reuses one instead of cudaMalloc / cudaFree
@@ -413,8 +422,20 @@ def _prepare_cached(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps
             if mode in ("fresnel", "2-layer"):
                 thick = 0                       # reference shg.py:414
             return hit, thick
-    eps1w, eps2w, chi_rot, thick_eff = _prepare(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, gamma, sigma_eps, sigma_chi,
-                                                mode)
+    # a miss: when only gamma is new (the GUI's rotation slider) the broadened / resampled spectra are still there and
+    # only the rotation is redone
+    rkey = (key[0],) + key[2:] if key is not None else None
+    res = _RESAMPLE_CACHE.get(rkey) if rkey is not None else None
+    if res is None:
+        res = _resample_all(e_arr, eps_m1, eps_m2, eps_m3, chi2, thick, sigma_eps, sigma_chi, mode)
+        if rkey is not None:
+            _RESAMPLE_CACHE[rkey] = res
+            while len(_RESAMPLE_CACHE) > _PREPARE_CACHE_SIZE:
+                _RESAMPLE_CACHE.pop(next(iter(_RESAMPLE_CACHE)))
+    eps1w, eps2w, packed, thick_eff = res
+    if mode not in ("fresnel", "2-layer"):
+        thick_eff = thick                       # the cached value belongs to another call; only the mode overrides it
+    chi_rot = _rotate_packed(packed, float(gamma)) if packed.shape[1] else packed
     ent = _Prepared(e_arr.ravel(), eps1w, eps2w, chi_rot)
     if key is not None:
         _PREPARE_CACHE[key] = ent

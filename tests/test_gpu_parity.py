@@ -499,7 +499,8 @@ def test_small_calls_replay_a_graph_with_the_same_bits(shg, spectra):
     shapes = (dict(energy=1.7, phi=np.arange(0, 361), sigma_out=0.0), dict(energy=cases.E_C1, phi=30, sigma_out=5))
     with ctx.options(graphs=0):
         plain = [shg.shgyield(**s, **kw) for s in shapes]
-    first = [shg.shgyield(**s, **kw) for s in shapes]                  # runs kernel by kernel, records
+    first = [shg.shgyield(**s, **kw) for s in shapes]                  # runs kernel by kernel; the combination is noted
+    second = [shg.shgyield(**s, **kw) for s in shapes]                 # second sighting: kernel by kernel, then recorded
     n0 = ctx.launches
     again = [shg.shgyield(**s, **kw) for s in shapes]                  # replays
     assert ctx.launches - n0 == 1 + 2                                  # polar: yield kernel; spectrum: yield kernel + FIR
@@ -507,8 +508,8 @@ def test_small_calls_replay_a_graph_with_the_same_bits(shg, spectra):
     with ctx.options(graphs=0):
         moved0 = shg.shgyield(energy=cases.E_C1, phi=31.5, sigma_out=5, **dict(kw, theta=40))
     for pol in cases.POLS:
-        for a, b, c in zip(plain, first, again):
-            assert np.array_equal(a[pol], b[pol]) and np.array_equal(a[pol], c[pol])
+        for a, b, c, d in zip(plain, first, second, again):
+            assert np.array_equal(a[pol], b[pol]) and np.array_equal(a[pol], c[pol]) and np.array_equal(a[pol], d[pol])
         assert np.array_equal(moved[pol], moved0[pol])
     gold = np.load(os.path.join(G, "ref_api_cases.npz"))
     for name, res in (("polar", again[0]), ("c1_d10", again[1])):
@@ -529,3 +530,19 @@ def test_gauss_nd_matches_scipy(shg):
         got = shg.broad(x, sigma)
         assert got.shape == want.shape
         assert np.max(np.abs(got - want)) <= 4e-15 * max(1.0, np.max(np.abs(want))), (shape, sigma)
+
+
+def test_gamma_only_changes_reuse_the_resampled_spectra(shg, spectra):
+    """A call that differs from an earlier one only in gamma (the GUI's rotation slider) redoes the rotation alone; the
+    result is bit for bit the one of a fresh preparation, also for the modes that override the thickness."""
+    m1, m2, m3, chi2 = cases.full_tensor_material(spectra)
+    kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, theta=50, phi=20, sigma_eps=1.0, sigma_chi=2.0, sigma_out=3.0)
+    for mode, thick in (("3-layer", 12.0), ("fresnel", 12.0), ("3-layer", np.array([[5.0], [25.0]]))):
+        shg.cache_prepared(True)
+        shg.shgyield(cases.E_C1, thick=thick, gamma=10, mode=mode, **kw)              # fills both levels
+        got = shg.shgyield(cases.E_C1, thick=thick, gamma=37.5, mode=mode, **kw)      # new gamma: resampled spectra reused
+        shg.cache_prepared(False)
+        want = shg.shgyield(cases.E_C1, thick=thick, gamma=37.5, mode=mode, **kw)
+        shg.cache_prepared(True)
+        for pol in cases.POLS:
+            assert got[pol].shape == want[pol].shape and np.array_equal(got[pol], want[pol]), (mode, pol)

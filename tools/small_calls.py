@@ -42,6 +42,7 @@ for name, s in shapes.items():
     l0 = ctx.launches
     call()
     first_launches = ctx.launches - l0
+    call()
     ms_default = wall(call, reps)
     l0 = ctx.launches
     call()
