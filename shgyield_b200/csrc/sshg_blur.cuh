@@ -432,12 +432,23 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                         const int part = wi >= FLW ? 1 : 0;
                         const int item = (wi - part * FLW) * 32 + bp;
                         const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                        rows[nb++] = (int)row;
+                        rows[nb] = (int)row;
+                        if (tid == nb) {        // basis row of this azimuth from the staged table: cos / sin of phi are its
+                            const double* t = tabs + 12 * item;          // first odd harmonic; phi + 180 deg flips both
+                            const double c = part == 1 && item < n_pair ? -t[6] : t[6], sn = part == 1 && item < n_pair ? -t[7] : t[7];
+                            double* bb = pb + nb * 6;
+                            bb[0] = c * c;
+                            bb[1] = sn * c;
+                            bb[2] = bb[0] * c;
+                            bb[3] = bb[1] * c;
+                            bb[4] = bb[1] * sn;
+                            bb[5] = sn * sn * sn;
+                        }
+                        ++nb;
                         if (nb < FX_RB) continue;
                     }
-                    // -- one batch: the un-broadened yields of the staged energies exactly as K2 computes them ...
+                    // -- one batch: the un-broadened yields of the staged energies as K2 computes them ...
                     double* rowbuf = raw;       // [FX_RB][S]
-                    if (tid < nb) phi_basis(b.phi_deg[rows[tid]], pb + tid * 6);
                     __syncthreads();
 #pragma unroll 1
                     for (int i = tid; i < S; i += NT) {

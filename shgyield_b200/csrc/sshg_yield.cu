@@ -760,10 +760,17 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     };
 
     // slabs of columns: the host-output pipeline and the two-pass broadening work slab by slab
-    const size_t slab_target = (size_t)256 << 20;
+    // (256 MB for host output: slab k is copied back while slab k + 1 is computed; 1 GB when the output stays on the
+    // device and the slab is only the intermediate of the two-pass path -- config 4, 288 MB, is then one launch of each
+    // kernel).  The slabs are made equal: a short last slab would be a badly filled launch.
+    const size_t slab_target = out_dev ? (size_t)1 << 30 : (size_t)256 << 20;
     int64_t cols_per_slab = (int64_t)(slab_target / ((size_t)per_col * 8));
     if (cols_per_slab < 1) cols_per_slab = 1;
     if (cols_per_slab > cols) cols_per_slab = cols;
+    {
+        const int64_t n_slabs = (cols + cols_per_slab - 1) / cols_per_slab;
+        cols_per_slab = (cols + n_slabs - 1) / n_slabs;
+    }
     const size_t slab_bytes = (size_t)cols_per_slab * per_col * 8;
     void* tmp = nullptr;                        // K2 output of a slab, input of K1 (two-pass only)
     if (two_pass) {

@@ -94,3 +94,69 @@ def test_context_options_and_stream_handling():
         assert ctx.lib.sshg_ctx_stream(ctx.handle) == own
         host = grid.yield_grid_host(**cfg)             # the host-array path keeps working on the own stream
         assert np.array_equal(host, ref.cpu().numpy())
+
+
+def test_points_broadened_device_resident_and_bad_index():
+    """sshg_yield_points_broadened with everything resident (where = SSHG_DEVICE): the same bits as the host call with
+    resident spectra and as the plain host call, on a 2-D broadcast with the filter along both axes; an out-of-range
+    column index in a device-resident list gives NaN for that point instead of an out-of-bounds read."""
+    import ctypes as C
+    import torch
+    from shgyield_b200 import _lib
+    from shgyield_b200.shg import _physics, physical_constants
+    from shgyield_b200.synthetic import synthetic_spectra
+    ctx = _lib.context(0)
+    energy, eps1w, eps2w, chi = synthetic_spectra(40, seed=5)
+    shape = (7, 40)
+    n = 7 * 40
+    theta = np.ascontiguousarray(np.broadcast_to(np.linspace(10, 70, 7)[:, None], shape)).ravel()
+    phi = np.full(n, 33.0)
+    thick = np.full(n, 12.0)
+    eidx = np.ascontiguousarray(np.broadcast_to(np.arange(40, dtype=np.int64), shape)).ravel()
+    phys = _physics(physical_constants(), True)
+    shp = (C.c_int64 * 2)(*shape)
+
+    def call(arrs, where, out_ptr):
+        p = _lib.Points(n=n, nE=40, energy_eV=arrs[0], eidx=arrs[1], theta_deg=arrs[2], phi_deg=arrs[3], thick_nm=arrs[4],
+                        eps1w=arrs[5], eps2w=arrs[6], chi2=arrs[7], phys=phys)
+        _lib.check(ctx.lib.sshg_yield_points_broadened(ctx.handle, C.byref(p), 1.5, 2, shp, out_ptr, where), ctx.lib)
+
+    host = [energy, eidx, theta, phi, thick, eps1w, eps2w, chi]
+    out_h = np.empty((4, n))
+    call([a.ctypes.data for a in host], _lib.HOST, out_h.ctypes.data)
+    dev = torch.device("cuda", 0)
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in host]
+    out_s = np.empty((4, n))
+    ptrs = [a.ctypes.data for a in host]
+    for k in (0, 5, 6, 7):
+        ptrs[k] = d[k].data_ptr()
+    call(ptrs, _lib.SPECTRA_DEVICE, out_s.ctypes.data)
+    out_d = torch.empty((4, n), dtype=torch.float64, device=dev)
+    call([t.data_ptr() for t in d], _lib.DEVICE, out_d.data_ptr())
+    ctx.sync()
+    assert np.array_equal(out_h, out_s) and np.array_equal(out_h, out_d.cpu().numpy())
+    # reference: the oracle's yields, scipy's filter over both axes
+    e1 = {"M%d" % (m + 1): eps1w[m] for m in range(3)}
+    e2 = {"M%d" % (m + 1): eps2w[m] for m in range(3)}
+    ch = {k: chi[i] for i, k in enumerate(cases.CHI2_KEYS)}
+    from tests import util
+    want = orc.yield_points(energy, e1, e2, ch, np.linspace(10, 70, 7)[:, None], 33.0, 12.0, True, util.load_consts())
+    for k, pol in enumerate(cases.POLS):
+        w = orc.gaussian_filter1d(orc.gaussian_filter1d(np.broadcast_to(want[pol], shape), 1.5, axis=0), 1.5, axis=1)
+        assert np.max(np.abs(out_h[k].reshape(shape) - w)) <= 1e-10 * np.max(np.abs(w)), pol
+    # a bad index in a device-resident list: NaN for that point only (sigma_out = 0: no filter spreads it)
+    bad = d[1].clone()
+    bad[5] = 40
+    p = _lib.Points(n=n, nE=40, energy_eV=d[0].data_ptr(), eidx=bad.data_ptr(), theta_deg=d[2].data_ptr(),
+                    phi_deg=d[3].data_ptr(), thick_nm=d[4].data_ptr(), eps1w=d[5].data_ptr(), eps2w=d[6].data_ptr(),
+                    chi2=d[7].data_ptr(), phys=phys)
+    _lib.check(ctx.lib.sshg_yield_points_broadened(ctx.handle, C.byref(p), 0.0, 2, shp, out_d.data_ptr(), _lib.DEVICE), ctx.lib)
+    ctx.sync()
+    got = out_d.cpu().numpy()
+    assert np.isnan(got[:, 5]).all() and np.count_nonzero(np.isnan(got)) == 4
+    with pytest.raises(ValueError):                 # host lists are validated before anything is launched
+        eb = eidx.copy()
+        eb[3] = -1
+        hb = [a.ctypes.data for a in host]
+        hb[1] = eb.ctypes.data
+        call(hb, _lib.HOST, out_h.ctypes.data)
