@@ -173,18 +173,18 @@ __device__ __forceinline__ void or_flag_bits(unsigned* fl, int it, unsigned m) {
 // Node test.  The hot loop is branch-free: besides the stores it compares the HIGH WORDS of the values it produced
 // (the high word of a double orders like the double; a negative value is below everything, a positive NaN above)
 // with the high word of NODE_FRACTION * U of its two energies and collects the outcome of an item in one bit of a
-// mask -- integer compares and a predicated OR, nothing on the FP64 pipe.  After every SWEEP_SB items a non-zero
-// mask (rare) is OR-ed into the CTA's bitmap of flagged rows: fl_lo bit i = the row of item i (i < n_pair: row i),
-// fl_hi bit i = the row i + H of pair item i.
+// mask -- integer minima, one compare and a select, nothing on the FP64 pipe.  After every SWEEP_SB items a non-zero
+// mask (rare) is OR-ed into the CTA's bitmap of flagged ITEMS (bit i = item i of the chunk: its row, or its two rows).
 // One part of a chunk: PAIR items give the rows i (q0) and i + H (q1), the others one un-paired row (q0).
+// One flag bit per ITEM: the minimum of the high words of its (up to four) values against one threshold h -- the
+// larger of the thread's two energies; phase (D) sorts out which row and which energy it was.
 template <bool SS, bool VEC, bool PAIR>
 __device__ __forceinline__ void sweep_part(const double* A0, const double* A1, const double* __restrict__ t, int n, int ibase,
-                                           double* q0, double* q1, long long stride, bool valid1, int h0, int h1,
-                                           unsigned* fl_lo, unsigned* fl_hi) {
+                                           double* q0, double* q1, long long stride, bool valid1, int h, unsigned* fl) {
 #pragma unroll 1
     for (int i0 = 0; i0 < n; i0 += SWEEP_SB) {
         const int nb = min(SWEEP_SB, n - i0);
-        unsigned mlo = 0u, mhi = 0u, bit = 1u;
+        unsigned mask = 0u, bit = 1u;
 #pragma unroll 2
         for (int i = 0; i < nb; ++i) {
             double ye0, ye1, yo0, yo1;
@@ -193,33 +193,27 @@ __device__ __forceinline__ void sweep_part(const double* A0, const double* A1, c
             const double a0 = ye0 + yo0, a1 = ye1 + yo1;
             store2t<VEC>(q0, a0, a1, valid1);
             q0 += stride;
-            if ((__double2hiint(a0) < h0) | (__double2hiint(a1) < h1)) mlo |= bit;
+            int m = min(__double2hiint(a0), __double2hiint(a1));
             if (PAIR) {
                 const double s0 = ye0 - yo0, s1 = ye1 - yo1;
                 store2t<VEC>(q1, s0, s1, valid1);
                 q1 += stride;
-                if (!SS) {
-                    if ((__double2hiint(s0) < h0) | (__double2hiint(s1) < h1)) mhi |= bit;
-                }
+                if (!SS) m = min(m, min(__double2hiint(s0), __double2hiint(s1)));    // sS: the two rows are equal
             }
+            if (m < h) mask |= bit;
             bit += bit;
         }
-        if (SS && PAIR) mhi = mlo;              // sS: the row at phi + 180 deg equals the row at phi
-        if (mlo | mhi) {                        // rare: a value of this block is next to a node
-            or_flag_bits(fl_lo, ibase + i0, mlo);
-            or_flag_bits(fl_hi, ibase + i0, mhi);
-        }
+        if (mask) or_flag_bits(fl, ibase + i0, mask);       // rare: a value of this block is next to a node
     }
 }
 
 template <bool SS, bool VEC>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
                                            int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                           long long stride, bool valid1, int h0, int h1, unsigned* fl_lo,
-                                           unsigned* fl_hi) {
+                                           long long stride, bool valid1, int h, unsigned* fl) {
     // pairs first (rows i and i + H), then the un-paired tail; each part in blocks of SWEEP_SB items
-    sweep_part<SS, VEC, true>(A0, A1, tb, n_pair, 0, plo, phi_, stride, valid1, h0, h1, fl_lo, fl_hi);
-    sweep_part<SS, VEC, false>(A0, A1, tb + 12 * n_pair, n_single, n_pair, psg, nullptr, stride, valid1, h0, h1, fl_lo, fl_hi);
+    sweep_part<SS, VEC, true>(A0, A1, tb, n_pair, 0, plo, phi_, stride, valid1, h, fl);
+    sweep_part<SS, VEC, false>(A0, A1, tb + 12 * n_pair, n_single, n_pair, psg, nullptr, stride, valid1, h, fl);
 }
 
 // the 7 (sS: 4) complex F-basis coefficients of one polarisation (shg.py:218-269, 290-313, 334-351, 372-377)
@@ -340,11 +334,11 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             if (pol == 3) fir_pair<NH_SS>(x, S, R, wf, A0, A1);
             else fir_pair<NH>(x, S, R, wf, A0, A1);
         }
-        int h0 = INT_LOWEST, h1 = INT_LOWEST;   // nothing is ever below: no flags
+        int h = INT_LOWEST;                     // nothing is ever below: no flags
         if (b.fixup && active) {
             const double u0 = amplitude_bound(A0, pol == 3), u1 = valid1 ? amplitude_bound(A1, pol == 3) : 0.0;
-            if (u0 < 1.0e300) h0 = __double2hiint(NODE_FRACTION * u0);      // a NaN / Inf column flags nothing
-            if (valid1 && u1 < 1.0e300) h1 = __double2hiint(NODE_FRACTION * u1);
+            const double u = fmax(u0, u1);      // one threshold for both energies; (D) tests each against its own
+            if (u < 1.0e300) h = __double2hiint(NODE_FRACTION * u);         // a NaN / Inf column flags nothing
         }
 
         // ---- (C) azimuthal sweep, (D) strict re-evaluation of the flagged rows, table chunk by chunk --------
@@ -363,7 +357,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                 double* phi_ = prow + (base + H) * nE;
                 double* psg = prow + (base + n_pair + H) * nE;
 #define SSHG_SWEEP(SS_, VEC_) \
-    sweep_harm<SS_, VEC_>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, valid1, h0, h1, fl, fl + FLW)
+    sweep_harm<SS_, VEC_>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, valid1, h, fl)
                 if (vec) {
                     if (pol == 3) SSHG_SWEEP(true, true);
                     else SSHG_SWEEP(false, true);
@@ -376,8 +370,8 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             __syncthreads();                    // bitmap complete; nobody reads raw or this chunk's table any more
 
             // ---- (D) flagged rows.  The bitmaps are the same for every thread: uniform control flow.
-            // First every thread looks at its own two values of each flagged row again (the arithmetic of the sweep: the
-            // same bits): a value in the band (DEEP, NODE) * U marks the row in the second bitmap `st`; negative rounding
+            // First every thread looks at its own values of each flagged item again (the arithmetic of the sweep: the
+            // same bits): a value in the band (DEEP, NODE) * U marks its row in the second bitmap `st`; negative rounding
             // noise (exact symmetry zeros) is stored again as 0.  Rows marked in `st` are then re-evaluated the
             // reference's way, FX_RB rows at a time; rows that were flagged only by exact zeros are done.
             if (!b.fixup) continue;
@@ -386,16 +380,15 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                 double thr0 = 0.0, thr1 = 0.0;  // NODE_FRACTION * U of this thread's energies (computed on first use)
                 bool have_thr = false;
 #pragma unroll 1
-                for (int wi = 0; wi < 2 * FLW; ++wi) {
+                for (int wi = 0; wi < FLW; ++wi) {
                     unsigned bits = fl[wi];
-                    unsigned mine = 0u;
+                    unsigned mine_lo = 0u, mine_hi = 0u;
 #pragma unroll 1
                     while (bits) {
                         const int bp = __ffs(bits) - 1;
                         bits &= bits - 1;
                         if (!active) continue;
-                        const int part = wi >= FLW ? 1 : 0;
-                        const int item = (wi - part * FLW) * 32 + bp;
+                        const int item = wi * 32 + bp;
                         if (!have_thr) {
                             thr0 = NODE_FRACTION * amplitude_bound(A0, pol == 3);
                             thr1 = valid1 ? NODE_FRACTION * amplitude_bound(A1, pol == 3) : 0.0;
@@ -404,18 +397,24 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                         double ye0, ye1, yo0, yo1;
                         if (pol == 3) harm_item<true>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
                         else harm_item<false>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
-                        const double y0 = part == 1 ? ye0 - yo0 : ye0 + yo0, y1 = part == 1 ? ye1 - yo1 : ye1 + yo1;
                         const double band = DEEP_FRACTION / NODE_FRACTION;
-                        if (((y0 < thr0) & (y0 > band * thr0)) | (valid1 & (y1 < thr1) & (y1 > band * thr1))) {
-                            mine |= 1u << bp;
-                        } else if ((y0 < 0.0) | (valid1 & (y1 < 0.0))) {
-                            const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                            double* dst = out_col + (pol * a.nP + row) * nE;
-                            if (vec) store2t<true>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
-                            else store2t<false>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+#pragma unroll
+                        for (int part = 0; part < 2; ++part) {
+                            if (part == 1 && item >= n_pair) break;         // an un-paired item has one row
+                            const double y0 = part == 1 ? ye0 - yo0 : ye0 + yo0, y1 = part == 1 ? ye1 - yo1 : ye1 + yo1;
+                            if (((y0 < thr0) & (y0 > band * thr0)) | (valid1 & (y1 < thr1) & (y1 > band * thr1))) {
+                                if (part == 1) mine_hi |= 1u << bp;
+                                else mine_lo |= 1u << bp;
+                            } else if ((y0 < 0.0) | (valid1 & (y1 < 0.0))) {
+                                const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
+                                double* dst = out_col + (pol * a.nP + row) * nE;
+                                if (vec) store2t<true>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+                                else store2t<false>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+                            }
                         }
                     }
-                    if (mine) atomicOr(st + wi, mine);
+                    if (mine_lo) atomicOr(st + wi, mine_lo);
+                    if (mine_hi) atomicOr(st + FLW + wi, mine_hi);
                 }
             }
             __syncthreads();                    // `st` complete
