@@ -56,30 +56,19 @@ __host__ __device__ constexpr int blur_flag_words(int chunk) { return chunk / 32
 __host__ __device__ constexpr int blur_fixed_doubles(int radius, int S) {
     return 2 * radius + 2 + (NCOL + NH) * S + FX_RB * 6;
 }
-// a chunk of the phi table: 12 doubles per item, in front of it four bitmaps (flagged / strict rows x two parts; 4 x words x 4 B)
-__host__ __device__ constexpr int blur_chunk_doubles(int chunk) { return chunk * 12 + 2 * blur_flag_words(chunk); }
+// a chunk of the phi table: 12 doubles per item, in front of it the bitmaps (flagged items; strict rows of the four row
+// kinds of an item): 6 x words x 4 B reserved
+__host__ __device__ constexpr int blur_chunk_doubles(int chunk) { return chunk * 12 + 3 * blur_flag_words(chunk) + (blur_flag_words(chunk) & 1); }
 
 __global__ void phi_harm_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
-                                      int allow_pairs) {
-    __shared__ int bad;
-    const long long H = nP / 2;
-    if (threadIdx.x == 0) bad = (allow_pairs && H > 0) ? 0 : 1;
-    __syncthreads();
-    if (allow_pairs && H > 0) {
-        int mybad = 0;
-        for (long long j = threadIdx.x; j < H; j += blockDim.x)
-            if (phi[j + H] != phi[j] + 180.0) mybad = 1;
-        if (mybad) bad = 1;
-    }
-    __syncthreads();
-    const long long h = bad ? 0 : H;
-    if (threadIdx.x == 0) tab[0] = (double)h;
-    const long long items = nP - h;
+                                      int allow_pairs, int allow_quads) {
+    const PhiItems it = phi_items_build(phi, nP, tab, allow_pairs, allow_quads);
+    const long long items = it.total();
     for (long long i = threadIdx.x; i < items; i += blockDim.x) {
         double t[12];
-        phi_harmonics(phi[i < h ? i : i + h], t);
+        phi_harmonics(phi[phi_item_row(it, i)], t);
 #pragma unroll
-        for (int k = 0; k < 12; ++k) tab[2 + i * 12 + k] = t[k];     // items start 16-byte aligned
+        for (int k = 0; k < 12; ++k) tab[TAB_HDR + i * 12 + k] = t[k];
     }
 }
 
@@ -159,6 +148,35 @@ __device__ __forceinline__ void harm_item(const double* A0, const double* A1, co
     }
 }
 
+// One QUAD item of the harmonic form for two energies: the four rows phi (a), 180 - phi (b), phi + 180 (c), 360 - phi (d)
+// from four partial sums -- even / odd harmonics x cosine / sine terms: 20 FP64 instructions per energy for four points
+// (sS, even harmonics only: 8).  tb as in harm_item.
+template <bool SS>
+__device__ __forceinline__ void harm_quad(const double* A, const double* __restrict__ tb, double& ya, double& yb, double& yc,
+                                          double& yd) {
+    double t[12];
+#pragma unroll
+    for (int j = 0; j < (SS ? 3 : 6); ++j) {
+        const double2 v = *reinterpret_cast<const double2*>(tb + 2 * j);
+        t[2 * j] = v.x;
+        t[2 * j + 1] = v.y;
+    }
+    const double ec = fma(A[5], t[4], fma(A[3], t[2], fma(A[1], t[0], A[0])));       // C0 + C2 c2 + C4 c4 + C6 c6
+    const double es = fma(A[6], t[5], fma(A[4], t[3], A[2] * t[1]));                 // S2 s2 + S4 s4 + S6 s6
+    const double p = ec + es, m = ec - es;
+    if (SS) {
+        ya = p; yc = p; yb = m; yd = m;
+        return;
+    }
+    const double oc = fma(A[11], t[10], fma(A[9], t[8], A[7] * t[6]));              // C1 c1 + C3 c3 + C5 c5
+    const double os = fma(A[12], t[11], fma(A[10], t[9], A[8] * t[7]));             // S1 s1 + S3 s3 + S5 s5
+    const double u = oc + os, v = oc - os;
+    ya = p + u;                                 // phi
+    yc = p - u;                                 // phi + 180: odd harmonics flip
+    yd = m + v;                                 // 360 - phi: sine terms flip
+    yb = m - v;                                 // 180 - phi: both
+}
+
 // mask bit k = item (it + k) of the chunk; rare path of the sweep
 __device__ __forceinline__ void or_flag_bits(unsigned* fl, int it, unsigned m) {
     if (!m) return;
@@ -207,13 +225,49 @@ __device__ __forceinline__ void sweep_part(const double* A0, const double* A1, c
     }
 }
 
+// The quad items of a chunk: rows ascend from pa (phi) and pc (phi + 180) and descend from pb (180 - phi) and pd (360 - phi).
 template <bool SS, bool VEC>
-__device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb,
-                                           int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                           long long stride, bool valid1, int h, unsigned* fl) {
-    // pairs first (rows i and i + H), then the un-paired tail; each part in blocks of SWEEP_SB items
-    sweep_part<SS, VEC, true>(A0, A1, tb, n_pair, 0, plo, phi_, stride, valid1, h, fl);
-    sweep_part<SS, VEC, false>(A0, A1, tb + 12 * n_pair, n_single, n_pair, psg, nullptr, stride, valid1, h, fl);
+__device__ __forceinline__ void sweep_quads(const double* A0, const double* A1, const double* __restrict__ t, int n, double* pa,
+                                            double* pb, double* pc, double* pd, long long stride, bool valid1, int h,
+                                            unsigned* fl) {
+#pragma unroll 1
+    for (int i0 = 0; i0 < n; i0 += SWEEP_SB) {
+        const int nb = min(SWEEP_SB, n - i0);
+        unsigned mask = 0u, bit = 1u;
+#pragma unroll 2
+        for (int i = 0; i < nb; ++i) {
+            double a0, b0, c0, d0, a1, b1, c1, d1;
+            harm_quad<SS>(A0, t, a0, b0, c0, d0);
+            harm_quad<SS>(A1, t, a1, b1, c1, d1);
+            t += 12;
+            store2t<VEC>(pa, a0, a1, valid1);
+            store2t<VEC>(pb, b0, b1, valid1);
+            store2t<VEC>(pc, c0, c1, valid1);
+            store2t<VEC>(pd, d0, d1, valid1);
+            pa += stride;
+            pc += stride;
+            pb -= stride;
+            pd -= stride;
+            int m = min(min(__double2hiint(a0), __double2hiint(a1)), min(__double2hiint(b0), __double2hiint(b1)));
+            if (!SS) m = min(m, min(min(__double2hiint(c0), __double2hiint(c1)), min(__double2hiint(d0), __double2hiint(d1))));
+            if (m < h) mask |= bit;
+            bit += bit;
+        }
+        if (mask) or_flag_bits(fl, i0, mask);
+    }
+}
+
+// A chunk of the item list: nq quads (first quad: rows q0 + 1, ...), np pair items (first: pair item p0), ns un-paired rows
+// (first: row 2 H + s0); prow = this thread's energies in row 0 of the polarisation.
+template <bool SS, bool VEC>
+__device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb, const PhiItems& it,
+                                           int nq, long long q0, int np, long long p0, int ns, long long s0, double* prow,
+                                           long long nE, bool valid1, int h, unsigned* fl) {
+    sweep_quads<SS, VEC>(A0, A1, tb, nq, prow + (q0 + 1) * nE, prow + (it.H - q0 - 1) * nE, prow + (q0 + 1 + it.H) * nE,
+                         prow + (2 * it.H - q0 - 1) * nE, nE, valid1, h, fl);
+    sweep_part<SS, VEC, true>(A0, A1, tb + 12 * nq, np, nq, prow + p0 * it.PSTEP * nE, prow + (p0 * it.PSTEP + it.H) * nE,
+                              it.PSTEP * nE, valid1, h, fl);
+    sweep_part<SS, VEC, false>(A0, A1, tb + 12 * (nq + np), ns, nq + np, prow + (2 * it.H + s0) * nE, nullptr, nE, valid1, h, fl);
 }
 
 // the 7 (sS: 4) complex F-basis coefficients of one polarisation (shg.py:218-269, 290-313, 334-351, 372-377)
@@ -291,8 +345,8 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
     const long long e0 = tile_e0 + (long long)tid * EPT;
     const bool active = e0 < nE;
     const bool valid1 = e0 + 1 < nE;
-    const long long H = (long long)a.tab[0];
-    const long long items = a.nP - H;
+    const PhiItems it = read_phi_items(a.tab, a.nP);
+    const long long items = it.total();
     const bool vec = a.vec_ok != 0;
     const long long rows_per_pol = a.nP * nE;
     double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
@@ -300,6 +354,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
     const long long seg_lo = seg * seg_len, seg_hi = min(items, (seg + 1) * seg_len);
     const bool one_chunk = seg_hi - seg_lo <= CH;               // the whole table of this CTA fits: staged once
     const int INT_LOWEST = (int)0x80000000;
+    unsigned* st = fl + FLW;                    // [4][FLW] strict rows of the row kinds a, b, c, d
 
 #pragma unroll 1
     for (int pol = 0; pol < 4; ++pol) {
@@ -346,18 +401,18 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
         for (long long base = seg_lo; base < seg_hi; base += CH) {
             const int n_items = (int)min((long long)CH, seg_hi - base);
             if (!one_chunk || pol == 0)         // (every thread is past the previous chunk: barrier at the end of the loop)
-                for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[2 + base * 12 + i];
-            for (int i = tid; i < 4 * FLW; i += NT) fl[i] = 0u;     // flagged rows and (D)'s strict rows
+                for (int i = tid; i < n_items * 12; i += NT) tabs[i] = a.tab[TAB_HDR + base * 12 + i];
+            for (int i = tid; i < 5 * FLW; i += NT) fl[i] = 0u;     // flagged items and (D)'s strict rows
             __syncthreads();
-            const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
-            const int n_single = n_items - n_pair;
+            // the kinds of item in [base, base + n_items): quads, then pair items, then un-paired rows
+            const long long q0 = min(base, it.Q), q1 = min(base + n_items, it.Q);
+            const long long p0 = min(max(base - it.Q, 0LL), it.NPI), p1 = min(max(base + n_items - it.Q, 0LL), it.NPI);
+            const long long s0 = max(base - it.Q - it.NPI, 0LL);
+            const int nq = (int)(q1 - q0), np = (int)(p1 - p0), ns = n_items - nq - np;
+            double* prow = out_col + pol * rows_per_pol;
             if (active) {
-                double* prow = out_col + pol * rows_per_pol;
-                double* plo = prow + base * nE;
-                double* phi_ = prow + (base + H) * nE;
-                double* psg = prow + (base + n_pair + H) * nE;
 #define SSHG_SWEEP(SS_, VEC_) \
-    sweep_harm<SS_, VEC_>(A0, A1, tabs, n_pair, n_single, plo, phi_, psg, nE, valid1, h, fl)
+    sweep_harm<SS_, VEC_>(A0, A1, tabs, it, nq, q0, np, p0, ns, s0, prow, nE, valid1, h, fl)
                 if (vec) {
                     if (pol == 3) SSHG_SWEEP(true, true);
                     else SSHG_SWEEP(false, true);
@@ -369,20 +424,28 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             }
             __syncthreads();                    // bitmap complete; nobody reads raw or this chunk's table any more
 
-            // ---- (D) flagged rows.  The bitmaps are the same for every thread: uniform control flow.
+            // ---- (D) flagged items.  The bitmaps are the same for every thread: uniform control flow.
             // First every thread looks at its own values of each flagged item again (the arithmetic of the sweep: the
-            // same bits): a value in the band (DEEP, NODE) * U marks its row in the second bitmap `st`; negative rounding
+            // same bits): a value in the band (DEEP, NODE) * U marks its row in the bitmaps `st`; negative rounding
             // noise (exact symmetry zeros) is stored again as 0.  Rows marked in `st` are then re-evaluated the
             // reference's way, FX_RB rows at a time; rows that were flagged only by exact zeros are done.
             if (!b.fixup) continue;
-            unsigned* st = fl + 2 * FLW;        // [2][FLW], cleared with fl
+            // row of kind k (0: phi, 1: 180 - phi, 2: phi + 180, 3: 360 - phi) of chunk item `item`
+            auto item_row = [&](int item, int k) -> long long {
+                if (item < nq) {
+                    const long long j = q0 + item + 1;
+                    return k == 0 ? j : k == 1 ? it.H - j : k == 2 ? j + it.H : 2 * it.H - j;
+                }
+                if (item < nq + np) return (p0 + item - nq) * it.PSTEP + (k == 2 ? it.H : 0);
+                return 2 * it.H + s0 + (item - nq - np);
+            };
             {
                 double thr0 = 0.0, thr1 = 0.0;  // NODE_FRACTION * U of this thread's energies (computed on first use)
                 bool have_thr = false;
 #pragma unroll 1
                 for (int wi = 0; wi < FLW; ++wi) {
                     unsigned bits = fl[wi];
-                    unsigned mine_lo = 0u, mine_hi = 0u;
+                    unsigned mine[4] = {0u, 0u, 0u, 0u};
 #pragma unroll 1
                     while (bits) {
                         const int bp = __ffs(bits) - 1;
@@ -394,47 +457,58 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                             thr1 = valid1 ? NODE_FRACTION * amplitude_bound(A1, pol == 3) : 0.0;
                             have_thr = true;
                         }
-                        double ye0, ye1, yo0, yo1;
-                        if (pol == 3) harm_item<true>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
-                        else harm_item<false>(A0, A1, tabs + 12 * item, ye0, ye1, yo0, yo1);
+                        double y0[4], y1[4];    // this thread's values of the item's rows a, b, c, d
+                        const double* tb = tabs + 12 * item;
+                        unsigned kinds;         // which of the four exist for this item
+                        if (item < nq) {
+                            if (pol == 3) { harm_quad<true>(A0, tb, y0[0], y0[1], y0[2], y0[3]); harm_quad<true>(A1, tb, y1[0], y1[1], y1[2], y1[3]); }
+                            else { harm_quad<false>(A0, tb, y0[0], y0[1], y0[2], y0[3]); harm_quad<false>(A1, tb, y1[0], y1[1], y1[2], y1[3]); }
+                            kinds = 0xFu;
+                        } else {
+                            double ye0, ye1, yo0, yo1;
+                            if (pol == 3) harm_item<true>(A0, A1, tb, ye0, ye1, yo0, yo1);
+                            else harm_item<false>(A0, A1, tb, ye0, ye1, yo0, yo1);
+                            y0[0] = ye0 + yo0; y1[0] = ye1 + yo1;
+                            y0[2] = ye0 - yo0; y1[2] = ye1 - yo1;
+                            y0[1] = y0[3] = y1[1] = y1[3] = 0.0;
+                            kinds = item < nq + np ? 0x5u : 0x1u;
+                        }
                         const double band = DEEP_FRACTION / NODE_FRACTION;
 #pragma unroll
-                        for (int part = 0; part < 2; ++part) {
-                            if (part == 1 && item >= n_pair) break;         // an un-paired item has one row
-                            const double y0 = part == 1 ? ye0 - yo0 : ye0 + yo0, y1 = part == 1 ? ye1 - yo1 : ye1 + yo1;
-                            if (((y0 < thr0) & (y0 > band * thr0)) | (valid1 & (y1 < thr1) & (y1 > band * thr1))) {
-                                if (part == 1) mine_hi |= 1u << bp;
-                                else mine_lo |= 1u << bp;
-                            } else if ((y0 < 0.0) | (valid1 & (y1 < 0.0))) {
-                                const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                                double* dst = out_col + (pol * a.nP + row) * nE;
-                                if (vec) store2t<true>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
-                                else store2t<false>(dst, fmax(y0, 0.0), fmax(y1, 0.0), valid1);
+                        for (int k = 0; k < 4; ++k) {
+                            if (!((kinds >> k) & 1u)) continue;
+                            const double v0 = y0[k], v1 = y1[k];
+                            if (((v0 < thr0) & (v0 > band * thr0)) | (valid1 & (v1 < thr1) & (v1 > band * thr1))) {
+                                mine[k] |= 1u << bp;
+                            } else if ((v0 < 0.0) | (valid1 & (v1 < 0.0))) {
+                                double* dst = prow + item_row(item, k) * nE;
+                                if (vec) store2t<true>(dst, fmax(v0, 0.0), fmax(v1, 0.0), valid1);
+                                else store2t<false>(dst, fmax(v0, 0.0), fmax(v1, 0.0), valid1);
                             }
                         }
                     }
-                    if (mine_lo) atomicOr(st + wi, mine_lo);
-                    if (mine_hi) atomicOr(st + FLW + wi, mine_hi);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (mine[k]) atomicOr(st + k * FLW + wi, mine[k]);
                 }
             }
             __syncthreads();                    // `st` complete
             int rows[FX_RB], nb = 0;
 #pragma unroll 1
-            for (int wi = 0; wi <= 2 * FLW; ++wi) {
-                unsigned bits = wi < 2 * FLW ? st[wi] : 0u;
-                const bool last = wi == 2 * FLW;
+            for (int wi = 0; wi <= 4 * FLW; ++wi) {
+                unsigned bits = wi < 4 * FLW ? st[wi] : 0u;
+                const bool last = wi == 4 * FLW;
 #pragma unroll 1
                 while (bits || (last && nb > 0)) {
                     if (bits) {
                         const int bp = __ffs(bits) - 1;
                         bits &= bits - 1;
-                        const int part = wi >= FLW ? 1 : 0;
-                        const int item = (wi - part * FLW) * 32 + bp;
-                        const long long row = (part == 1 || item >= n_pair) ? base + item + H : base + item;
-                        rows[nb] = (int)row;
+                        const int kind = wi / FLW;
+                        const int item = (wi - kind * FLW) * 32 + bp;
+                        rows[nb] = (int)item_row(item, kind);
                         if (tid == nb) {        // basis row of this azimuth from the staged table: cos / sin of phi are its
-                            const double* t = tabs + 12 * item;          // first odd harmonic; phi + 180 deg flips both
-                            const double c = part == 1 && item < n_pair ? -t[6] : t[6], sn = part == 1 && item < n_pair ? -t[7] : t[7];
+                            const double* t = tabs + 12 * item;          // first odd harmonic; the row kind sets their signs
+                            const double c = (kind == 1 || kind == 2) ? -t[6] : t[6], sn = (kind == 2 || kind == 3) ? -t[7] : t[7];
                             double* bb = pb + nb * 6;
                             bb[0] = c * c;
                             bb[1] = sn * c;
@@ -486,13 +560,13 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                     // -- ... filtered along E (four rows at a time: one LDS.128 feeds 4 FMAs) and stored
                     if (active) {
 #pragma unroll 1
-                        for (int q0 = 0; q0 < nb; q0 += 4) {
+                        for (int r0 = 0; r0 < nb; r0 += 4) {
                             double o0[4], o1[4];
-                            fir_pair<4>(rowbuf + q0 * S + tid * EPT, S, R, wf, o0, o1);
+                            fir_pair<4>(rowbuf + r0 * S + tid * EPT, S, R, wf, o0, o1);
 #pragma unroll
                             for (int q = 0; q < 4; ++q)
-                                if (q0 + q < nb) {
-                                    double* dst = out_col + (pol * a.nP + (long long)rows[q0 + q]) * nE;
+                                if (r0 + q < nb) {
+                                    double* dst = prow + (long long)rows[r0 + q] * nE;
                                     if (vec) store2t<true>(dst, o0[q], o1[q], valid1);
                                     else store2t<false>(dst, o0[q], o1[q], valid1);
                                 }
@@ -502,7 +576,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                     nb = 0;
                 }
             }
-            __syncthreads();                    // every thread has read the bitmap before the next chunk clears it
+            __syncthreads();                    // every thread has read the bitmaps before the next chunk clears them
         }
     }
 }

@@ -39,6 +39,7 @@ struct sshg_options {
     int nseg;           // phi segments per column (1 .. 16)
     int k1_generic;     // 1: never use the fixed-radius FIR kernels
     int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
+    int quads;          // 0: no four-row items (phi, 180 - phi, phi + 180, 360 - phi) in the azimuthal sweeps
 };
 
 // A recorded small call: copy in -> yield_points_kernel -> FIR passes -> copy out, keyed on everything the recorded

@@ -74,30 +74,84 @@ __device__ __forceinline__ void store2t(double* p, double y0, double y1, bool va
     }
 }
 
-// phi table: tab[0] = H (number of (phi, phi+180) pairs), tab[1] unused, then item rows of 6 doubles (16-byte aligned).
-// item i < H      -> rows i and i + H of the cube, basis of phi[i]
-// item i >= H     -> row i + H (the un-paired tail), basis of phi[i + H]
-__global__ void phi_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
-                                 int allow_pairs) {
-    __shared__ int bad;
+// The phi item list of a sweep, built on the device (exact comparisons in degrees):
+//   tab[0] = H      (phi, phi + 180 deg) row pairs: rows j and j + H, j < H           (0: the grid has no such pairing)
+//   tab[1] = Q      quad items: phi_j, 180 - phi_j, phi_j + 180 and 360 - phi_j are all on the grid -- rows j, H - j,
+//                   j + H, 2 H - j for j = 1 .. Q (true for linspace(0, 360, 721), arange(0, 360), ...)
+//   tab[2] = NPI    pair items, tab[3] = PSTEP: pair item k owns the rows k PSTEP and k PSTEP + H (with quads: the
+//                   self-mirrored angles 0 and 90 deg; without: every j < H)
+//   items from tab[4] (16-byte aligned): the quads, then the pairs, then the un-paired rows 2 H, 2 H + 1, ...
+// One evaluation of an item gives all its rows.  K2's basis {1, c^2, sc | c^3, sc^2, s^2 c, s^3}: the first three are
+// unchanged and the last four flip under phi -> phi + 180 deg; under phi -> 180 - phi (c -> -c) sc, c^3 and s^2 c flip.
+// K3's harmonics: cos(q phi) is even and sin(q phi) odd under phi -> -phi, even-q harmonics are unchanged and odd-q
+// ones flip under phi -> phi + 180 deg.
+constexpr int TAB_HDR = 4;
+struct PhiItems {
+    long long H, Q, NPI, PSTEP, NS;
+    __device__ __forceinline__ long long total() const { return Q + NPI + NS; }
+};
+__device__ __forceinline__ PhiItems read_phi_items(const double* __restrict__ tab, long long nP) {
+    PhiItems it;
+    it.H = (long long)tab[0];
+    it.Q = (long long)tab[1];
+    it.NPI = (long long)tab[2];
+    it.PSTEP = (long long)tab[3];
+    it.NS = nP - 2 * it.H;
+    return it;
+}
+// base-angle row of item i
+__device__ __forceinline__ long long phi_item_row(const PhiItems& it, long long i) {
+    if (i < it.Q) return i + 1;
+    if (i < it.Q + it.NPI) return (i - it.Q) * it.PSTEP;
+    return 2 * it.H + (i - it.Q - it.NPI);
+}
+
+// Decides the structure of the grid and writes the header; every thread of the (single) CTA returns the same PhiItems.
+__device__ __forceinline__ PhiItems phi_items_build(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
+                                                    int allow_pairs, int allow_quads) {
+    __shared__ int bad_pair, bad_quad;
     const long long H = nP / 2;
-    if (threadIdx.x == 0) bad = (allow_pairs && H > 0) ? 0 : 1;
-    __syncthreads();
-    if (allow_pairs && H > 0) {
-        int mybad = 0;
-        for (long long j = threadIdx.x; j < H; j += blockDim.x)
-            if (phi[j + H] != phi[j] + 180.0) mybad = 1;
-        if (mybad) bad = 1;
+    if (threadIdx.x == 0) {
+        bad_pair = (allow_pairs && H > 0) ? 0 : 1;
+        bad_quad = (allow_quads && H >= 3) ? 0 : 1;
     }
     __syncthreads();
-    const long long h = bad ? 0 : H;
-    if (threadIdx.x == 0) tab[0] = (double)h;
-    const long long items = nP - h;
+    if (allow_pairs && H > 0) {
+        int bp = 0, bq = 0;
+        for (long long j = threadIdx.x; j < H; j += blockDim.x) {
+            if (phi[j + H] != phi[j] + 180.0) bp = 1;
+            if (j >= 1 && phi[H - j] != 180.0 - phi[j]) bq = 1;
+        }
+        if (bp) bad_pair = 1;
+        if (bq) bad_quad = 1;
+    }
+    __syncthreads();
+    PhiItems it;
+    it.H = bad_pair ? 0 : H;
+    const bool quads = !bad_pair && !bad_quad;
+    it.Q = quads ? (H - 1) / 2 : 0;
+    it.NPI = quads ? H - 2 * it.Q : it.H;
+    it.PSTEP = quads ? (it.NPI > 1 ? H / 2 : 1) : 1;
+    it.NS = nP - 2 * it.H;
+    if (threadIdx.x == 0) {
+        tab[0] = (double)it.H;
+        tab[1] = (double)it.Q;
+        tab[2] = (double)it.NPI;
+        tab[3] = (double)it.PSTEP;
+    }
+    return it;
+}
+
+// K2's table: items of 6 doubles {c^2, s c, c^3, s c^2, s^2 c, s^3} of the item's base angle.
+__global__ void phi_table_kernel(const double* __restrict__ phi, long long nP, double* __restrict__ tab,
+                                 int allow_pairs, int allow_quads) {
+    const PhiItems it = phi_items_build(phi, nP, tab, allow_pairs, allow_quads);
+    const long long items = it.total();
     for (long long i = threadIdx.x; i < items; i += blockDim.x) {
         double b[6];
-        phi_basis(phi[i < h ? i : i + h], b);
+        phi_basis(phi[phi_item_row(it, i)], b);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) tab[2 + i * 6 + k] = b[k];
+        for (int k = 0; k < 6; ++k) tab[TAB_HDR + i * 6 + k] = b[k];
     }
 }
 
@@ -109,7 +163,7 @@ struct Coef7 {
 template <bool VEC>
 __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const double* __restrict__ tb,
                                        int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                       long long stride, bool valid1) {
+                                       long long stride, long long pair_stride, bool valid1) {
 #pragma unroll 2
     for (int i = 0; i < n_pair; ++i) {
         const double b0 = tb[0], b1 = tb[1], b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
@@ -126,8 +180,8 @@ __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const d
         double ar1 = er1 + or1, ai1 = ei1 + oi1, sr1 = er1 - or1, si1 = ei1 - oi1;
         store2t<VEC>(plo, fma(ar0, ar0, ai0 * ai0), fma(ar1, ar1, ai1 * ai1), valid1);
         store2t<VEC>(phi_, fma(sr0, sr0, si0 * si0), fma(sr1, sr1, si1 * si1), valid1);
-        plo += stride;
-        phi_ += stride;
+        plo += pair_stride;
+        phi_ += pair_stride;
     }
 #pragma unroll 2
     for (int i = 0; i < n_single; ++i) {
@@ -146,6 +200,45 @@ __device__ __forceinline__ void sweep7(const Coef7& k0, const Coef7& k1, const d
     }
 }
 
+// (C) quad items of a 7-term polarisation: the four rows phi (a), 180 - phi (b), phi + 180 (c), 360 - phi (d) from the
+// four parts of r -- even / odd under phi + 180 x even / odd under 180 - phi: 36 FP64 instructions per energy for four
+// points (9 per point instead of 10).  Rows ascend from pa and pc and descend from pb and pd.
+template <bool VEC>
+__device__ __forceinline__ void sweep7_quads(const Coef7& k0, const Coef7& k1, const double* __restrict__ tb, int n,
+                                             double* pa, double* pb, double* pc, double* pd, long long stride, bool valid1) {
+    auto rows4 = [](const Coef7& k, double b0, double b1, double b2, double b3, double b4, double b5, double& ya, double& yb,
+                    double& yc, double& yd) {
+        const double epr = fma(k.r[1], b0, k.r[0]), epi = fma(k.i[1], b0, k.i[0]);           // 1, c^2
+        const double emr = k.r[2] * b1, emi = k.i[2] * b1;                                   // s c
+        const double opr = fma(k.r[6], b5, k.r[4] * b3), opi = fma(k.i[6], b5, k.i[4] * b3); // s c^2, s^3
+        const double omr = fma(k.r[5], b4, k.r[3] * b2), omi = fma(k.i[5], b4, k.i[3] * b2); // c^3, s^2 c
+        const double Epr = epr + emr, Epi = epi + emi, Emr = epr - emr, Emi = epi - emi;
+        const double Opr = opr + omr, Opi = opi + omi, Omr = opr - omr, Omi = opi - omi;
+        const double ar = Epr + Opr, ai = Epi + Opi, cr = Epr - Opr, ci = Epi - Opi;
+        const double br = Emr + Omr, bi = Emi + Omi, dr = Emr - Omr, di = Emi - Omi;
+        ya = fma(ar, ar, ai * ai);
+        yb = fma(br, br, bi * bi);
+        yc = fma(cr, cr, ci * ci);
+        yd = fma(dr, dr, di * di);
+    };
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const double b0 = tb[0], b1 = tb[1], b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
+        tb += 6;
+        double a0, b0y, c0, d0, a1, b1y, c1, d1;
+        rows4(k0, b0, b1, b2, b3, b4, b5, a0, b0y, c0, d0);
+        rows4(k1, b0, b1, b2, b3, b4, b5, a1, b1y, c1, d1);
+        store2t<VEC>(pa, a0, a1, valid1);
+        store2t<VEC>(pb, b0y, b1y, valid1);
+        store2t<VEC>(pc, c0, c1, valid1);
+        store2t<VEC>(pd, d0, d1, valid1);
+        pa += stride;
+        pc += stride;
+        pb -= stride;
+        pd -= stride;
+    }
+}
+
 struct Coef4 {
     double r[4], i[4];
 };
@@ -154,7 +247,7 @@ struct Coef4 {
 template <bool VEC>
 __device__ __forceinline__ void sweep4(const Coef4& k0, const Coef4& k1, const double* __restrict__ tb,
                                        int n_pair, int n_single, double* plo, double* phi_, double* psg,
-                                       long long stride, bool valid1) {
+                                       long long stride, long long pair_stride, bool valid1) {
 #pragma unroll 2
     for (int i = 0; i < n_pair + n_single; ++i) {
         const double b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
@@ -167,12 +260,41 @@ __device__ __forceinline__ void sweep4(const Coef4& k0, const Coef4& k1, const d
         if (i < n_pair) {
             store2t<VEC>(plo, y0, y1, valid1);
             store2t<VEC>(phi_, y0, y1, valid1);
-            plo += stride;
-            phi_ += stride;
+            plo += pair_stride;
+            phi_ += pair_stride;
         } else {
             store2t<VEC>(psg, y0, y1, valid1);
             psg += stride;
         }
+    }
+}
+
+// (C) quad items of sS (odd part only): rows a and c are equal, and so are b and d.
+template <bool VEC>
+__device__ __forceinline__ void sweep4_quads(const Coef4& k0, const Coef4& k1, const double* __restrict__ tb, int n,
+                                             double* pa, double* pb, double* pc, double* pd, long long stride, bool valid1) {
+    auto rows2 = [](const Coef4& k, double b2, double b3, double b4, double b5, double& ya, double& yb) {
+        const double opr = fma(k.r[3], b5, k.r[1] * b3), opi = fma(k.i[3], b5, k.i[1] * b3); // s c^2, s^3
+        const double omr = fma(k.r[2], b4, k.r[0] * b2), omi = fma(k.i[2], b4, k.i[0] * b2); // c^3, s^2 c
+        const double ar = opr + omr, ai = opi + omi, br = opr - omr, bi = opi - omi;
+        ya = fma(ar, ar, ai * ai);
+        yb = fma(br, br, bi * bi);
+    };
+#pragma unroll 2
+    for (int i = 0; i < n; ++i) {
+        const double b2 = tb[2], b3 = tb[3], b4 = tb[4], b5 = tb[5];
+        tb += 6;
+        double a0, b0y, a1, b1y;
+        rows2(k0, b2, b3, b4, b5, a0, b0y);
+        rows2(k1, b2, b3, b4, b5, a1, b1y);
+        store2t<VEC>(pa, a0, a1, valid1);
+        store2t<VEC>(pc, a0, a1, valid1);
+        store2t<VEC>(pb, b0y, b1y, valid1);
+        store2t<VEC>(pd, b0y, b1y, valid1);
+        pa += stride;
+        pc += stride;
+        pb -= stride;
+        pd -= stride;
     }
 }
 
@@ -225,8 +347,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
         }
     }
 
-    const long long H = (long long)a.tab[0];
-    const long long items = a.nP - H;
+    const PhiItems it = read_phi_items(a.tab, a.nP);
+    const long long items = it.total();
     const bool vec = a.vec_ok != 0;
     const long long rows_per_pol = a.nP * nE;
     double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
@@ -248,20 +370,28 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
     for (long long base = seg * seg_len; base < seg_hi; base += CHUNK) {
         const int n_items = (int)min((long long)CHUNK, seg_hi - base);
         __syncthreads();                        // previous chunk fully consumed; columns parked
-        for (int i = tid; i < n_items * 6; i += NT) tabs[i] = a.tab[2 + base * 6 + i];
+        for (int i = tid; i < n_items * 6; i += NT) tabs[i] = a.tab[TAB_HDR + base * 6 + i];
         __syncthreads();
         if (!active) continue;
-        // items [base, base + n_items): pairs are the items below H
-        const int n_pair = (int)max(0LL, min((long long)n_items, H - base));
-        const int n_single = n_items - n_pair;
-        const long long first_single_item = base + n_pair;       // >= H when n_single > 0
+        // the kinds of item in [base, base + n_items): quads, then pair items, then un-paired rows
+        const long long q0 = min(base, it.Q), q1 = min(base + n_items, it.Q);
+        const long long p0 = min(max(base - it.Q, 0LL), it.NPI), p1 = min(max(base + n_items - it.Q, 0LL), it.NPI);
+        const long long s0 = max(base - it.Q - it.NPI, 0LL);
+        const int nq = (int)(q1 - q0), np = (int)(p1 - p0), ns = n_items - nq - np;
+        const double* tq = tabs;
+        const double* tp = tabs + 6 * nq;       // pair items, then singles
 
 #pragma unroll 1
         for (int pol = 0; pol < 4; ++pol) {
             double* prow = out_col + pol * rows_per_pol;
-            double* plo = prow + base * nE;                      // row = item           (item < H)
-            double* phi_ = prow + (base + H) * nE;               // row = item + H
-            double* psg = prow + (first_single_item + H) * nE;   // row = item + H       (item >= H)
+            double* pa = prow + (q0 + 1) * nE;                           // quads: rows j, H - j, j + H, 2 H - j
+            double* pb = prow + (it.H - q0 - 1) * nE;
+            double* pc = prow + (q0 + 1 + it.H) * nE;
+            double* pd = prow + (2 * it.H - q0 - 1) * nE;
+            double* plo = prow + p0 * it.PSTEP * nE;                     // pair item k: rows k PSTEP and k PSTEP + H
+            double* phi_ = prow + (p0 * it.PSTEP + it.H) * nE;
+            double* psg = prow + (2 * it.H + s0) * nE;                   // un-paired rows
+            const long long pstride = it.PSTEP * nE;
             if (pol == 3) {
                 Coef4 k[2];
 #pragma unroll
@@ -273,8 +403,13 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
-                if (vec) sweep4<true>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
-                else sweep4<false>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
+                if (vec) {
+                    sweep4_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    sweep4<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                } else {
+                    sweep4_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    sweep4<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                }
             } else {
                 Coef7 k[2];
 #pragma unroll
@@ -289,8 +424,13 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 #pragma unroll
                     for (int j = 0; j < 7; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
-                if (vec) sweep7<true>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
-                else sweep7<false>(k[0], k[1], tabs, n_pair, n_single, plo, phi_, psg, nE, valid1);
+                if (vec) {
+                    sweep7_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    sweep7<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                } else {
+                    sweep7_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    sweep7<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                }
             }
         }
     }
@@ -579,10 +719,10 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     const bool two_pass = radius >= 1 && !fused;
 
     void* tab;
-    if (int rc = sshg_scratch(ctx, 7, (size_t)(2 + 12 * p->nP) * 8, &tab)) return rc;
+    if (int rc = sshg_scratch(ctx, 7, (size_t)(4 + 12 * p->nP) * 8, &tab)) return rc;
     a.tab = (const double*)tab;
-    if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
-    else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1);
+    if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, opt.quads == 0 ? 0 : 1);
+    else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, opt.quads == 0 ? 0 : 1);
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
 

@@ -34,8 +34,8 @@ for name, args, t_range, shape in (("config3", c3, None, (90, 1, 4, 360, 2000)),
     out = torch.empty(shape, dtype=torch.float64, device=dev)
     for sigma in (0.0, 2.0, 5.0, 12.0):
         med, best = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 9)
-        with _lib.context(0).options(k3_nt=64):     # 128-energy tiles
+        with _lib.context(0).options(quads=0):      # pairs (phi, phi + 180) only, no four-row items
             med1, best1 = timed(lambda: grid.yield_grid_device(*args, out=out, consts=consts, t_range=t_range, sigma_out=sigma), 9)
         print(json.dumps({"tag": tag, "case": name, "sigma_out": sigma, "ms_median": round(med, 4), "ms_best": round(best, 4),
-                          "store_gbs": round(8e-9 * out.numel() / (med * 1e-3)), "ms_median_k3_nt64": round(med1, 4)}), flush=True)
+                          "store_gbs": round(8e-9 * out.numel() / (med * 1e-3)), "ms_median_no_quads": round(med1, 4)}), flush=True)
     del out
