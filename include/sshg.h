@@ -143,7 +143,7 @@ SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by
  *   "k1_generic"    0 | 1     generic instead of fixed-radius FIR kernels     (default 0)
  *   "graphs"        0 | 1     CUDA-graph replay of small point-list calls      (default 1)
  *   "quads"         0 | 1     four rows (phi, 180 - phi, phi + 180, 360 - phi) from one evaluation on grids that
- *                             contain them                                      (default 1)
+ *                             contain them             (default: fused kernel on short launches and radii > 32)
  * Unknown keys and values outside the listed sets fail with SSHG_EINVAL. */
 SSHG_API int sshg_ctx_set_option(sshg_ctx* ctx, const char* key, int64_t value);
 SSHG_API int sshg_ctx_get_option(sshg_ctx* ctx, const char* key, int64_t* value);

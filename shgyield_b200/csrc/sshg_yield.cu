@@ -721,8 +721,19 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     void* tab;
     if (int rc = sshg_scratch(ctx, 7, (size_t)(4 + 12 * p->nP) * 8, &tab)) return rc;
     a.tab = (const double*)tab;
-    if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, opt.quads == 0 ? 0 : 1);
-    else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, opt.quads == 0 ? 0 : 1);
+    // Quad items (four rows per evaluation) cut the instructions per point but make every thread write four row streams,
+    // two of them descending.  Measured (profiles/r02_k3_quick_quads.jsonl, same process, same box): K2 is store-bound and
+    // gets slower with them (config 3: 0.416 against 0.387 ms; config-5 shards +-1 %), so K2 uses them only on request;
+    // K3 gains where it is bound by instruction latency -- short launches (config 3: 0.491 against 0.512 ms) and large
+    // radii (sigma_out = 12: -3 ... -4 %) -- and loses 1-3 % on the long store-bound launches of config 5 at sigma_out <= 5.
+    bool quads = opt.quads == 1;
+    if (fused && opt.quads < 0) {
+        // (decided on the WHOLE sweep, not on the shard: a shard must stay bitwise equal to its slice of the full cube)
+        const double k3_waves = (double)(p->nT * p->nD) * (double)((p->nE + 255) / 256) / (2.0 * ctx->num_sms);
+        quads = k3_waves < 4.0 || radius > 32;
+    }
+    if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, quads ? 1 : 0);
+    else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, quads ? 1 : 0);
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
 

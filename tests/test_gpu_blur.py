@@ -65,7 +65,7 @@ BLUR_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("path", ["fused", "fused64", "fused128", "two_pass"])
+@pytest.mark.parametrize("path", ["fused", "fused64", "fused128", "fused_quads", "fused_pairs", "two_pass"])
 @pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0])
 @pytest.mark.parametrize("nE,theta,phi,thick", BLUR_SHAPES, ids=[str(i) for i in range(len(BLUR_SHAPES))])
 def test_broadened_sweep_matches_oracle(grid, consts, libopt, nE, theta, phi, thick, sigma, path):
@@ -74,6 +74,8 @@ def test_broadened_sweep_matches_oracle(grid, consts, libopt, nE, theta, phi, th
     libopt(k3=0 if path == "two_pass" else 1)
     if path in ("fused64", "fused128"):
         libopt(k3_nt=int(path[5:]))
+    if path in ("fused_quads", "fused_pairs"):
+        libopt(quads=1 if path == "fused_quads" else 0)
     cfg = _small_cfg(nE, theta, phi, thick, seed=3)
     got = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma)
     _check(got, _blurred_oracle(cfg, consts, sigma), path != "two_pass", (nE, sigma, path))

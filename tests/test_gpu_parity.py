@@ -193,12 +193,15 @@ GRID_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["auto", "dense", "sparse"])
+@pytest.mark.parametrize("kernel", ["auto", "dense", "dense_quads", "sparse"])
 @pytest.mark.parametrize("nE,theta,phi,thick", GRID_SHAPES, ids=[str(i) for i in range(len(GRID_SHAPES))])
 def test_grid_kernel_matches_oracle(grid, consts, libopt, nE, theta, phi, thick, kernel):
-    """Every shape through the dense (harmonic, phi-pair) kernel and the sparse-phi kernel."""
+    """Every shape through the dense kernel (phi / phi + 180 pairs; with the second mirror: four rows per evaluation)
+    and the sparse-phi kernel."""
     if kernel != "auto":
         libopt(k2_sparse=1 if kernel == "sparse" else 0)
+    if kernel == "dense_quads":
+        libopt(quads=1)
     cfg = _small_cfg(nE, theta, phi, thick)
     got = grid.yield_grid_host(**cfg, consts=consts)
     want = _oracle_cube(cfg, consts)
