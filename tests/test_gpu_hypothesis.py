@@ -58,11 +58,11 @@ def test_points_kernel_random(seed, n, mref, sn, zq):
 
 @settings(max_examples=25 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 1300), nT=st.integers(1, 5), nD=st.integers(1, 3),
-       grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single"]),
-       kernel=st.sampled_from(["dense", "sparse"]))
+       grid_kind=st.sampled_from(["paired", "paired_tail", "free", "single", "regular", "regular_closed"]),
+       kernel=st.sampled_from(["dense", "dense_quads", "sparse"]))
 def test_grid_kernel_random(seed, nE, nT, nD, grid_kind, kernel):
     from shgyield_b200 import grid
-    with util.lib_options(k2_sparse=1 if kernel == "sparse" else 0):
+    with util.lib_options(k2_sparse=1 if kernel == "sparse" else 0, quads=1 if kernel == "dense_quads" else None):
         _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel)
 
 
@@ -73,10 +73,14 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel):
     thick = rng.uniform(0, 80, nD)
     h = int(rng.integers(1, 9))
     base = np.sort(rng.uniform(0, 180, h))
+    m = int(rng.choice([4, 6, 8, 10, 12, 16, 18, 20, 24, 30, 36, 40]))     # regular grids over the full circle with steps that
+                                                                           # are exact in binary: four rows per evaluation
     phi = {"paired": np.concatenate([base, base + 180.0]),
            "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
            "free": rng.uniform(0, 360, 2 * h + 1),
-           "single": np.array([rng.uniform(0, 360)])}[grid_kind]
+           "single": np.array([rng.uniform(0, 360)]),
+           "regular": np.arange(m) * (360.0 / m),
+           "regular_closed": np.linspace(0.0, 360.0, m + 1)}[grid_kind]
     got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS)
     want = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
     scale = max(np.max(np.abs(want[p])) for p in cases.POLS)
@@ -88,7 +92,7 @@ def _grid_kernel_random(grid, seed, nE, nT, nD, grid_kind, kernel):
 
 @settings(max_examples=20 * MORE, deadline=None, suppress_health_check=list(HealthCheck))
 @given(seed=st.integers(0, 2 ** 31 - 1), nE=st.integers(1, 900), nT=st.integers(1, 3), nD=st.integers(1, 2),
-       sigma=st.floats(0.13, 16.0), grid_kind=st.sampled_from(["paired", "paired_tail", "free"]),
+       sigma=st.floats(0.13, 16.0), grid_kind=st.sampled_from(["paired", "paired_tail", "free", "regular", "regular_closed"]),
        tiles=st.sampled_from(["64", "128"]))
 def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     """K3 (yields broadened along E inside the kernel, both tile widths) on generated media / tensors /
@@ -102,9 +106,12 @@ def test_broadened_sweep_random(seed, nE, nT, nD, sigma, grid_kind, tiles):
     thick = rng.uniform(0, 80, nD)
     h = int(rng.integers(4, 12))
     base = np.sort(rng.uniform(0, 180, h))
+    m = int(rng.choice([8, 10, 12, 16, 18, 20, 24, 30, 36, 40, 48]))
     phi = {"paired": np.concatenate([base, base + 180.0]),
            "paired_tail": np.concatenate([base, base + 180.0, [360.0]]),
-           "free": rng.uniform(0, 360, 2 * h + 1)}[grid_kind]
+           "free": rng.uniform(0, 360, 2 * h + 1),
+           "regular": np.arange(m) * (360.0 / m),          # small launch: K3 takes four rows per evaluation
+           "regular_closed": np.linspace(0.0, 360.0, m + 1)}[grid_kind]
     with util.lib_options(k3_nt=int(tiles), k2_sparse=0):  # fewer than 16 azimuths would otherwise take K2s -> K1
         got = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi, consts=CONSTS, sigma_out=sigma)
     raw = _oracle(energy, eps1w, eps2w, chi, theta.reshape(-1, 1, 1, 1), phi.reshape(1, 1, -1, 1), thick.reshape(1, -1, 1, 1))
