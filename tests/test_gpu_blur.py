@@ -62,6 +62,7 @@ BLUR_SHAPES = [
     (64, [45.0], np.linspace(0, 350, 17), [3.0]),                 # no pairing possible
     (30, [55.0], np.linspace(0, 360, 1001), [12.0]),              # several phi chunks, nE < radius
     (1030, [20.0, 40.0], np.arange(0, 360, 22.5), [5.0]),         # tile boundaries inside the axis
+    (70, [45.0], np.arange(0, 360, 0.5), [7.0]),                  # 720 phi: quads / pairs over several table chunks at large radii
 ]
 
 
