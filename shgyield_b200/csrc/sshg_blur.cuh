@@ -259,14 +259,15 @@ __device__ __forceinline__ void sweep_quads(const double* A0, const double* A1, 
 
 // A chunk of the item list: nq quads (first quad: rows q0 + 1, ...), np pair items (first: pair item p0), ns un-paired rows
 // (first: row 2 H + s0); prow = this thread's energies in row 0 of the polarisation.
-template <bool SS, bool VEC>
+template <bool SS, bool VEC, bool QUADS>
 __device__ __forceinline__ void sweep_harm(const double* A0, const double* A1, const double* __restrict__ tb, const PhiItems& it,
                                            int nq, long long q0, int np, long long p0, int ns, long long s0, double* prow,
                                            long long nE, bool valid1, int h, unsigned* fl) {
-    sweep_quads<SS, VEC>(A0, A1, tb, nq, prow + (q0 + 1) * nE, prow + (it.H - q0 - 1) * nE, prow + (q0 + 1 + it.H) * nE,
-                         prow + (2 * it.H - q0 - 1) * nE, nE, valid1, h, fl);
-    sweep_part<SS, VEC, true>(A0, A1, tb + 12 * nq, np, nq, prow + p0 * it.PSTEP * nE, prow + (p0 * it.PSTEP + it.H) * nE,
-                              it.PSTEP * nE, valid1, h, fl);
+    if (QUADS)
+        sweep_quads<SS, VEC>(A0, A1, tb, nq, prow + (q0 + 1) * nE, prow + (it.H - q0 - 1) * nE, prow + (q0 + 1 + it.H) * nE,
+                             prow + (2 * it.H - q0 - 1) * nE, nE, valid1, h, fl);
+    const long long pj = QUADS ? p0 * it.PSTEP : p0, pstride = QUADS ? it.PSTEP * nE : nE;
+    sweep_part<SS, VEC, true>(A0, A1, tb + 12 * nq, np, nq, prow + pj * nE, prow + (pj + it.H) * nE, pstride, valid1, h, fl);
     sweep_part<SS, VEC, false>(A0, A1, tb + 12 * (nq + np), ns, nq + np, prow + (2 * it.H + s0) * nE, nullptr, nE, valid1, h, fl);
 }
 
@@ -290,7 +291,8 @@ __device__ __forceinline__ Column parked_column(const double* cols, int S, int i
 
 // shared memory: wf[2 R + 2] | cols[NCOL][S] | raw[NH][S] (rowbuf[FX_RB][S] during (D)) | pb[FX_RB][6] |
 //                bitmaps fl[2][chunk / 32 + 1], st[2][chunk / 32 + 1] | tabs[chunk][12]
-template <int NT>
+// QUADS: the item list may contain four-row items (instantiated apart: the pair form keeps its registers and schedule)
+template <int NT, bool QUADS>
 __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
     extern __shared__ double smem[];
     const YieldArgs& a = b.y;
@@ -405,14 +407,14 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             for (int i = tid; i < 5 * FLW; i += NT) fl[i] = 0u;     // flagged items and (D)'s strict rows
             __syncthreads();
             // the kinds of item in [base, base + n_items): quads, then pair items, then un-paired rows
-            const long long q0 = min(base, it.Q), q1 = min(base + n_items, it.Q);
+            const long long q0 = QUADS ? min(base, it.Q) : 0, q1 = QUADS ? min(base + n_items, it.Q) : 0;
             const long long p0 = min(max(base - it.Q, 0LL), it.NPI), p1 = min(max(base + n_items - it.Q, 0LL), it.NPI);
             const long long s0 = max(base - it.Q - it.NPI, 0LL);
             const int nq = (int)(q1 - q0), np = (int)(p1 - p0), ns = n_items - nq - np;
             double* prow = out_col + pol * rows_per_pol;
             if (active) {
 #define SSHG_SWEEP(SS_, VEC_) \
-    sweep_harm<SS_, VEC_>(A0, A1, tabs, it, nq, q0, np, p0, ns, s0, prow, nE, valid1, h, fl)
+    sweep_harm<SS_, VEC_, QUADS>(A0, A1, tabs, it, nq, q0, np, p0, ns, s0, prow, nE, valid1, h, fl)
                 if (vec) {
                     if (pol == 3) SSHG_SWEEP(true, true);
                     else SSHG_SWEEP(false, true);
@@ -432,11 +434,11 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
             if (!b.fixup) continue;
             // row of kind k (0: phi, 1: 180 - phi, 2: phi + 180, 3: 360 - phi) of chunk item `item`
             auto item_row = [&](int item, int k) -> long long {
-                if (item < nq) {
+                if (QUADS && item < nq) {
                     const long long j = q0 + item + 1;
                     return k == 0 ? j : k == 1 ? it.H - j : k == 2 ? j + it.H : 2 * it.H - j;
                 }
-                if (item < nq + np) return (p0 + item - nq) * it.PSTEP + (k == 2 ? it.H : 0);
+                if (item < nq + np) return (p0 + item - nq) * (QUADS ? it.PSTEP : 1) + (k == 2 ? it.H : 0);
                 return 2 * it.H + s0 + (item - nq - np);
             };
             {
@@ -460,7 +462,7 @@ __global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(cons
                         double y0[4], y1[4];    // this thread's values of the item's rows a, b, c, d
                         const double* tb = tabs + 12 * item;
                         unsigned kinds;         // which of the four exist for this item
-                        if (item < nq) {
+                        if (QUADS && item < nq) {
                             if (pol == 3) { harm_quad<true>(A0, tb, y0[0], y0[1], y0[2], y0[3]); harm_quad<true>(A1, tb, y1[0], y1[1], y1[2], y1[3]); }
                             else { harm_quad<false>(A0, tb, y0[0], y0[1], y0[2], y0[3]); harm_quad<false>(A1, tb, y1[0], y1[1], y1[2], y1[3]); }
                             kinds = 0xFu;

@@ -303,7 +303,8 @@ __device__ __forceinline__ cplx ldc(const double2* p) {
     return mk(v.x, v.y);
 }
 
-template <int NT, int CHUNK>
+// QUADS: the item list may contain four-row items (instantiated apart so that the default pair form keeps its registers)
+template <int NT, int CHUNK, bool QUADS>
 __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(const YieldArgs a) {
     extern __shared__ double smem[];
     double* tabs = smem;                        // [CHUNK][6]
@@ -374,7 +375,7 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
         __syncthreads();
         if (!active) continue;
         // the kinds of item in [base, base + n_items): quads, then pair items, then un-paired rows
-        const long long q0 = min(base, it.Q), q1 = min(base + n_items, it.Q);
+        const long long q0 = QUADS ? min(base, it.Q) : 0, q1 = QUADS ? min(base + n_items, it.Q) : 0;
         const long long p0 = min(max(base - it.Q, 0LL), it.NPI), p1 = min(max(base + n_items - it.Q, 0LL), it.NPI);
         const long long s0 = max(base - it.Q - it.NPI, 0LL);
         const int nq = (int)(q1 - q0), np = (int)(p1 - p0), ns = n_items - nq - np;
@@ -388,10 +389,11 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
             double* pb = prow + (it.H - q0 - 1) * nE;
             double* pc = prow + (q0 + 1 + it.H) * nE;
             double* pd = prow + (2 * it.H - q0 - 1) * nE;
-            double* plo = prow + p0 * it.PSTEP * nE;                     // pair item k: rows k PSTEP and k PSTEP + H
-            double* phi_ = prow + (p0 * it.PSTEP + it.H) * nE;
+            const long long pj = QUADS ? p0 * it.PSTEP : p0;
+            double* plo = prow + pj * nE;                                // pair item k: rows k PSTEP and k PSTEP + H
+            double* phi_ = prow + (pj + it.H) * nE;
             double* psg = prow + (2 * it.H + s0) * nE;                   // un-paired rows
-            const long long pstride = it.PSTEP * nE;
+            const long long pstride = QUADS ? it.PSTEP * nE : nE;
             if (pol == 3) {
                 Coef4 k[2];
 #pragma unroll
@@ -404,10 +406,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
                     for (int j = 0; j < 4; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
                 if (vec) {
-                    sweep4_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    if (QUADS) sweep4_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
                     sweep4<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
                 } else {
-                    sweep4_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    if (QUADS) sweep4_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
                     sweep4<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
                 }
             } else {
@@ -425,10 +427,10 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
                     for (int j = 0; j < 7; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
                 if (vec) {
-                    sweep7_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    if (QUADS) sweep7_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
                     sweep7<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
                 } else {
-                    sweep7_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
+                    if (QUADS) sweep7_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
                     sweep7<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
                 }
             }
@@ -757,9 +759,13 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     const int64_t cols = (int64_t)a.nTs * a.nDs;
     const int64_t per_col = 4 * p->nP * p->nE;            // doubles per column
     SSHG_REQUIRE(cols * a.n_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
-    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_BIG, CHUNK_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_BIG, CHUNK_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)grid_smem(NT_BIG, CHUNK_BIG)));
-    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_BIG, CHUNK_BIG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)grid_smem(NT_BIG, CHUNK_BIG)));
+    SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_SMALL, CHUNK_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)grid_smem(NT_SMALL, CHUNK_SMALL)));
 
 
@@ -827,12 +833,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         ba.fixup = opt.k3_fixup == 0 ? 0 : 1;
         ba.phi_deg = (const double*)dphi;
         sshg_gaussian_taps(sigma_out, radius, ba.w);
-        if (blur_nt == NT_BLUR)
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)blur_smem));
-        else
-            SSHG_CUDA(cudaFuncSetAttribute(yield_blur_kernel<NT_BLUR_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)blur_smem));
+        const void* kfn = blur_nt == NT_BLUR ? (quads ? (const void*)yield_blur_kernel<NT_BLUR, true> : (const void*)yield_blur_kernel<NT_BLUR, false>)
+                                             : (quads ? (const void*)yield_blur_kernel<NT_BLUR_WIDE, true> : (const void*)yield_blur_kernel<NT_BLUR_WIDE, false>);
+        SSHG_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem));
     }
     const int blur_tiles = (int)((p->nE + blur_te - 1) / blur_te);
     SSHG_REQUIRE(cols * blur_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
@@ -877,10 +880,14 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         // (Staging the warps' runs in shared memory and writing them with cp.async.bulk reaches the sequential-store
         // peak on this address pattern in isolation, but costs resident warps in the real kernel and measured 1.6-1.8x
         // slower: profiles/r02_store_experiments.txt, profiles/r02_k2_bulk_store_*.jsonl, DESIGN.md.)
-        if (nt == NT_BIG)
-            yield_grid_kernel<NT_BIG, CHUNK_BIG><<<ctas, NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
+        if (nt == NT_BIG && quads)
+            yield_grid_kernel<NT_BIG, CHUNK_BIG, true><<<ctas, NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
+        else if (nt == NT_BIG)
+            yield_grid_kernel<NT_BIG, CHUNK_BIG, false><<<ctas, NT_BIG, grid_smem(NT_BIG, CHUNK_BIG), st>>>(b);
+        else if (quads)
+            yield_grid_kernel<NT_SMALL, CHUNK_SMALL, true><<<ctas, NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
         else
-            yield_grid_kernel<NT_SMALL, CHUNK_SMALL><<<ctas, NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
+            yield_grid_kernel<NT_SMALL, CHUNK_SMALL, false><<<ctas, NT_SMALL, grid_smem(NT_SMALL, CHUNK_SMALL), st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
@@ -901,10 +908,14 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.y.n_seg = opt.nseg >= 1 ? opt.nseg : 1;
         SSHG_REQUIRE(nc * blur_tiles * b.y.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
         const unsigned ctas = (unsigned)(nc * blur_tiles * b.y.n_seg);
-        if (blur_nt == NT_BLUR)
-            yield_blur_kernel<NT_BLUR><<<ctas, NT_BLUR, blur_smem, st>>>(b);
+        if (blur_nt == NT_BLUR && quads)
+            yield_blur_kernel<NT_BLUR, true><<<ctas, NT_BLUR, blur_smem, st>>>(b);
+        else if (blur_nt == NT_BLUR)
+            yield_blur_kernel<NT_BLUR, false><<<ctas, NT_BLUR, blur_smem, st>>>(b);
+        else if (quads)
+            yield_blur_kernel<NT_BLUR_WIDE, true><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         else
-            yield_blur_kernel<NT_BLUR_WIDE><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
+            yield_blur_kernel<NT_BLUR_WIDE, false><<<ctas, NT_BLUR_WIDE, blur_smem, st>>>(b);
         SSHG_CUDA(cudaGetLastError());
         ctx->launches++;
         return SSHG_OK;
@@ -1140,6 +1151,24 @@ extern "C" int sshg_yield_points_broadened(sshg_ctx* ctx, const sshg_points* p, 
     for (size_t i = 0; i < n; ++i)
         SSHG_REQUIRE(p->eidx[i] >= 0 && p->eidx[i] < p->nE, "sshg_yield_points_broadened: eidx[%zu] = %lld out of range", i,
                      (long long)p->eidx[i]);
+
+    if (n > ((size_t)1 << 20)) {
+        // a large broadcast: no page-locked staging of hundreds of megabytes, the arrays go up one by one
+        if (int rc = sshg_stage_in(ctx, 4, p->theta_deg, n * 8, 0, &d)) return rc;
+        a.theta_deg = (const double*)d;
+        if (int rc = sshg_stage_in(ctx, 5, p->thick_nm, n * 8, 0, &d)) return rc;
+        a.thick_nm = (const double*)d;
+        if (int rc = sshg_stage_in(ctx, 6, p->phi_deg, n * 8, 0, &d)) return rc;
+        a.phi_deg = (const double*)d;
+        if (int rc = sshg_stage_in(ctx, 7, p->eidx, n * 8, 0, &d)) return rc;
+        a.eidx = (const long long*)d;
+        if (int rc = sshg_scratch(ctx, SCR_PTS_OUT, 4 * n * 8, &d_out)) return rc;
+        int nl;
+        if (int rc = small_call_enqueue(ctx, a, sigma_out, ndim, shape, (double*)d_y, (double*)d_out, &nl)) return rc;
+        SSHG_CUDA(cudaMemcpyAsync(out, d_out, 4 * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SSHG_OK;
+    }
 
     // point arrays: theta | phi | thick | eidx packed in page-locked memory, ONE upload; result through page-locked memory
     void* d_in;

@@ -160,3 +160,40 @@ def test_points_broadened_device_resident_and_bad_index():
         hb = [a.ctypes.data for a in host]
         hb[1] = eb.ctypes.data
         call(hb, _lib.HOST, out_h.ctypes.data)
+
+
+def test_points_broadened_large_broadcast_takes_the_unstaged_path():
+    """More than 2^20 points: no page-locked staging; the same bits as sshg_yield_points (sigma_out = 0) and a filter
+    along the second axis that matches scipy's."""
+    import ctypes as C
+    from shgyield_b200 import _lib
+    from shgyield_b200 import shg as host
+    from shgyield_b200.synthetic import synthetic_spectra
+    ctx = _lib.context(0)
+    energy, eps1w, eps2w, chi = synthetic_spectra(24, seed=9)
+    shape = (44000, 24)
+    n = shape[0] * shape[1]
+    assert n > 1 << 20
+    rng = np.random.default_rng(3)
+    theta = np.ascontiguousarray(np.broadcast_to(rng.uniform(0, 89, shape[0])[:, None], shape)).ravel()
+    phi = np.ascontiguousarray(np.broadcast_to(rng.uniform(0, 360, shape[0])[:, None], shape)).ravel()
+    thick = np.full(n, 8.0)
+    eidx = np.ascontiguousarray(np.broadcast_to(np.arange(24, dtype=np.int64), shape)).ravel()
+    want = host.yield_points(energy, eidx, theta, phi, thick, eps1w, eps2w, chi)
+    phys = host._physics(host.physical_constants(), True)
+    p = _lib.Points(n=n, nE=24, energy_eV=energy.ctypes.data, eidx=eidx.ctypes.data, theta_deg=theta.ctypes.data,
+                    phi_deg=phi.ctypes.data, thick_nm=thick.ctypes.data, eps1w=eps1w.ctypes.data, eps2w=eps2w.ctypes.data,
+                    chi2=chi.ctypes.data, phys=phys)
+    shp = (C.c_int64 * 2)(*shape)
+    got = np.empty((4, n))
+    _lib.check(ctx.lib.sshg_yield_points_broadened(ctx.handle, C.byref(p), 0.0, 2, shp, got.ctypes.data, _lib.HOST), ctx.lib)
+    assert np.array_equal(got, want)
+    shp1 = (C.c_int64 * 2)(n // 24, 24)
+    _lib.check(ctx.lib.sshg_yield_points_broadened(ctx.handle, C.byref(p), 1.0, 2, shp1, got.ctypes.data, _lib.HOST), ctx.lib)
+    rows = want[2].reshape(shape)[:50]
+    ref = orc.gaussian_filter1d(want[2].reshape(shape), 1.0, axis=1)[:50]
+    ref = orc.gaussian_filter1d(np.pad(ref, ((0, 0), (0, 0))), 0.0, axis=0) if False else ref
+    # the filter ran along BOTH axes; check the second axis on rows far from each other's influence is not possible, so
+    # compare with the full two-axis filter of the first 200 rows (radius 4 along axis 0)
+    full = orc.gaussian_filter1d(orc.gaussian_filter1d(want[2].reshape(shape)[:300], 1.0, axis=0), 1.0, axis=1)[:200]
+    assert np.max(np.abs(got[2].reshape(shape)[:200] - full)) <= 1e-10 * np.max(np.abs(full))
