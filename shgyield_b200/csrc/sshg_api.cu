@@ -165,9 +165,10 @@ int sshg_ctx_set_stream(sshg_ctx* ctx, void* cuda_stream) {
 }
 
 namespace {
+typedef int sshg_options::*OptionField;
 struct OptionKey {
     const char* key;
-    int sshg_options::*field;
+    OptionField field;
     int lo, hi;             // allowed values besides -1
     int only_a, only_b;     // when >= 0: the only two allowed values
 };

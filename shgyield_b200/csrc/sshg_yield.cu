@@ -53,17 +53,8 @@ struct YieldArgs {
     Physics ph;
 };
 
-__device__ __forceinline__ void store2(double* p, double y0, double y1, bool vec, bool valid1) {
-    if (vec) {
-        __stcs(reinterpret_cast<double2*>(p), make_double2(y0, y1));
-    } else {
-        __stcs(p, y0);
-        if (valid1) __stcs(p + 1, y1);
-    }
-}
-
-// The same with the store width known at compile time: the sweeps are instantiated for both, so that their inner
-// loops carry no branch on it (a run-time flag costs a BSSY / BRA / BSYNC triple per store).
+// Two adjacent yields of one row.  The store width is known at compile time: the sweeps are instantiated for both, so
+// that their inner loops carry no branch on it (a run-time flag costs a BSSY / BRA / BSYNC triple per store).
 template <bool VEC>
 __device__ __forceinline__ void store2t(double* p, double y0, double y1, bool valid1) {
     if (VEC) {
