@@ -29,10 +29,10 @@ constexpr int CHUNK_BIG = 384;    // phi items per shared-memory table chunk (18
 constexpr int CHUNK_SMALL = 256;  // ... 12 KB for the 64-thread CTAs (32 KB of shared memory each)
 constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
 #ifndef SSHG_NSEG_MAX
-#define SSHG_NSEG_MAX 2
+#define SSHG_NSEG_MAX 4
 #endif
 #ifndef SSHG_NSEG_WAVES
-#define SSHG_NSEG_WAVES 7.0
+#define SSHG_NSEG_WAVES 4.5
 #endif
 
 struct YieldArgs {
@@ -834,12 +834,15 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // Short launches: a CTA that is left alone at the end of a launch still needs its full azimuthal sweep
     // (~40-75 us), and every CTA starts with a store-free setup phase.  Cutting the phi items of a column
     // into segments (one CTA each, the setup is repeated) shortens both.  option "nseg" overrides (tuning).
-    auto pick_segments = [&](int64_t ctas, int per_sm, double below_waves) -> int {
+    // K2 (tools/tune_nseg.py, profiles/r02_tune_nseg.jsonl): segments until the launch has about 4.5 waves, at most 4 --
+    // config 3 (1.6 waves un-cut) 3 segments: 0.401 -> 0.365 ms (2: 0.374, 4: 0.382); an 8-theta slab of config 5 (1.4
+    // waves) 4 segments: 0.672 -> 0.587 ms; a 23-theta shard (4.1 waves) 2: 1.682 -> 1.652 ms; 46 thetas (8.1 waves) none.
+    auto pick_segments = [&](int64_t ctas, int per_sm, double target_waves) -> int {
         if (opt.nseg >= 1) return opt.nseg;
         const double waves = (double)ctas / ((double)ctx->num_sms * per_sm);
         const long long items = p->nP - p->nP / 2;
         int ns = 1;
-        while (ns < SSHG_NSEG_MAX && waves < below_waves && items / (2 * ns) >= 32) ns *= 2;
+        while (ns < SSHG_NSEG_MAX && waves * ns < target_waves && items / (ns + 1) >= 32) ++ns;
         return ns;
     };
 
