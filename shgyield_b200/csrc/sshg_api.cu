@@ -112,7 +112,7 @@ int sshg_ctx_create(int device, sshg_ctx** out) {
     }
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
@@ -183,6 +183,7 @@ const OptionKey kOptions[] = {
     {"k1_generic", &sshg_options::k1_generic, 0, 1, -1, -1},
     {"graphs", &sshg_options::graphs, 0, 1, -1, -1},
     {"quads", &sshg_options::quads, 0, 1, -1, -1},
+    {"k1_bulk", &sshg_options::k1_bulk, 0, 1, -1, -1},
 };
 const OptionKey* find_option(const char* key) {
     for (const OptionKey& o : kOptions)

@@ -182,6 +182,96 @@ __global__ void __launch_bounds__(FT_MAX) gauss_fixed_kernel(const double* __res
     }
 }
 
+// ---- the same with the tile moved by the bulk-copy engine (TMA, cp.async.bulk) ---------------------
+// ncu on the kernel above (profiles/r01_k1d_fixed_radius_ncu_full.txt): 1225 warp instructions per thread of which 533
+// are the DFMAs -- the staging loop (64-bit index arithmetic, bounds and reflect tests, LDG + STS per sample) and the
+// store loop (LDS + STG per sample) take 40 % of the issue slots of a kernel whose FP64 pipe already needs 50 % of
+// them.  Here ONE thread issues one cp.async.bulk global -> shared for the whole tile + halo (completion on an
+// mbarrier) and one cp.async.bulk shared -> global for the results; the reflected samples at the two ends of a row are
+// filled from the staged ones.  Needs 16-byte aligned rows of even length (decided on the host); other launches take the
+// kernel above.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int RAD>
+__global__ void __launch_bounds__(FT_MAX) gauss_fixed_bulk_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                                  const FixedTaps<RAD> taps, long long n,
+                                                                  long long row_stride, int tiles_per_row) {
+    extern __shared__ __align__(128) double smb[];
+    __shared__ __align__(8) unsigned long long bar;
+    const int FTN = blockDim.x;
+    const int tile_n = FTN * FR;
+    double* xs = smb;                              // xs[j] = x[lo + j], j < tile_n + 2 RAD
+    const int tid = threadIdx.x;
+    const long long row = blockIdx.x / tiles_per_row;
+    const long long i0 = (long long)(blockIdx.x % tiles_per_row) * tile_n;
+    const double* src = in + row * row_stride;
+    double* dst = out + row * row_stride;
+    const long long lo = i0 - RAD;
+    const long long g0 = lo < 0 ? 0 : lo;                                   // samples [g0, g1) exist
+    const long long g1 = i0 + tile_n + RAD < n ? i0 + tile_n + RAD : n;
+    const unsigned bar_a = smem_addr(&bar);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)(g1 - g0) * 8u;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_addr(xs + (g0 - lo))),
+                     "l"(src + g0), "r"(bytes), "r"(bar_a)
+                     : "memory");
+    }
+    __syncthreads();                               // the barrier is initialised before anybody polls it
+    {
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
+    // 'reflect' boundary (d c b a | a b c d | d c b a) from the staged samples; the host guarantees n >= 2 RAD
+    const bool left = lo < 0, right = i0 + tile_n + RAD > n;
+    if (left || right) {
+        for (int k = tid; k < RAD; k += FTN) {
+            if (left) xs[k] = xs[2 * RAD - 1 - k];                          // x[-1 - j] = x[j]
+            const long long i = n + k;                                      // x[n + j] = x[n - 1 - j]
+            if (right && i < i0 + tile_n + RAD) xs[i - lo] = xs[2 * n - 1 - i - lo];
+        }
+        __syncthreads();
+    }
+
+    const double* xw = xs + tid * FR;              // xw[t] = x[o0 - RAD + t], o0 = first output of this thread
+    double acc[FR];
+#pragma unroll
+    for (int q = 0; q < FR; ++q) acc[q] = 0.0;
+#pragma unroll
+    for (int t = 0; t < 2 * RAD + FR; ++t) {
+        const double v = xw[t];
+#pragma unroll
+        for (int q = 0; q < FR; ++q) {
+            const int j = t - q;                   // tap index 0 .. 2 RAD of the full kernel; absent taps are skipped
+            if (j >= 0 && j <= 2 * RAD) acc[q] = fma(taps.w[j <= RAD ? RAD - j : j - RAD], v, acc[q]);
+        }
+    }
+    __syncthreads();                               // every window read is done: reuse xs for the results
+#pragma unroll
+    for (int q = 0; q < FR; ++q) xs[tid * FR + q] = acc[q];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // results visible to the copy engine
+    __syncthreads();
+    if (tid == 0) {
+        const long long valid = n - i0 < tile_n ? n - i0 : tile_n;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + i0), "r"(smem_addr(xs)),
+                     "r"((unsigned)valid * 8u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // shared memory is read before the CTA retires
+    }
+}
+
 template <int RAD>
 int launch_fixed(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                  const double* w_host) {
@@ -202,8 +292,16 @@ int launch_fixed(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, i
     const long long tiles = (n + tile - 1) / tile;
     SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
     const size_t smem = (size_t)(tile + 2 * RAD) * 8;
-    SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    gauss_fixed_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
+    // bulk-copy staging: 16-byte aligned rows of even length (tile widths and the fixed radii are even), simple reflection
+    const bool bulk = ctx->opt.k1_bulk != 0 && ((uintptr_t)din | (uintptr_t)dout) % 16 == 0 && n % 2 == 0 &&
+                      (rows == 1 || row_stride % 2 == 0) && n >= 2 * RAD;
+    if (bulk) {
+        SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_bulk_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        gauss_fixed_bulk_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
+    } else {
+        SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        gauss_fixed_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
+    }
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
     return SSHG_OK;
@@ -346,7 +444,8 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         switch (r) {                               // radii with a compile-time specialisation
 #define SSHG_FIXED(R_) case R_: return launch_fixed<R_>(ctx, din, dout, rows, n, row_stride, ctx->tap_host);
             SSHG_FIXED(4) SSHG_FIXED(6) SSHG_FIXED(8) SSHG_FIXED(10) SSHG_FIXED(12) SSHG_FIXED(14) SSHG_FIXED(16)
-            SSHG_FIXED(18) SSHG_FIXED(20) SSHG_FIXED(22) SSHG_FIXED(24) SSHG_FIXED(28) SSHG_FIXED(32) SSHG_FIXED(40)
+            SSHG_FIXED(18) SSHG_FIXED(20) SSHG_FIXED(22) SSHG_FIXED(24) SSHG_FIXED(26) SSHG_FIXED(28) SSHG_FIXED(30)
+            SSHG_FIXED(32) SSHG_FIXED(36) SSHG_FIXED(40) SSHG_FIXED(48) SSHG_FIXED(56) SSHG_FIXED(64)
 #undef SSHG_FIXED
             default: break;
         }

@@ -17,7 +17,7 @@ struct sshg_trace_range {
 #define SSHG_TRACE(name) sshg_trace_range sshg_trace_range_(name)
 
 #define SSHG_NSCRATCH 32
-#define SSHG_TAP_HOST 64
+#define SSHG_TAP_HOST 72
 #define SCR_TAPS 20      // Gaussian taps of the last sigma (cached)
 #define SCR_SPLFAC 17    // spline elimination coefficients of the last axis (cached)
 #define SCR_XPHI 18      // phi-contracted chi2 of the sparse-phi kernel (slot 19: thickness-axis info)
@@ -40,6 +40,7 @@ struct sshg_options {
     int k1_generic;     // 1: never use the fixed-radius FIR kernels
     int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
     int quads;          // 0: no four-row items (phi, 180 - phi, phi + 180, 360 - phi) in the azimuthal sweeps
+    int k1_bulk;        // 0: the fixed-radius FIR kernels stage their tiles with per-thread loads / stores (no bulk copies)
 };
 
 // A recorded small call: copy in -> yield_points_kernel -> FIR passes -> copy out, keyed on everything the recorded

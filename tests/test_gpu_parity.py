@@ -86,6 +86,42 @@ def test_gauss_nan_stays_within_the_radius(shg, sigma):
     assert got.shape == x.shape
 
 
+@pytest.mark.parametrize("n", [40, 80, 126, 128, 832, 834, 2912, 2914, 5824, 5850, 20000])
+@pytest.mark.parametrize("sigma", [1.0, 5.0, 6.5, 8.0, 10.0, 12.0, 16.0])
+def test_gauss_bulk_copy_staging(shg, n, sigma):
+    """The fixed-radius FIR kernels move their tile + halo and their results with cp.async.bulk when rows are 16-byte
+    aligned and of even length; the reflected ends of a row are filled from the staged samples.  Bitwise equal to the
+    per-thread staging (option k1_bulk = 0) and equal to SciPy, over several rows, tiles that end exactly at / just
+    before / just after the end of a row, and rows shorter than one tile; a NaN stays within the radius."""
+    import torch
+    from scipy import ndimage
+    from shgyield_b200 import grid
+    r = int(4 * sigma + 0.5)
+    x = np.random.default_rng(n).normal(size=(7, n))
+    x[3, n // 2] = np.nan
+    x[5, 0] = np.inf
+    x[6, n - 1] = -np.inf
+    d = torch.from_numpy(x).cuda()
+    with util.lib_options(k1_bulk=0):
+        a = grid.broaden_energy_device(d, sigma).cpu().numpy()
+    with util.lib_options(k1_bulk=1):
+        b = grid.broaden_energy_device(d, sigma).cpu().numpy()
+    c = grid.broaden_energy_device(d, sigma).cpu().numpy()                # the default
+    assert np.array_equal(a, b, equal_nan=True) and np.array_equal(b, c, equal_nan=True)
+    want = np.stack([ndimage.gaussian_filter(row, sigma) for row in x])
+    assert np.array_equal(np.isfinite(b), np.isfinite(want)) and np.array_equal(np.isnan(b), np.isnan(want))
+    ok = np.isfinite(want)
+    np.testing.assert_allclose(b[ok], want[ok], rtol=0, atol=1e-14)
+    if n >= 2 * r + 2:
+        assert np.array_equal(np.isnan(b[3]), np.abs(np.arange(n) - n // 2) <= r)
+    # rows of odd length (every other row only 8-byte aligned) take the per-thread staging
+    e = grid.broaden_energy_device(d[:, 1:].contiguous(), sigma).cpu().numpy()
+    w2 = np.stack([ndimage.gaussian_filter(row[1:], sigma) for row in x])
+    ok2 = np.isfinite(w2)
+    assert np.array_equal(np.isfinite(e), ok2)
+    np.testing.assert_allclose(e[ok2], w2[ok2], rtol=0, atol=1e-14)
+
+
 def test_gauss_matches_oracle_restatement(shg):
     x = np.random.default_rng(9).normal(size=(3, 300))
     np.testing.assert_allclose(shg.broad(x, 4.0), orc.gaussian_filter(x, 4.0), rtol=0, atol=1e-14)
