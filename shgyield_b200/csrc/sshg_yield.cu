@@ -26,7 +26,10 @@ constexpr int NT_BIG = 256;    // threads per CTA when the column setup dominate
 constexpr int NT_SMALL = 64;   // ... when the stores dominate: 128-energy tiles, up to 7 CTAs per SM
 constexpr int EPT = 2;         // energies per thread
 constexpr int CHUNK_BIG = 384;    // phi items per shared-memory table chunk (18 KB)
-constexpr int CHUNK_SMALL = 256;  // ... 12 KB for the 64-thread CTAs (32 KB of shared memory each)
+#ifndef SSHG_K2_CHUNK
+#define SSHG_K2_CHUNK 256
+#endif
+constexpr int CHUNK_SMALL = SSHG_K2_CHUNK;  // ... 12 KB for the 64-thread CTAs (32 KB of shared memory each)
 constexpr int NCOL = 20;       // doubles per parked Column (10 complex)
 #ifndef SSHG_NSEG_MAX
 #define SSHG_NSEG_MAX 4
@@ -652,6 +655,9 @@ int check_physics(const sshg_physics& p) {
 }
 
 constexpr size_t grid_smem(int nt, int chunk) { return (size_t)(chunk * 6 + EPT * NCOL * nt) * sizeof(double); }
+// resident 64-thread CTAs per SM: shared memory (228 KB, 1 KB per CTA reserved), at most 8 by registers (128 per thread)
+constexpr int K2_SMALL_PER_SM_SMEM = (int)((228 * 1024) / (grid_smem(NT_SMALL, CHUNK_SMALL) + 1024));
+constexpr int K2_SMALL_PER_SM = K2_SMALL_PER_SM_SMEM < 8 ? K2_SMALL_PER_SM_SMEM : 8;
 
 }  // namespace
 
@@ -868,7 +874,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         b.col0 = c0;
         b.out = dst;
         b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
-        b.n_seg = pick_segments(nc * a.n_tiles, nt == NT_BIG ? 2 : 6, SSHG_NSEG_WAVES);
+        b.n_seg = pick_segments(nc * a.n_tiles, nt == NT_BIG ? 2 : K2_SMALL_PER_SM, SSHG_NSEG_WAVES);
         SSHG_REQUIRE(nc * a.n_tiles * b.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
         const unsigned ctas = (unsigned)(nc * a.n_tiles * b.n_seg);
         // (Staging the warps' runs in shared memory and writing them with cp.async.bulk reaches the sequential-store
