@@ -433,6 +433,8 @@ def run_ours(args):
         v = C.c_double()
         _lib.check(ctx.lib.sshg_peak_store(ctx.handle, 8 << 30, 5, C.byref(v)), ctx.lib)
         peaks["store_gbs"] = v.value
+        _lib.check(ctx.lib.sshg_peak_copy(ctx.handle, 4 << 30, 5, C.byref(v)), ctx.lib)
+        peaks["copy_bulk_gbs"] = v.value
         _lib.check(ctx.lib.sshg_peak_dfma(ctx.handle, 5, C.byref(v)), ctx.lib)
         peaks["fp64_tflops"] = v.value
 
@@ -657,6 +659,7 @@ def run_ours(args):
                                    "duration = mean CUDA-event time of the %d timed launches on rank 0 (%.3f ms)"
                                    % (my_pts, args.steps, k2_ms),
                          "store_peak_gbs_measured": peaks.get("store_gbs"),
+                         "copy_peak_bulk_gbs_measured": peaks.get("copy_bulk_gbs"),
                          "fp64_peak_tflops_measured": peaks.get("fp64_tflops"),
                          "alg_fp64_tflops": flops / (k2_ms * 1e-3) / 1e12},
             "cpu_baseline": cpu,

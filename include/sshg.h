@@ -242,6 +242,9 @@ SSHG_API int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, double*
 /* ---- measurement helpers used by bench.py for the roofline denominators ---------------- */
 /* streaming 128-bit stores over `bytes` of device memory; returns achieved GB/s (best of iters) */
 SSHG_API int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs);
+/* device-to-device copy of `bytes` by the bulk-copy engine (cp.async.bulk through shared memory, as K1 stages its
+ * tiles); returns achieved GB/s, read + written (best of iters) */
+SSHG_API int sshg_peak_copy(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs);
 /* register-resident DFMA loop on all SMs; returns achieved FP64 TFLOP/s (best of iters) */
 SSHG_API int sshg_peak_dfma(sshg_ctx* ctx, int iters, double* tflops);
 

@@ -89,6 +89,7 @@ SYMBOLS = {
                                 C.c_void_p, C.POINTER(Physics), C.c_void_p, C.c_int64, C.c_int]),
     "sshg_amplitudes_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
     "sshg_peak_store": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p]),
+    "sshg_peak_copy": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "sshg_peak_dfma": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),
 }
 

@@ -20,6 +20,34 @@ __global__ void __launch_bounds__(256) store_kernel(double2* __restrict__ p, lon
     }
 }
 
+// Device-to-device copy by the bulk-copy engine: one elected thread per CTA moves a 16 KB tile global -> shared
+// (cp.async.bulk, completion on an mbarrier) and shared -> global (bulk group): what K1's staging does, without the FIR.
+constexpr int COPY_TILE = 16 * 1024;
+__global__ void __launch_bounds__(32) copy_bulk_kernel(const char* __restrict__ src, char* __restrict__ dst, long long bytes) {
+    __shared__ __align__(128) char buf[COPY_TILE];
+    __shared__ __align__(8) unsigned long long bar;
+    if (threadIdx.x != 0) return;
+    const long long off = (long long)blockIdx.x * COPY_TILE;
+    const unsigned n = (unsigned)(bytes - off < COPY_TILE ? bytes - off : COPY_TILE);
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(&bar), buf_a = (unsigned)__cvta_generic_to_shared(buf);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_a),
+                 "l"(src + off), "r"(n), "r"(bar_a)
+                 : "memory");
+    unsigned done = 0;
+    while (!done)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar_a)
+            : "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + off), "r"(buf_a), "r"(n) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
 constexpr int DFMA_ILP = 8;
 constexpr int DFMA_ITERS = 4096;
 
@@ -72,6 +100,42 @@ extern "C" int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* 
     cudaFree(buf);
     if (e != cudaSuccess) return sshg_cuda_fail(e, "store_kernel", __FILE__, __LINE__);
     *gbs = (double)(n2 * 16) / (best * 1e-3) / 1e9;
+    return SSHG_OK;
+}
+
+extern "C" int sshg_peak_copy(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs) {
+    SSHG_REQUIRE(ctx && gbs && bytes >= 1024 && bytes % 16 == 0 && iters > 0, "sshg_peak_copy: bad argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    void *src = nullptr, *dst = nullptr;
+    if (cudaMalloc(&src, (size_t)bytes) != cudaSuccess || cudaMalloc(&dst, (size_t)bytes) != cudaSuccess) {
+        (void)cudaGetLastError();
+        if (src) cudaFree(src);
+        sshg_set_error("sshg_peak_copy: device allocation of 2 x %lld bytes failed", (long long)bytes);
+        return SSHG_ENOMEM;
+    }
+    cudaMemsetAsync(src, 1, (size_t)bytes, ctx->stream);
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const long long tiles = (bytes + COPY_TILE - 1) / COPY_TILE;
+    float best = 1e30f;
+    for (int it = 0; it < iters + 2; ++it) {
+        cudaEventRecord(t0, ctx->stream);
+        copy_bulk_kernel<<<(unsigned)tiles, 32, 0, ctx->stream>>>((const char*)src, (char*)dst, bytes);
+        cudaEventRecord(t1, ctx->stream);
+        cudaEventSynchronize(t1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, t0, t1);
+        if (it >= 2 && ms < best) best = ms;
+        ctx->launches++;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(src);
+    cudaFree(dst);
+    if (e != cudaSuccess) return sshg_cuda_fail(e, "copy_bulk_kernel", __FILE__, __LINE__);
+    *gbs = 2.0 * (double)bytes / (best * 1e-3) / 1e9;          // read + written
     return SSHG_OK;
 }
 
