@@ -33,6 +33,10 @@
 // computed row-wise; no second kernel, no flag memory in HBM, no repeated column setup.
 constexpr int NT_BLUR = 64;                     // 128-energy tiles (short energy axes)
 constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 64
+#ifndef SSHG_K3_NARROW_PER_SM
+#define SSHG_K3_NARROW_PER_SM 4
+#endif
+constexpr int BLUR_NARROW_PER_SM = SSHG_K3_NARROW_PER_SM;   // resident 64-thread CTAs per SM the registers allow
 constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
 constexpr int FX_RB = 12;                       // flagged rows re-evaluated together (rowbuf aliases raw: <= NH)
 #ifndef SSHG_SWEEP_SB
@@ -293,7 +297,7 @@ __device__ __forceinline__ Column parked_column(const double* cols, int S, int i
 //                bitmaps fl[2][chunk / 32 + 1], st[2][chunk / 32 + 1] | tabs[chunk][12]
 // QUADS: the item list may contain four-row items (instantiated apart: the pair form keeps its registers and schedule)
 template <int NT, bool QUADS>
-__global__ void __launch_bounds__(NT, (NT <= 64 ? 3 : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
+__global__ void __launch_bounds__(NT, (NT <= 64 ? BLUR_NARROW_PER_SM : 2)) yield_blur_kernel(const __grid_constant__ BlurArgs b) {
     extern __shared__ double smem[];
     const YieldArgs& a = b.y;
     const int R = b.radius, S = b.S, CH = b.chunk;

@@ -726,11 +726,9 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // K3 gains where it is bound by instruction latency -- short launches (config 3: 0.491 against 0.512 ms) and large
     // radii (sigma_out = 12: -3 ... -4 %) -- and loses 1-3 % on the long store-bound launches of config 5 at sigma_out <= 5.
     bool quads = opt.quads == 1;
-    if (fused && opt.quads < 0) {
-        // (decided on the WHOLE sweep, not on the shard: a shard must stay bitwise equal to its slice of the full cube)
-        const double k3_waves = (double)(p->nT * p->nD) * (double)((p->nE + 255) / 256) / (2.0 * ctx->num_sms);
-        quads = k3_waves < 4.0 || radius > 32;
-    }
+    // (decided on the WHOLE sweep, not on the shard: a shard must stay bitwise equal to its slice of the full cube)
+    const double k3_waves = (double)(p->nT * p->nD) * (double)((p->nE + 255) / 256) / (2.0 * ctx->num_sms);
+    if (fused && opt.quads < 0) quads = k3_waves < 4.0 || radius > 32;
     if (fused) phi_harm_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, quads ? 1 : 0);
     else phi_table_kernel<<<1, 256, 0, ctx->stream>>>((const double*)dphi, p->nP, (double*)tab, 1, quads ? 1 : 0);
     SSHG_CUDA(cudaGetLastError());
@@ -805,14 +803,18 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         // 256-energy tiles (128 threads, two energies each) whenever the axis is longer than one narrow tile.  (One energy
         // per thread -- 256 threads, 16 warps per SM instead of 8, 64-bit stores -- measured 12-18 % slower:
         // profiles/r02_k3_one_energy_per_thread.jsonl.)
-        if (p->nE > NT_BLUR * EPT) blur_nt = NT_BLUR_WIDE;
+        // Short launches (fewer than 4 waves of wide CTAs: config 3) take 128-energy tiles, FOUR 64-thread CTAs per SM:
+        // half of a CTA's life is store-free (setup, harmonics, FIR, strict rows), and four independent CTAs interleave
+        // those phases better than two -- config 3 with sigma_out = 5 0.488 -> 0.459 ms; long launches lose 3-4 % to the
+        // doubled halo and stay wide (profiles/r02_k3_narrow4.jsonl).
+        if (p->nE > NT_BLUR * EPT && !(k3_waves < 4.0 && radius <= 32)) blur_nt = NT_BLUR_WIDE;
         if (opt.k3_nt == NT_BLUR || opt.k3_nt == NT_BLUR_WIDE) blur_nt = opt.k3_nt;
         blur_te = blur_nt * EPT;
         auto fixed = [&]() { return (size_t)blur_fixed_doubles((int)radius, blur_te + 2 * (int)radius) * sizeof(double); };
         auto need = [&]() { return fixed() + (size_t)blur_chunk_doubles(32) * sizeof(double); };
         auto share = [&](int per_sm) { return sm_bytes / per_sm - 1024; };     // 1 KB per CTA is reserved by the system
         SSHG_REQUIRE(need() <= cta_max, "sshg_yield: internal: K3 shared-memory plan");
-        const int reg_limit = blur_nt == NT_BLUR ? 3 : 2;                      // registers per thread (launch bounds)
+        const int reg_limit = blur_nt == NT_BLUR ? BLUR_NARROW_PER_SM : 2;                      // registers per thread (launch bounds)
         blur_per_sm = 1;
         for (int k = reg_limit; k >= 1; --k)
             if (need() <= share(k)) { blur_per_sm = k; break; }
