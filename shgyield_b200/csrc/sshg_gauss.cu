@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(FT_MAX) gauss_fixed_kernel(const double* __res
 // them.  Here ONE thread issues one cp.async.bulk global -> shared for the whole tile + halo (completion on an
 // mbarrier) and one cp.async.bulk shared -> global for the results; the reflected samples at the two ends of a row are
 // filled from the staged ones.  Needs 16-byte aligned rows of even length (decided on the host); other launches take the
-// kernel above.
+// kernel above (the radii of sigma = 1, 1.5, 2, ...) or the generic kernel.  Instantiated for EVERY radius up to 64: an odd
+// radius stages one more sample on each side so that the copy stays 16-byte aligned.
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 template <int RAD>
@@ -200,15 +201,16 @@ __global__ void __launch_bounds__(FT_MAX) gauss_fixed_bulk_kernel(const double* 
     __shared__ __align__(8) unsigned long long bar;
     const int FTN = blockDim.x;
     const int tile_n = FTN * FR;
-    double* xs = smb;                              // xs[j] = x[lo + j], j < tile_n + 2 RAD
+    constexpr int PAD = RAD & 1;                   // odd radii: one more sample on each side keeps the copy 16-byte aligned
+    double* xs = smb;                              // xs[j] = x[lo + j], j < tile_n + 2 (RAD + PAD)
     const int tid = threadIdx.x;
     const long long row = blockIdx.x / tiles_per_row;
     const long long i0 = (long long)(blockIdx.x % tiles_per_row) * tile_n;
     const double* src = in + row * row_stride;
     double* dst = out + row * row_stride;
-    const long long lo = i0 - RAD;
+    const long long lo = i0 - RAD - PAD;
     const long long g0 = lo < 0 ? 0 : lo;                                   // samples [g0, g1) exist
-    const long long g1 = i0 + tile_n + RAD < n ? i0 + tile_n + RAD : n;
+    const long long g1 = i0 + tile_n + RAD + PAD < n ? i0 + tile_n + RAD + PAD : n;
     const unsigned bar_a = smem_addr(&bar);
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
@@ -234,17 +236,17 @@ __global__ void __launch_bounds__(FT_MAX) gauss_fixed_bulk_kernel(const double* 
         }
     }
     // 'reflect' boundary (d c b a | a b c d | d c b a) from the staged samples; the host guarantees n >= 2 RAD
-    const bool left = lo < 0, right = i0 + tile_n + RAD > n;
+    const bool left = i0 == 0, right = i0 + tile_n + RAD > n;
     if (left || right) {
         for (int k = tid; k < RAD; k += FTN) {
-            if (left) xs[k] = xs[2 * RAD - 1 - k];                          // x[-1 - j] = x[j]
-            const long long i = n + k;                                      // x[n + j] = x[n - 1 - j]
+            if (left) xs[RAD + PAD - 1 - k] = xs[RAD + PAD + k];            // x[-1 - k] = x[k]
+            const long long i = n + k;                                      // x[n + k] = x[n - 1 - k]
             if (right && i < i0 + tile_n + RAD) xs[i - lo] = xs[2 * n - 1 - i - lo];
         }
         __syncthreads();
     }
 
-    const double* xw = xs + tid * FR;              // xw[t] = x[o0 - RAD + t], o0 = first output of this thread
+    const double* xw = xs + PAD + tid * FR;        // xw[t] = x[o0 - RAD + t], o0 = first output of this thread
     double acc[FR];
 #pragma unroll
     for (int q = 0; q < FR; ++q) acc[q] = 0.0;
@@ -272,7 +274,10 @@ __global__ void __launch_bounds__(FT_MAX) gauss_fixed_bulk_kernel(const double* 
     }
 }
 
-template <int RAD>
+// Returns 1 when this launch cannot take the fixed-radius kernels (the caller falls through to the generic kernel).
+// PLAIN: the per-thread-staging kernel exists for this radius as well (the radii of sigma = 1, 1.5, 2, ...); the other
+// radii up to 64 have the bulk-copy kernel only.
+template <int RAD, bool PLAIN>
 int launch_fixed(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, int64_t n, int64_t row_stride,
                  const double* w_host) {
     FixedTaps<RAD> taps;
@@ -291,16 +296,19 @@ int launch_fixed(sshg_ctx* ctx, const double* din, double* dout, int64_t rows, i
     const long long tile = (long long)ft * FR;
     const long long tiles = (n + tile - 1) / tile;
     SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
-    const size_t smem = (size_t)(tile + 2 * RAD) * 8;
-    // bulk-copy staging: 16-byte aligned rows of even length (tile widths and the fixed radii are even), simple reflection
+    // bulk-copy staging: 16-byte aligned rows of even length (tile widths are even), simple reflection
     const bool bulk = ctx->opt.k1_bulk != 0 && ((uintptr_t)din | (uintptr_t)dout) % 16 == 0 && n % 2 == 0 &&
                       (rows == 1 || row_stride % 2 == 0) && n >= 2 * RAD;
     if (bulk) {
+        const size_t smem = (size_t)(tile + 2 * (RAD + (RAD & 1))) * 8;
         SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_bulk_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         gauss_fixed_bulk_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
-    } else {
+    } else if constexpr (PLAIN) {
+        const size_t smem = (size_t)(tile + 2 * RAD) * 8;
         SSHG_CUDA(cudaFuncSetAttribute(gauss_fixed_kernel<RAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         gauss_fixed_kernel<RAD><<<(unsigned)(rows * tiles), ft, smem, ctx->stream>>>(din, dout, taps, n, row_stride, (int)tiles);
+    } else {
+        return 1;
     }
     SSHG_CUDA(cudaGetLastError());
     ctx->launches++;
@@ -441,14 +449,25 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         ctx->tap_ptr = dw;
     }
     if (elem_stride == 1 && plain && ctx->opt.k1_generic != 1) {
+        int rc = 1;                                // 1: not taken
         switch (r) {                               // radii with a compile-time specialisation
-#define SSHG_FIXED(R_) case R_: return launch_fixed<R_>(ctx, din, dout, rows, n, row_stride, ctx->tap_host);
+#define SSHG_FIXED(R_) case R_: rc = launch_fixed<R_, true>(ctx, din, dout, rows, n, row_stride, ctx->tap_host); break;
+#define SSHG_BULK(R_) case R_: rc = launch_fixed<R_, false>(ctx, din, dout, rows, n, row_stride, ctx->tap_host); break;
             SSHG_FIXED(4) SSHG_FIXED(6) SSHG_FIXED(8) SSHG_FIXED(10) SSHG_FIXED(12) SSHG_FIXED(14) SSHG_FIXED(16)
             SSHG_FIXED(18) SSHG_FIXED(20) SSHG_FIXED(22) SSHG_FIXED(24) SSHG_FIXED(26) SSHG_FIXED(28) SSHG_FIXED(30)
             SSHG_FIXED(32) SSHG_FIXED(36) SSHG_FIXED(40) SSHG_FIXED(48) SSHG_FIXED(56) SSHG_FIXED(64)
+            // every other radius up to 64 (sigma <= 16): bulk-copy staging only
+            SSHG_BULK(1) SSHG_BULK(2) SSHG_BULK(3) SSHG_BULK(5) SSHG_BULK(7) SSHG_BULK(9) SSHG_BULK(11) SSHG_BULK(13)
+            SSHG_BULK(15) SSHG_BULK(17) SSHG_BULK(19) SSHG_BULK(21) SSHG_BULK(23) SSHG_BULK(25) SSHG_BULK(27) SSHG_BULK(29)
+            SSHG_BULK(31) SSHG_BULK(33) SSHG_BULK(34) SSHG_BULK(35) SSHG_BULK(37) SSHG_BULK(38) SSHG_BULK(39) SSHG_BULK(41)
+            SSHG_BULK(42) SSHG_BULK(43) SSHG_BULK(44) SSHG_BULK(45) SSHG_BULK(46) SSHG_BULK(47) SSHG_BULK(49) SSHG_BULK(50)
+            SSHG_BULK(51) SSHG_BULK(52) SSHG_BULK(53) SSHG_BULK(54) SSHG_BULK(55) SSHG_BULK(57) SSHG_BULK(58) SSHG_BULK(59)
+            SSHG_BULK(60) SSHG_BULK(61) SSHG_BULK(62) SSHG_BULK(63)
 #undef SSHG_FIXED
+#undef SSHG_BULK
             default: break;
         }
+        if (rc != 1) return rc;
     }
     const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;

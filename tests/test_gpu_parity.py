@@ -87,10 +87,10 @@ def test_gauss_nan_stays_within_the_radius(shg, sigma):
 
 
 @pytest.mark.parametrize("n", [40, 80, 126, 128, 832, 834, 2912, 2914, 5824, 5850, 20000])
-@pytest.mark.parametrize("sigma", [1.0, 5.0, 6.5, 8.0, 10.0, 12.0, 16.0])
+@pytest.mark.parametrize("sigma", [0.3, 0.7, 1.0, 3.3, 5.0, 6.5, 7.3, 8.0, 10.0, 12.0, 15.3, 16.0])
 def test_gauss_bulk_copy_staging(shg, n, sigma):
-    """The fixed-radius FIR kernels move their tile + halo and their results with cp.async.bulk when rows are 16-byte
-    aligned and of even length; the reflected ends of a row are filled from the staged samples.  Bitwise equal to the
+    """The fixed-radius FIR kernels (every radius up to 64; odd radii stage one more sample on each side) move their
+    tile + halo and their results with cp.async.bulk when rows are 16-byte aligned and of even length; the reflected ends of a row are filled from the staged samples.  Bitwise equal to the
     per-thread staging (option k1_bulk = 0) and equal to SciPy, over several rows, tiles that end exactly at / just
     before / just after the end of a row, and rows shorter than one tile; a NaN stays within the radius."""
     import torch

@@ -21,7 +21,7 @@ dev = torch.device("cuda", 0)
 slab = torch.rand((nth, 1, 4, 721, 20000), dtype=torch.float64, device=dev)
 n = slab.numel()
 ctx = _lib.context(0)
-for sigma in (1.0, 2.0, 3.0, 5.0, 6.0, 8.0, 10.0, 12.0, 16.0):
+for sigma in (0.7, 1.0, 2.0, 3.0, 3.3, 5.0, 6.0, 7.3, 8.0, 10.0, 12.0, 15.3, 16.0):
     row = {"tag": tag, "case": "k1_cube_sigma%g" % sigma, "samples": n, "taps": 2 * int(4 * sigma + 0.5) + 1}
     for name, opts in (("bulk", {}), ("per_thread", {"k1_bulk": 0})):
         with ctx.options(**opts):
