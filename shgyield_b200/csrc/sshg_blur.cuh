@@ -32,12 +32,12 @@
 // along E.  Everything the harmonic sum cannot resolve to 1e-10 -- including exact symmetry zeros -- is thus
 // computed row-wise; no second kernel, no flag memory in HBM, no repeated column setup.
 constexpr int NT_BLUR = 64;                     // 128-energy tiles (short energy axes)
-constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 64
+constexpr int NT_BLUR_WIDE = 128;               // 256-energy tiles (half the halo overhead), 2 CTAs/SM up to radius 64, 1 beyond
 #ifndef SSHG_K3_NARROW_PER_SM
 #define SSHG_K3_NARROW_PER_SM 4
 #endif
 constexpr int BLUR_NARROW_PER_SM = SSHG_K3_NARROW_PER_SM;   // resident 64-thread CTAs per SM the registers allow
-constexpr int BLUR_RMAX = 64;                   // largest fused radius (sigma_out <= 16)
+constexpr int BLUR_RMAX = 200;                  // largest fused radius (sigma_out <= 50, the range of the reference GUI's slider)
 constexpr int FX_RB = 12;                       // flagged rows re-evaluated together (rowbuf aliases raw: <= NH)
 #ifndef SSHG_SWEEP_SB
 #define SSHG_SWEEP_SB 16

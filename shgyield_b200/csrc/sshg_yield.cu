@@ -705,7 +705,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
                  "sshg_yield: complex device arrays must be 16-byte aligned");
 
     // Output broadening (shg.py:433-436): radius as scipy.ndimage (int(4 sigma + 0.5)); a radius of 0 is the
-    // identity.  Dense sweeps with radius <= 64 take the fused kernel K3, everything else K2 -> K1 slab by slab.
+    // identity.  Dense sweeps with radius <= 200 take the fused kernel K3, everything else K2 -> K1 slab by slab.
     // Option "k3" = 0 forces the two-pass path (tests compare both).
     const sshg_options& opt = ctx->opt;                  // test / tuning switches (sshg_ctx_set_option); -1 = automatic
     bool sparse = 4 * p->nP < 64;

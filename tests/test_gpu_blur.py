@@ -67,10 +67,11 @@ BLUR_SHAPES = [
 
 
 @pytest.mark.parametrize("path", ["fused", "fused64", "fused128", "fused_quads", "fused_pairs", "two_pass"])
-@pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0])
+@pytest.mark.parametrize("sigma", [0.3, 1.2, 5.0, 16.0, 23.0, 50.0])
 @pytest.mark.parametrize("nE,theta,phi,thick", BLUR_SHAPES, ids=[str(i) for i in range(len(BLUR_SHAPES))])
 def test_broadened_sweep_matches_oracle(grid, consts, libopt, nE, theta, phi, thick, sigma, path):
-    """radius 1, 5, 20 (the default sigma_out = 5) and 64 (the largest fused radius); K3 with the tile width
+    """radius 1, 5, 20 (the default sigma_out = 5), 64 (two CTAs per SM up to there), 92 and 200 (the largest fused
+    radius: sigma_out = 50, the end of the reference GUI's slider); K3 with the tile width
     the library picks and with 128- / 256-energy tiles forced."""
     libopt(k3=0 if path == "two_pass" else 1)
     if path in ("fused64", "fused128"):
@@ -83,14 +84,15 @@ def test_broadened_sweep_matches_oracle(grid, consts, libopt, nE, theta, phi, th
 
 
 def test_sparse_phi_sweeps_and_large_radii_take_the_two_pass_path(grid, consts):
-    """P = 1 (config-4 shape) and sigma_out > 16: K2 / K2s -> K1 slab by slab; P = 1 forced through K3."""
+    """P = 1 (config-4 shape) and sigma_out > 50: K2 / K2s -> K1 slab by slab; P = 1 forced through K3."""
     cfg = _small_cfg(300, np.arange(0, 90, 9.0), [30.0], np.arange(1.0, 31.0), seed=5)
     want = _blurred_oracle(cfg, consts, 5.0)
     _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, False, "sparse")
     with util.lib_options(k2_sparse=0):
         _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=5.0), want, True, "P=1 through K3")
     cfg = _small_cfg(400, [30.0, 60.0], np.arange(0, 360, 30.0), [10.0], seed=6)
-    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=20.0), _blurred_oracle(cfg, consts, 20.0), False, "r=80")
+    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=20.0), _blurred_oracle(cfg, consts, 20.0), True, "r=80")
+    _check(grid.yield_grid_host(**cfg, consts=consts, sigma_out=60.0), _blurred_oracle(cfg, consts, 60.0), False, "r=240")
     # a radius of 0 (sigma_out < 0.125) is the identity
     assert np.array_equal(grid.yield_grid_host(**cfg, consts=consts, sigma_out=0.1), grid.yield_grid_host(**cfg, consts=consts))
 
