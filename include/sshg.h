@@ -239,6 +239,20 @@ SSHG_API int sshg_multiref(sshg_ctx* ctx, int harmonic, const double* energy_eV,
  * list, out complex [4][n][2]; honours SSHG_FLAG_RADIANS. */
 SSHG_API int sshg_amplitudes_points(sshg_ctx* ctx, const sshg_points* p, double* out, int where);
 
+/* The tail of shgyield() (shg.py:428-437) for LARGE NumPy broadcasts with outer-product structure -- the reference's
+ * only way to express a sweep, e.g. energy[E], theta[T, 1], phi[P, 1, 1].  `p` describes the grid (host arrays, full
+ * range); element (t, d, pol, phi, e) of the result is written to offset
+ *   pol strides[2] + t strides[0] + d strides[1] + phi strides[3] + e        (doubles; strides[2] = prod(shape))
+ * i.e. straight into the C-contiguous broadcast result of every polarisation, whose LAST axis must be the energy;
+ * broad(., sigma_out) then runs over EVERY axis of each polarisation's array (scipy.ndimage.gaussian_filter, as the
+ * reference does on N-D results) on the device, and the four arrays are copied to out_host[0..3] (pp, ps, sp, ss;
+ * prod(shape) doubles each; pageable memory is written by several host threads). */
+SSHG_API int sshg_yield_broadcast(sshg_ctx* ctx, const sshg_problem* p, const int64_t strides[4], double sigma_out,
+                                  int32_t ndim, const int64_t* shape, double* const out_host[4]);
+/* blocking device -> host copy of a large result (ordered after the context's stream); pageable destinations are
+ * written by several host threads through page-locked staging buffers */
+SSHG_API int sshg_download(sshg_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
 /* ---- measurement helpers used by bench.py for the roofline denominators ---------------- */
 /* streaming 128-bit stores over `bytes` of device memory; returns achieved GB/s (best of iters) */
 SSHG_API int sshg_peak_store(sshg_ctx* ctx, int64_t bytes, int iters, double* gbs);

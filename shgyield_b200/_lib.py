@@ -88,6 +88,9 @@ SYMBOLS = {
     "sshg_multiref": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.POINTER(Physics), C.c_void_p, C.c_int64, C.c_int]),
     "sshg_amplitudes_points": (C.c_int, [C.c_void_p, C.POINTER(Points), C.c_void_p, C.c_int]),
+    "sshg_yield_broadcast": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_double, C.c_int32,
+                                       C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
+    "sshg_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]),
     "sshg_peak_store": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "sshg_peak_copy": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, c_double_p]),
     "sshg_peak_dfma": (C.c_int, [C.c_void_p, C.c_int, c_double_p]),

@@ -6,6 +6,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
+#include <thread>
+#include <vector>
+
 static thread_local char g_err[512] = "";
 
 void sshg_set_error(const char* fmt, ...) {
@@ -66,6 +70,96 @@ int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on
     // free to change as soon as the API call returns.
     SSHG_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
     *dev = d;
+    return SSHG_OK;
+}
+
+// ---- threaded device-to-host copy into pageable memory -------------------------------------------------------------
+namespace {
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;       // per staging buffer
+constexpr size_t STAGED_MIN = (size_t)32 << 20;        // smaller copies: one cudaMemcpy
+
+int copy_threads() {
+    unsigned n = std::thread::hardware_concurrency();   // the CPUs this process may run on (glibc: sched_getaffinity)
+    if (n == 0) n = 4;
+    return (int)(n > 16 ? 16 : n);
+}
+}  // namespace
+
+int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes) {
+    if (bytes == 0) return SSHG_OK;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, dst_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();                           // un-registered host memory may report an error on old drivers
+    if (pinned || bytes < STAGED_MIN) {
+        SSHG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SSHG_OK;
+    }
+    if (!ctx->stage[0]) {
+        for (int k = 0; k < 2; ++k) {
+            cudaError_t e = cudaMallocHost(&ctx->stage[k], STAGE_BYTES);
+            if (e != cudaSuccess) {                     // no page-locked memory left: the driver's own pageable path
+                (void)cudaGetLastError();
+                if (k == 1) cudaFreeHost(ctx->stage[0]);
+                ctx->stage[0] = ctx->stage[1] = nullptr;
+                SSHG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+                return SSHG_OK;
+            }
+        }
+        ctx->stage_bytes = STAGE_BYTES;
+    }
+    // the copies run on the copy stream, after everything queued on the compute stream so far
+    SSHG_CUDA(cudaEventRecord(ctx->ev_switch, ctx->stream));
+    SSHG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_switch, 0));
+    const size_t n_chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    auto chunk_len = [&](size_t i) { return i + 1 < n_chunks ? STAGE_BYTES : bytes - i * STAGE_BYTES; };
+    const int T = copy_threads();
+    // workers: chunk i may be copied once ready > i; a worker bumps done[i % 2] when its part of chunk i is out
+    std::atomic<long long> ready(0);
+    std::atomic<int> done[2];
+    done[0] = done[1] = 0;
+    std::atomic<bool> abort_flag(false);
+    std::vector<std::thread> pool;
+    pool.reserve(T);
+    for (int t = 0; t < T; ++t) {
+        pool.emplace_back([&, t]() {
+            for (size_t i = 0; i < n_chunks; ++i) {
+                while (ready.load(std::memory_order_acquire) <= (long long)i) {
+                    if (abort_flag.load(std::memory_order_relaxed)) return;
+                    std::this_thread::yield();
+                }
+                const size_t len = chunk_len(i);
+                const size_t per = ((len + T - 1) / T + 4095) & ~(size_t)4095;       // page-sized shares
+                const size_t lo = (size_t)t * per, hi = lo + per < len ? lo + per : len;
+                if (lo < hi)
+                    memcpy((char*)dst_host + i * STAGE_BYTES + lo, (const char*)ctx->stage[i % 2] + lo, hi - lo);
+                done[i % 2].fetch_add(1, std::memory_order_release);
+            }
+        });
+    }
+    cudaError_t err = cudaSuccess;
+    auto issue = [&](size_t i) {
+        if (err != cudaSuccess) return;
+        err = cudaMemcpyAsync(ctx->stage[i % 2], (const char*)src_dev + i * STAGE_BYTES, chunk_len(i), cudaMemcpyDeviceToHost,
+                              ctx->copy_stream);
+        if (err == cudaSuccess) err = cudaEventRecord(ctx->ev_copied[i % 2], ctx->copy_stream);
+    };
+    issue(0);
+    for (size_t i = 0; i < n_chunks && err == cudaSuccess; ++i) {
+        if (i + 1 < n_chunks) {
+            if (i >= 1) {                               // buffer (i + 1) % 2 held chunk i - 1: every worker is out of it
+                while (done[(i + 1) % 2].load(std::memory_order_acquire) < T) std::this_thread::yield();
+                done[(i + 1) % 2].store(0, std::memory_order_relaxed);
+            }
+            issue(i + 1);
+        }
+        if (err == cudaSuccess) err = cudaEventSynchronize(ctx->ev_copied[i % 2]);
+        if (err == cudaSuccess) ready.store((long long)i + 1, std::memory_order_release);
+    }
+    if (err != cudaSuccess) abort_flag.store(true);
+    for (auto& th : pool) th.join();
+    if (err != cudaSuccess) return sshg_cuda_fail(err, "staged device-to-host copy", __FILE__, __LINE__);
     return SSHG_OK;
 }
 
@@ -142,6 +236,8 @@ void sshg_ctx_destroy(sshg_ctx* ctx) {
     }
     for (int k = 0; k < SSHG_NGRAPH; ++k)
         if (ctx->graphs[k].exec) cudaGraphExecDestroy(ctx->graphs[k].exec);
+    for (int k = 0; k < 2; ++k)
+        if (ctx->stage[k]) cudaFreeHost(ctx->stage[k]);
     if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
     if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
     if (ctx->ev_switch) cudaEventDestroy(ctx->ev_switch);
@@ -239,6 +335,12 @@ int sshg_host_free(void* ptr) {
     if (!ptr) return SSHG_OK;
     SSHG_CUDA(cudaFreeHost(ptr));
     return SSHG_OK;
+}
+
+int sshg_download(sshg_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+    SSHG_REQUIRE(ctx && dst_host && src_dev && bytes > 0, "sshg_download: bad argument");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    return sshg_copy_out(ctx, dst_host, src_dev, (size_t)bytes);
 }
 
 int sshg_upload(sshg_ctx* ctx, void* dst_dev, const void* src_host, int64_t bytes) {

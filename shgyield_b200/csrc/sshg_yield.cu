@@ -52,7 +52,11 @@ struct YieldArgs {
     int nTs, nDs, t0, d0;      // shard extents / offsets
     int n_tiles;
     int n_seg;                 // the phi items of a column are cut into n_seg segments, one CTA each (short launches)
-    int vec_ok;                // 128-bit stores allowed (nE even, out 16-B aligned)
+    int vec_ok;                // 128-bit stores allowed (nE even, out 16-B aligned, even strides)
+    // output layout (K2 / K2s; K3 always writes the cube layout): yield (tl, dl, pol, row, e) of the shard goes to
+    // out[tl t_stride + dl d_stride - out_off + pol pol_stride + row row_stride + e].  Cube layout [T][D][pol][P][E]:
+    // d_stride = 4 nP nE, t_stride = nDs d_stride, pol_stride = nP nE, row_stride = nE, out_off = col0 d_stride.
+    long long t_stride, d_stride, pol_stride, row_stride, out_off;
     Physics ph;
 };
 
@@ -345,8 +349,8 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
     const PhiItems it = read_phi_items(a.tab, a.nP);
     const long long items = it.total();
     const bool vec = a.vec_ok != 0;
-    const long long rows_per_pol = a.nP * nE;
-    double* out_col = a.out + lcol * 4 * rows_per_pol + e0;
+    const long long rows_per_pol = a.pol_stride, rs = a.row_stride;
+    double* out_col = a.out + ((long long)tl * a.t_stride + (long long)dl * a.d_stride - a.out_off) + e0;
 
     auto col_field = [&](int k, int j) -> cplx {
         const double* d = cols + (k * NCOL) * NT + tid;
@@ -379,15 +383,15 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
 #pragma unroll 1
         for (int pol = 0; pol < 4; ++pol) {
             double* prow = out_col + pol * rows_per_pol;
-            double* pa = prow + (q0 + 1) * nE;                           // quads: rows j, H - j, j + H, 2 H - j
-            double* pb = prow + (it.H - q0 - 1) * nE;
-            double* pc = prow + (q0 + 1 + it.H) * nE;
-            double* pd = prow + (2 * it.H - q0 - 1) * nE;
+            double* pa = prow + (q0 + 1) * rs;                           // quads: rows j, H - j, j + H, 2 H - j
+            double* pb = prow + (it.H - q0 - 1) * rs;
+            double* pc = prow + (q0 + 1 + it.H) * rs;
+            double* pd = prow + (2 * it.H - q0 - 1) * rs;
             const long long pj = QUADS ? p0 * it.PSTEP : p0;
-            double* plo = prow + pj * nE;                                // pair item k: rows k PSTEP and k PSTEP + H
-            double* phi_ = prow + (pj + it.H) * nE;
-            double* psg = prow + (2 * it.H + s0) * nE;                   // un-paired rows
-            const long long pstride = QUADS ? it.PSTEP * nE : nE;
+            double* plo = prow + pj * rs;                                // pair item k: rows k PSTEP and k PSTEP + H
+            double* phi_ = prow + (pj + it.H) * rs;
+            double* psg = prow + (2 * it.H + s0) * rs;                   // un-paired rows
+            const long long pstride = QUADS ? it.PSTEP * rs : rs;
             if (pol == 3) {
                 Coef4 k[2];
 #pragma unroll
@@ -400,11 +404,11 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
                     for (int j = 0; j < 4; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
                 if (vec) {
-                    if (QUADS) sweep4_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
-                    sweep4<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                    if (QUADS) sweep4_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, rs, valid1);
+                    sweep4<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, rs, pstride, valid1);
                 } else {
-                    if (QUADS) sweep4_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
-                    sweep4<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                    if (QUADS) sweep4_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, rs, valid1);
+                    sweep4<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, rs, pstride, valid1);
                 }
             } else {
                 Coef7 k[2];
@@ -421,11 +425,11 @@ __global__ void __launch_bounds__(NT, (NT >= 256 ? 2 : 7)) yield_grid_kernel(con
                     for (int j = 0; j < 7; ++j) { k[q].r[j] = kk[j].re; k[q].i[j] = kk[j].im; }
                 }
                 if (vec) {
-                    if (QUADS) sweep7_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
-                    sweep7<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                    if (QUADS) sweep7_quads<true>(k[0], k[1], tq, nq, pa, pb, pc, pd, rs, valid1);
+                    sweep7<true>(k[0], k[1], tp, np, ns, plo, phi_, psg, rs, pstride, valid1);
                 } else {
-                    if (QUADS) sweep7_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, nE, valid1);
-                    sweep7<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, nE, pstride, valid1);
+                    if (QUADS) sweep7_quads<false>(k[0], k[1], tq, nq, pa, pb, pc, pd, rs, valid1);
+                    sweep7<false>(k[0], k[1], tp, np, ns, plo, phi_, psg, rs, pstride, valid1);
                 }
             }
         }
@@ -455,6 +459,7 @@ struct SparseArgs {
     int nDs, t0, d0;
     int n_tiles, chunk;        // energies tiles of SNT threads; columns per CTA
     const double* dinfo;       // [2]: {1.0 if thick_nm is uniformly spaced, its step} (thick_uniform_kernel)
+    long long t_stride, d_stride, pol_stride, row_stride, out_off;     // output layout, as in YieldArgs
     Physics ph;
 };
 
@@ -520,7 +525,6 @@ __global__ void __launch_bounds__(SNT, SSHG_SPARSE_MINB) yield_sparse_kernel(con
         e2[m] = ldc(a.eps2w + m * nE + e);
     }
     const double energy = a.energy[e];
-    const long long rows = 4 * a.nP * nE;                  // doubles per column
     ColumnStatic cs;
     PhaseWalk walk;
     const bool recur = a.dinfo[0] != 0.0 && a.ph.mref;
@@ -548,7 +552,7 @@ __global__ void __launch_bounds__(SNT, SSHG_SPARSE_MINB) yield_sparse_kernel(con
         } else {
             cd = column_dynamic(cs, energy, thick, a.ph);
         }
-        double* o = a.out + (col - a.col0) * rows + e;
+        double* o = a.out + ((long long)tl * a.t_stride + (long long)dl * a.d_stride - a.out_off) + e;
         for (long long p = 0; p < a.nP; ++p) {
             cplx x[NX];
 #pragma unroll
@@ -556,7 +560,7 @@ __global__ void __launch_bounds__(SNT, SSHG_SPARSE_MINB) yield_sparse_kernel(con
             double y[4];
             sparse_yields(cd, x, y);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) __stcs(o + (k * a.nP + p) * nE, y[k]);
+            for (int k = 0; k < 4; ++k) __stcs(o + k * a.pol_stride + p * a.row_stride, y[k]);
         }
     }
 }
@@ -661,7 +665,11 @@ constexpr int K2_SMALL_PER_SM = K2_SMALL_PER_SM_SMEM < 8 ? K2_SMALL_PER_SM_SMEM 
 
 }  // namespace
 
-static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where) {
+// layout: null = the cube layout [T][D][pol][P][E]; else {t_stride, d_stride, pol_stride, phi_stride} in doubles (energy
+// contiguous): the un-broadened yields of the whole grid written straight into a caller-defined device layout
+// (sshg_yield_broadcast).
+static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where,
+                      const int64_t* layout = nullptr) {
     SSHG_TRACE("sshg_yield");
     SSHG_REQUIRE(ctx && p && out, "sshg_yield: null argument");
     SSHG_REQUIRE(sigma_out >= 0.0 && isfinite(sigma_out), "sshg_yield: sigma_out must be finite and >= 0 (got %g)",
@@ -716,6 +724,10 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     if (p->phys.flags & SSHG_FLAG_STRICT_BROADENING) fused = false;
     if (opt.k3 == 0) fused = false;
     const bool two_pass = radius >= 1 && !fused;
+    if (layout) {
+        SSHG_REQUIRE(out_dev && radius == 0 && t0 == 0 && t1 == p->nT && d0 == 0 && d1 == p->nD,
+                     "sshg_yield: a caller-defined layout needs device output, no output broadening and the full grid");
+    }
 
     void* tab;
     if (int rc = sshg_scratch(ctx, 7, (size_t)(4 + 12 * p->nP) * 8, &tab)) return rc;
@@ -753,6 +765,11 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
 
     const int64_t cols = (int64_t)a.nTs * a.nDs;
     const int64_t per_col = 4 * p->nP * p->nE;            // doubles per column
+    a.d_stride = layout ? layout[1] : per_col;
+    a.t_stride = layout ? layout[0] : (int64_t)a.nDs * per_col;
+    a.pol_stride = layout ? layout[2] : p->nP * p->nE;
+    a.row_stride = layout ? layout[3] : p->nE;
+    const bool even_layout = !layout || ((layout[0] | layout[1] | layout[2] | layout[3]) % 2 == 0);
     SSHG_REQUIRE(cols * a.n_tiles < (1LL << 31), "sshg_yield: too many tiles for one launch");
     SSHG_CUDA(cudaFuncSetAttribute(yield_grid_kernel<NT_BIG, CHUNK_BIG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)grid_smem(NT_BIG, CHUNK_BIG)));
@@ -779,6 +796,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         sa.energy = a.energy; sa.theta_deg = a.theta_deg; sa.thick_nm = a.thick_nm; sa.phi_deg = (const double*)dphi;
         sa.nE = p->nE; sa.nP = p->nP; sa.nDs = a.nDs; sa.t0 = a.t0; sa.d0 = a.d0;
         sa.n_tiles = (int)((p->nE + SNT - 1) / SNT);
+        sa.t_stride = a.t_stride; sa.d_stride = a.d_stride; sa.pol_stride = a.pol_stride; sa.row_stride = a.row_stride;
         sa.ph = a.ph;
         // uniformly spaced thicknesses -> phase factors by recurrence (option "k2_recurrence" = 0 disables)
         void* dinfo;
@@ -861,6 +879,7 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
             b.col0 = c0;
             b.ncols = nc;
             b.out = dst;
+            b.out_off = layout ? 0 : c0 * per_col;           // dst points at column c0
             // columns per CTA: enough CTAs for ~8 waves of 3 CTAs per SM, at most 32 columns each
             const long long want = 8LL * 3 * ctx->num_sms;
             long long chunk = nc * b.n_tiles / want;
@@ -875,7 +894,8 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
         YieldArgs b = a;
         b.col0 = c0;
         b.out = dst;
-        b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0);
+        b.out_off = layout ? 0 : c0 * per_col;               // dst points at column c0
+        b.vec_ok = (p->nE % 2 == 0) && ((uintptr_t)dst % 16 == 0) && even_layout;
         b.n_seg = pick_segments(nc * a.n_tiles, nt == NT_BIG ? 2 : K2_SMALL_PER_SM, SSHG_NSEG_WAVES);
         SSHG_REQUIRE(nc * a.n_tiles * b.n_seg < (1LL << 31), "sshg_yield: too many tiles for one launch");
         const unsigned ctas = (unsigned)(nc * a.n_tiles * b.n_seg);
@@ -961,6 +981,21 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     // copy stream while slab k+1 is computed.
     void* buf[2];
     if (int rc = sshg_scratch(ctx, 8, slab_bytes, &buf[0])) return rc;
+    {
+        // A pageable destination (a fresh NumPy array) goes through the threaded staged copy: the driver's own pageable
+        // path runs at 4 GB/s into memory that has never been touched (one thread takes the page faults).
+        cudaPointerAttributes at;
+        const bool pinned = cudaPointerGetAttributes(&at, out) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        (void)cudaGetLastError();
+        if (!pinned) {
+            for (int64_t c0 = 0; c0 < cols; c0 += cols_per_slab) {
+                const int64_t nc = (cols - c0 < cols_per_slab) ? cols - c0 : cols_per_slab;
+                if (int rc = produce(c0, nc, (double*)buf[0])) return rc;
+                if (int rc = sshg_copy_out(ctx, out + c0 * per_col, buf[0], (size_t)nc * per_col * 8)) return rc;
+            }
+            return SSHG_OK;
+        }
+    }
     if (cols_per_slab < cols) {
         if (int rc = sshg_scratch(ctx, 9, slab_bytes, &buf[1])) return rc;
     } else {
@@ -990,6 +1025,70 @@ extern "C" int sshg_yield(sshg_ctx* ctx, const sshg_problem* p, double* out, int
 
 extern "C" int sshg_yield_broadened(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, double* out, int where) {
     return yield_impl(ctx, p, sigma_out, out, where);
+}
+
+// The tail of shgyield() for LARGE NumPy broadcasts with outer-product structure (the reference's only way to express a
+// sweep: energy[E], theta[T, 1], phi[P, 1, 1], ...; shg.py:381-437): the yields of the grid are written by K2 / K2s
+// straight into the layout of the broadcast result ([pol][...result axes...], energy contiguous), broad(., sigma_out)
+// runs over EVERY axis of each polarisation's array on the device (scipy.ndimage.gaussian_filter semantics, shg.py:26-28,
+// 433-436), and the four arrays go to the host by the threaded staged copy.  No host-side transposes or re-uploads.
+extern "C" int sshg_yield_broadcast(sshg_ctx* ctx, const sshg_problem* p, const int64_t strides[4], double sigma_out,
+                                    int32_t ndim, const int64_t* shape, double* const out_host[4]) {
+    SSHG_TRACE("sshg_yield_broadcast");
+    SSHG_REQUIRE(ctx && p && strides && out_host && (shape || ndim == 0), "sshg_yield_broadcast: null argument");
+    SSHG_REQUIRE(ndim >= 0 && ndim <= 15, "sshg_yield_broadcast: ndim must be in 0 .. 15 (got %d)", (int)ndim);
+    SSHG_REQUIRE(sigma_out >= 0.0 && isfinite(sigma_out), "sshg_yield_broadcast: sigma_out must be finite and >= 0");
+    SSHG_REQUIRE(p->nE > 0 && p->nT > 0 && p->nP > 0 && p->nD > 0, "sshg_yield_broadcast: empty grid");
+    int64_t total = 1;
+    for (int a = 0; a < ndim; ++a) {
+        SSHG_REQUIRE(shape[a] > 0, "sshg_yield_broadcast: extents must be positive");
+        total *= shape[a];
+    }
+    SSHG_REQUIRE(total == p->nE * p->nT * p->nP * p->nD, "sshg_yield_broadcast: shape does not match the grid");
+    SSHG_REQUIRE(strides[2] == total, "sshg_yield_broadcast: the polarisation stride must be the size of one result array");
+    for (int k = 0; k < 4; ++k) SSHG_REQUIRE(out_host[k], "sshg_yield_broadcast: null output array");
+    // the largest element index the layout can reach must stay inside one polarisation's array
+    SSHG_REQUIRE(strides[0] >= 0 && strides[1] >= 0 && strides[3] >= 0 &&
+                     (p->nT - 1) * strides[0] + (p->nD - 1) * strides[1] + (p->nP - 1) * strides[3] + p->nE <= total,
+                 "sshg_yield_broadcast: layout exceeds the result array");
+    SSHG_CUDA(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)total * 4 * 8;
+    const bool blur = sigma_out > 1e-15 && ndim > 0;
+    // large intermediates are not kept in the context's scratch slots
+    void *a = nullptr, *b = nullptr;
+    auto release = [&]() {
+        if (a) cudaFree(a);
+        if (b) cudaFree(b);
+    };
+    if (cudaMalloc(&a, bytes) != cudaSuccess || (blur && cudaMalloc(&b, bytes) != cudaSuccess)) {
+        (void)cudaGetLastError();
+        release();
+        sshg_set_error("sshg_yield_broadcast: device allocation of %zu bytes failed", bytes * (blur ? 2 : 1));
+        return SSHG_ENOMEM;
+    }
+    int rc = yield_impl(ctx, p, 0.0, (double*)a, SSHG_HOST | SSHG_OUT_DEVICE, strides);
+    const double* res = (const double*)a;
+    if (!rc && blur) {
+        // one pass per axis of the result, ping-pong between the two buffers (as sshg_gauss_nd_device, which would need a
+        // third one); the four polarisations are the leading, un-filtered axis
+        double *src = (double*)a, *dst = (double*)b;
+        for (int ax = 0; ax < ndim && !rc; ++ax) {
+            int64_t outer = 4, inner = 1;
+            for (int j = 0; j < ax; ++j) outer *= shape[j];
+            for (int j = ax + 1; j < ndim; ++j) inner *= shape[j];
+            const int64_t n = shape[ax];
+            if (inner == 1) rc = sshg_gauss_device(ctx, src, dst, outer, n, n, 1, sigma_out);
+            else rc = sshg_gauss_device_ex(ctx, src, dst, outer * inner, n, 1, inner, inner, n * inner, sigma_out);
+            double* t = src;
+            src = dst;
+            dst = t;
+        }
+        res = src;
+    }
+    for (int k = 0; k < 4 && !rc; ++k) rc = sshg_copy_out(ctx, out_host[k], res + (size_t)k * total, (size_t)total * 8);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess && !rc) rc = sshg_cuda_fail(cudaGetLastError(), "sync", __FILE__, __LINE__);
+    release();
+    return rc;
 }
 
 static int points_impl(sshg_ctx* ctx, const sshg_points* p, double* out, int where, bool amp) {

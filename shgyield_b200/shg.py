@@ -474,6 +474,38 @@ def _points_tail(prep, e_arr, t_arr, p_arr, d_arr, shape, n, sigma_out, mref, co
     return out
 
 
+def _broadcast_tail(prep, e_arr, t_arr, p_arr, d_arr, ax, shape, sigma_out, mref, consts):
+    """Large outer-product broadcasts whose last axis is the energy: [pp, ps, sp, ss] arrays of `shape`, or None when the
+    device cannot hold the intermediates (the caller then takes the slab-wise path)."""
+    from .grid import _problem
+    ctx = _lib.context()
+    ndim = len(shape)
+    elem = [1] * ndim                               # C-contiguous element strides of the result
+    for i in range(ndim - 2, -1, -1):
+        elem[i] = elem[i + 1] * shape[i + 1]
+    total = int(np.prod(shape, dtype=np.int64))
+
+    def axis_stride(axes):                          # an operand varies along at most one axis here, or is a scalar
+        if len(axes) > 1:
+            return None
+        return elem[axes[0]] if axes else 0
+    st = [axis_stride(ax[0]), axis_stride(ax[1]), total, axis_stride(ax[2])]       # theta, thick, pol, phi
+    if any(v is None for v in st):
+        return None                                 # an operand spread over several axes: not a 1-D axis of a grid
+    keep = []
+    p = _problem(e_arr.ravel(), t_arr.ravel(), p_arr.ravel(), d_arr.ravel(), prep.eps1w, prep.eps2w, prep.chi_rot,
+                 _physics(consts, mref), None, None, keep)
+    outs = [np.empty(shape) for _ in range(4)]
+    strides = (C.c_int64 * 4)(*st)
+    shp = (C.c_int64 * max(ndim, 1))(*shape)
+    ptrs = (C.c_void_p * 4)(*[o.ctypes.data for o in outs])
+    rc = ctx.lib.sshg_yield_broadcast(ctx.handle, C.byref(p), strides, float(sigma_out), ndim, shp, ptrs)
+    if rc == _lib.SSHG_ENOMEM:
+        return None
+    _lib.check(rc, ctx.lib)
+    return outs
+
+
 def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, sigma_eps=0.0, sigma_chi=0.0,
              sigma_out=5.0, mode="3-layer", mref=True):
     """
@@ -497,7 +529,12 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
     if n >= GRID_MIN_POINTS:
         ax = [_axes_of(a.shape, ndim) for a in (t_arr, d_arr, p_arr, e_arr)]       # cube order T, D, P, E
         flat = [a for axes in ax for a in axes]
-        if len(set(flat)) == len(flat):                                             # outer-product structure
+        if len(set(flat)) == len(flat) and ax[3] == (ndim - 1,) and e_arr.size > 1:
+            # outer-product structure with the energy as the last axis (the reference's sweep idiom: energy[E],
+            # theta[T, 1], phi[P, 1, 1]): the kernels write straight into the layout of the result, the output
+            # broadening of every axis runs on the device, four arrays come back (sshg_yield_broadcast)
+            stack = _broadcast_tail(prep, e_arr, t_arr, p_arr, d_arr, ax, shape, sigma_out, mref, consts)
+        if stack is None and len(set(flat)) == len(flat):                           # outer-product structure
             from .grid import yield_grid_host
             cube = yield_grid_host(e_arr.ravel(), t_arr.ravel(), p_arr.ravel(), d_arr.ravel(), prep.eps1w, prep.eps2w,
                                    prep.chi_rot, mref=mref, consts=consts)          # [T, D, 4, P, E]
@@ -526,7 +563,8 @@ def shgyield(energy, eps_m1, eps_m2, eps_m3, chi2, theta, phi, thick, gamma=90, 
             stack = np.empty((4,) + shape)
     out = {"energy": energy, "phi": phi}
     for k, pol in enumerate(POLS):
-        out[pol] = np.array(stack[k])             # own array per polarisation (0-d stays a 0-d ndarray)
+        # own array per polarisation (0-d stays a 0-d ndarray); the broadcast tail already made four of them
+        out[pol] = stack[k] if isinstance(stack, list) else np.array(stack[k])
     return out
 
 

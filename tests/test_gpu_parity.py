@@ -338,6 +338,64 @@ def test_api_grid_path_matches_points_path(shg, spectra, monkeypatch):
         assert ok, (pol, msg)
 
 
+@pytest.mark.parametrize("tail", ["device", "slabs"])
+@pytest.mark.parametrize("name", ["bcast3d", "bcast3d_blur", "bcast_thick"])
+def test_api_broadcast_tails_match_reference(shg, spectra, monkeypatch, name, tail):
+    """Large outer-product broadcasts take sshg_yield_broadcast (kernels write the result layout, N-D output broadening
+    on the device, four arrays come back); without device memory for it, or with another axis order, the slab-wise
+    path with host-side transposes.  Both against the reference's outputs, incl. sigma_out blurring EVERY axis."""
+    gold = np.load(os.path.join(G, "ref_api_cases.npz"))
+    _, mat, kw = next(c for c in cases.API_CASES if c[0] == name)
+    m1, m2, m3, chi2 = cases.MATERIALS[mat](spectra)
+    monkeypatch.setattr(shg, "GRID_MIN_POINTS", 1)
+    calls = []
+    real = shg._broadcast_tail
+    monkeypatch.setattr(shg, "_broadcast_tail", lambda *a: (calls.append(1), real(*a) if tail == "device" else None)[1])
+    res = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, **kw)
+    assert calls, "the energy is the last axis of these cases"
+    for pol in cases.POLS:
+        want = gold[name + "_" + pol]
+        assert res[pol].shape == want.shape and res[pol].flags["C_CONTIGUOUS"] and res[pol].flags["OWNDATA"]
+        ok, msg = cases.parity_ok(res[pol], want, rtol=RTOL, scale=cases.case_scale(gold, name + "_"))
+        assert ok, (name, tail, pol, msg)
+
+
+def test_api_broadcast_tail_large_and_other_axis_orders(shg, spectra, monkeypatch):
+    """A 173 MB broadcast (threaded staged copies into four fresh arrays) is bitwise the transposed cube of
+    shgyield_grid; with sigma_out the device tail agrees with the slab-wise one; an axis order with theta last, a
+    thickness axis and scalar operands go through whichever tail applies and agree with the point-list path."""
+    from shgyield_b200 import grid
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    E, T, P = np.linspace(0.4, 4.9, 2000), np.arange(0, 90, 3.0), np.arange(0, 360, 4.0)
+    kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, thick=10.0, gamma=0)
+    res = shg.shgyield(energy=E, theta=T[:, None], phi=P[:, None, None], sigma_out=0.0, **kw)
+    cube = grid.shgyield_grid(E, m1, m2, m3, chi2, T, P, 10.0, gamma=0, device=False)["cube"]     # [T, 1, 4, P, E]
+    for k, pol in enumerate(cases.POLS):
+        assert np.array_equal(res[pol], np.transpose(cube[:, 0, k], (1, 0, 2))), pol
+    blur = shg.shgyield(energy=E, theta=T[:, None], phi=P[:, None, None], sigma_out=1.5, **kw)
+    with monkeypatch.context() as mp:
+        mp.setattr(shg, "_broadcast_tail", lambda *a: None)
+        slabs = shg.shgyield(energy=E, theta=T[:, None], phi=P[:, None, None], sigma_out=1.5, **kw)
+    for pol in cases.POLS:
+        np.testing.assert_allclose(blur[pol], slabs[pol], rtol=0, atol=1e-14 * np.max(slabs[pol]))
+    # other structures (small, through the lowered threshold): thickness axis first, phi scalar; theta last
+    monkeypatch.setattr(shg, "GRID_MIN_POINTS", 1)
+    e, t, d = np.linspace(0.5, 4.5, 60), np.array([10.0, 40.0, 70.0]), np.arange(1.0, 9.0)
+    shapes = [dict(energy=e, theta=t[:, None], phi=30.0, thick=d[:, None, None]),
+              dict(energy=e[:, None], theta=t, phi=30.0, thick=12.0),
+              dict(energy=e, theta=t[:, None, None], phi=np.array([0.0, 45.0])[:, None], thick=d[:, None, None, None])]
+    for sh in shapes:
+        for so in (0.0, 0.8):
+            got = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, gamma=20, sigma_out=so, **sh)
+            with monkeypatch.context() as mp:
+                mp.setattr(shg, "GRID_MIN_POINTS", 10 ** 12)          # point-list path
+                want = shg.shgyield(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, gamma=20, sigma_out=so, **sh)
+            sc = max(np.max(want[p]) for p in cases.POLS)
+            for pol in cases.POLS:
+                ok, msg = cases.parity_ok(got[pol], want[pol], rtol=RTOL, scale=sc)
+                assert ok and got[pol].shape == want[pol].shape, (sorted(sh), so, pol, msg)
+
+
 def test_golden_si111_reference_out(shg, spectra):
     """The reference's own golden file example/reference/si111-reference.out (printed %.8e)."""
     gold = np.load(os.path.join(G, "si111_reference_out.npz"))
