@@ -514,10 +514,7 @@ extern "C" int sshg_gauss1d(sshg_ctx* ctx, const double* in, double* out, int64_
         if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
     }
     if (int rc = sshg_gauss_device(ctx, (const double*)din, (double*)dout, rows, n, row_stride, elem_stride, sigma)) return rc;
-    if (!out_dev) {
-        SSHG_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    if (!out_dev) return sshg_copy_out(ctx, out, dout, bytes);      // large pageable results: threaded staged copy
     return SSHG_OK;
 }
 
@@ -577,9 +574,6 @@ extern "C" int sshg_gauss_nd(sshg_ctx* ctx, const double* in, double* out, int32
         if (int rc = sshg_scratch(ctx, 11, bytes, &dout)) return rc;
     }
     if (int rc = sshg_gauss_nd_device(ctx, (const double*)din, (double*)dout, 0, ndim, shape, sigma)) return rc;
-    if (!out_dev) {
-        SSHG_CUDA(cudaMemcpyAsync(out, dout, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
-    }
+    if (!out_dev) return sshg_copy_out(ctx, out, dout, bytes);      // large pageable results: threaded staged copy
     return SSHG_OK;
 }
