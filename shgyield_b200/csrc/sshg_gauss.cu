@@ -35,9 +35,6 @@ __device__ __forceinline__ long long reflect(long long i, long long n) {
 constexpr int ST = 128;             // threads per CTA
 constexpr int SR = sshg::SR;        // consecutive outputs per thread
 constexpr int STILE = ST * SR;      // outputs per CTA
-using sshg::fir_full;
-using sshg::fir_head;
-using sshg::fir_tail;
 
 // smem: xs[STILE + 2r + SR] samples (zero padded), then wext[2r + 1 + 3 SR] taps:
 // wext[k] = w_full[k - (SR-1)] for 0 <= k - (SR-1) <= 2r, else 0.
@@ -368,6 +365,65 @@ __global__ void __launch_bounds__(GT) gauss_tiled_kernel(const double* __restric
     }
 }
 
+// ---- a non-contiguous axis of an N-D array: column kernel ------------------------------------------------------------
+// broad() of an N-D result filters EVERY axis (scipy.ndimage.gaussian_filter; the reference's shgyield() does that to
+// broadcast results, shg.py:433-436).  Along an axis that is not the last one, the elements of a signal are `inner`
+// doubles apart, but `inner` neighbouring signals are contiguous: a CTA stages a tile [positions along the axis + halo] x
+// [32 neighbouring signals] (coalesced 256-byte rows), lane = signal, warp = a group of SR consecutive outputs along the
+// axis, and every thread runs the register-window FIR of the contiguous kernels down its column of the tile
+// (conflict-free: the lanes of a warp read neighbouring words).  The strided kernel above stages 1024 + 2 r samples per
+// CTA with `inner`-strided loads (one 32-byte sector per sample) and fills its CTAs badly on short axes (90 thetas).
+constexpr int CW = 32;              // signals per CTA (one per lane)
+constexpr int CG = 8;               // output groups per CTA (one per warp): CG * SR outputs along the axis
+
+__global__ void __launch_bounds__(CW * CG) gauss_column_kernel(const double* __restrict__ in, double* __restrict__ out,
+                                                               const double* __restrict__ taps, long long n, long long inner,
+                                                               int r, int tiles_a, int tiles_c) {
+    extern __shared__ double sm[];
+    constexpr int TA = CG * SR;                    // outputs along the axis per CTA
+    const int span_max = TA + 2 * r + SR;          // row count the shared-memory layout is planned for
+    const int ntap = 2 * r + 1 + 3 * SR;
+    double* xs = sm;                               // [span][CW]
+    double* wext = sm + (size_t)span_max * CW;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long blk = blockIdx.x;
+    const long long tc = blk % tiles_c, ta = (blk / tiles_c) % tiles_a, o = blk / tiles_c / tiles_a;
+    const long long a0 = ta * TA, col = tc * CW + lane;
+    // output groups of this tile that exist (a short axis, or the last tile of a long one): the others stage and compute nothing
+    const int groups = (int)((((n - a0 < TA) ? n - a0 : TA) + SR - 1) / SR);
+    const int used = groups * SR + 2 * r;          // staged positions that feed an output of this tile
+    const int span = used + SR;                    // incl. zero padding (the window of the last output group over-reads)
+    const bool colok = col < inner;
+    const double* src = in + o * n * inner;
+    double* dst = out + o * n * inner;
+    for (int j = warp; j < span; j += CG) {
+        const long long a = a0 - r + j;
+        double v = 0.0;                            // positions beyond n - 1 + r feed no valid output
+        if (j < used && colok && a < n + r) v = src[reflect(a, n) * inner + col];
+        xs[j * CW + lane] = v;
+    }
+    for (int k = threadIdx.x; k < ntap; k += CW * CG) {
+        const int j = k - (SR - 1);                // index into the full symmetric kernel
+        wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
+    }
+    __syncthreads();
+    double acc[SR], wr[SR];
+#pragma unroll
+    for (int q = 0; q < SR; ++q) {
+        acc[q] = 0.0;
+        wr[q] = wext[q];
+    }
+    if (warp >= groups) return;
+    sshg::fir_window<CW>(xs + (warp * SR) * CW + lane, wext, r, acc, wr);
+    if (colok) {
+#pragma unroll
+        for (int q = 0; q < SR; ++q) {
+            const long long a = a0 + warp * SR + q;
+            if (a < n) dst[a * inner + col] = acc[q];
+        }
+    }
+}
+
 // Fallback for radii whose halo does not fit in shared memory.
 __global__ void gauss_direct_kernel(const double* __restrict__ in, double* __restrict__ out,
                                     const double* __restrict__ taps, long long rows, long long n,
@@ -469,6 +525,25 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         }
         if (rc != 1) return rc;
     }
+    // a non-contiguous axis of a C-contiguous N-D array (neighbouring signals contiguous): column kernel
+    const size_t smem_col = ((size_t)(CG * SR + 2 * r + SR) * CW + (size_t)(2 * r + 1 + 3 * SR)) * 8;
+    // (rows k = o * inner + c at o * n * inner + c, elements `inner` apart; a single block of interleaved rows -- the
+    // FIRST axis of an array -- arrives as rows == inner_rows)
+    const long long inner_c = inner_rows < rows ? inner_rows : rows;
+    if (row_stride == 1 && elem_stride == inner_c && elem_stride > 1 && (rows == inner_c || outer_stride == n * inner_c) &&
+        inner_c >= 8 && rows % inner_c == 0 && smem_col <= SMEM_CAP) {
+        const long long outer = rows / inner_c;
+        const long long inner_rows = inner_c;
+        const long long tiles_a = (n + CG * SR - 1) / (CG * SR), tiles_c = (inner_rows + CW - 1) / CW;
+        if (outer * tiles_a * tiles_c < (1LL << 31)) {
+            SSHG_CUDA(cudaFuncSetAttribute(gauss_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+            gauss_column_kernel<<<(unsigned)(outer * tiles_a * tiles_c), CW * CG, smem_col, ctx->stream>>>(
+                din, dout, (const double*)dw, n, inner_rows, (int)r, (int)tiles_a, (int)tiles_c);
+            SSHG_CUDA(cudaGetLastError());
+            ctx->launches++;
+            return SSHG_OK;
+        }
+    }
     const size_t smem_stream = (size_t)(STILE + 2 * r + SR + 2 * r + 1 + 3 * SR) * 8;
     const size_t smem_tiled = (size_t)(GTILE + 2 * r + r + 1) * 8;
     if (elem_stride == 1 && plain && smem_stream <= SMEM_CAP) {
@@ -477,7 +552,9 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         SSHG_CUDA(cudaFuncSetAttribute(gauss_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
         gauss_stream_kernel<<<(unsigned)(rows * tiles), ST, smem_stream, ctx->stream>>>(din, dout, (const double*)dw, n,
                                                                                       row_stride, (int)r, tiles);
-    } else if (smem_tiled <= SMEM_CAP) {
+    } else if (smem_tiled <= SMEM_CAP && n >= 64) {
+        // (short strided axes -- the four-entry axis of a [4, P, E] stack, an axis of extent 1 of a broadcast result -- would
+        // make one CTA stage 1024 + 2 r samples for a handful of outputs per row: they take the direct kernel below)
         const int tiles = (int)((n + GTILE - 1) / GTILE);
         SSHG_REQUIRE(rows * tiles < (1LL << 31), "sshg_gauss1d: too many tiles");
         SSHG_CUDA(cudaFuncSetAttribute(gauss_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));

@@ -27,6 +27,7 @@ struct sshg_trace_range {
 #define SCR_PTS_Y 23     // ... un-broadened yields [4][n]
 #define SCR_PTS_OUT 24   // ... broadened yields [4][n]
 #define SCR_SPLTAB 25    // spline: cyclic-reduction coefficient tables of the cached axis
+#define SCR_BCAST 26     // sshg_yield_broadcast: result layout buffers (slots 26, 27) of calls up to 256 MB
 
 // Test / tuning switches of a context (sshg_ctx_set_option, include/sshg.h); -1 = the library decides.
 struct sshg_options {

@@ -1054,13 +1054,20 @@ extern "C" int sshg_yield_broadcast(sshg_ctx* ctx, const sshg_problem* p, const 
     SSHG_CUDA(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)total * 4 * 8;
     const bool blur = sigma_out > 1e-15 && ndim > 0;
-    // large intermediates are not kept in the context's scratch slots
+    // intermediates up to 256 MB live in the context's scratch slots (no allocation per call); larger ones are
+    // allocated for the call and released again
     void *a = nullptr, *b = nullptr;
+    const bool own = bytes > ((size_t)256 << 20);
     auto release = [&]() {
-        if (a) cudaFree(a);
-        if (b) cudaFree(b);
+        if (own && a) cudaFree(a);
+        if (own && b) cudaFree(b);
     };
-    if (cudaMalloc(&a, bytes) != cudaSuccess || (blur && cudaMalloc(&b, bytes) != cudaSuccess)) {
+    if (!own) {
+        if (int rc = sshg_scratch(ctx, SCR_BCAST, bytes, &a)) return rc;
+        if (blur) {
+            if (int rc = sshg_scratch(ctx, SCR_BCAST + 1, bytes, &b)) return rc;
+        }
+    } else if (cudaMalloc(&a, bytes) != cudaSuccess || (blur && cudaMalloc(&b, bytes) != cudaSuccess)) {
         (void)cudaGetLastError();
         release();
         sshg_set_error("sshg_yield_broadcast: device allocation of %zu bytes failed", bytes * (blur ? 2 : 1));

@@ -69,6 +69,22 @@ def test_gauss_huge_radius_and_nd(shg):
     np.testing.assert_allclose(shg.broadC(z, 2.5), want, rtol=0, atol=1e-14)
 
 
+@pytest.mark.parametrize("shape", [(90, 7, 50), (361, 1, 126), (4, 100, 33), (75, 64), (200, 9), (3, 130, 8, 40), (700, 33)])
+@pytest.mark.parametrize("sigma", [0.4, 1.5, 5.0, 12.0, 30.0])
+def test_gauss_nd_every_axis(shg, shape, sigma):
+    """broad() of an N-D array filters every axis like scipy.ndimage.gaussian_filter: the last axis with the contiguous
+    kernels, the others with the column kernel (32 neighbouring signals per CTA, register window down the column), very
+    short axes and narrow trailing axes with the direct / strided kernels; a NaN poisons exactly its neighbourhood."""
+    from scipy import ndimage
+    x = np.random.default_rng(len(shape) * 1000 + shape[0]).normal(size=shape)
+    np.testing.assert_allclose(shg.broad(x, sigma), ndimage.gaussian_filter(x, sigma), rtol=0, atol=2e-14)
+    x[tuple(s // 2 for s in shape)] = np.nan
+    got, want = shg.broad(x, sigma), ndimage.gaussian_filter(x, sigma)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_allclose(got[ok], want[ok], rtol=0, atol=2e-14)
+
+
 @pytest.mark.parametrize("sigma", [2.0, 3.3, 5.0, 10.0])
 def test_gauss_nan_stays_within_the_radius(shg, sigma):
     """An Inf/NaN sample poisons exactly the outputs within the radius, as in SciPy (taps that do not

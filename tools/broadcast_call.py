@@ -18,7 +18,8 @@ from shgyield_b200.synthetic import si111_material  # noqa: E402
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
 m1, m2, m3, chi2 = si111_material()
 kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, thick=10.0, gamma=0)
-cases_ = {"E500_T30_P72": (np.linspace(0.5, 5.0, 500), np.arange(0, 90, 3.0), np.arange(0, 360, 5.0)),
+cases_ = {"E126_T1_P361": (np.linspace(1.25, 2.5, 126), np.array([65.0]), np.arange(0, 361.0)),
+          "E500_T30_P72": (np.linspace(0.5, 5.0, 500), np.arange(0, 90, 3.0), np.arange(0, 360, 5.0)),
           "config3_E2000_T90_P360": (np.linspace(0.005, 10.0, 2000), np.arange(0, 90, 1.0), np.arange(0, 360, 1.0))}
 for name, (E, T, P) in cases_.items():
     pts = 4 * E.size * T.size * P.size
@@ -26,7 +27,7 @@ for name, (E, T, P) in cases_.items():
         call = lambda: shg.shgyield(energy=E, theta=T[:, None], phi=P[:, None, None], sigma_out=sigma_out, **kw)
         call()
         t0 = time.perf_counter()
-        reps = 3
+        reps = 3 if pts > 10 ** 7 else 30
         for _ in range(reps):
             r = call()
         dt = (time.perf_counter() - t0) / reps
