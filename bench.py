@@ -510,6 +510,24 @@ def run_ours(args):
     h2d = sum(int(v.nbytes) for v in host_in.values())
     d2h = int(host_out.nbytes)
     e2e_pts = n_e2e * 4 * N_PHI * N_ENERGY
+    # the same call with an ordinary (pageable, never touched) NumPy array per step as the result -- what a caller gets
+    # who does not ask for page-locked memory: the library copies through page-locked staging buffers with several host
+    # threads (sshg_copy_out).  Single-GPU runs only, 8 thetas per step.
+    e2e_pageable = None
+    if rank == 0 and world == 1:
+        n_pg = min(8, n_e2e)
+        pg_times = []
+        for _ in range(3):
+            fresh = np.empty((n_pg, 1, 4, N_PHI, N_ENERGY))
+            t0 = time.perf_counter()
+            grid.yield_grid_host(host_in["energy"], host_in["theta"], host_in["phi"], host_in["thick"], host_in["eps1w"],
+                                 host_in["eps2w"], host_in["chi2"], consts=consts, t_range=(t_lo, t_lo + n_pg), out=fresh)
+            pg_times.append(time.perf_counter() - t0)
+            del fresh
+        pg_pts = n_pg * 4 * N_PHI * N_ENERGY
+        e2e_pageable = {"value": pg_pts / min(pg_times[1:]), "unit": "points/s", "d2h_gbs": 8e-9 * pg_pts / min(pg_times[1:]),
+                        "sample": "%d thetas per call into a fresh np.empty array (first-touch page faults included), "
+                                  "best of 2 after one warm-up call" % n_pg}
 
     # ---- the one collective of the path: gather of the slabs onto rank 0 (reported separately) --------
     gather = None
@@ -634,7 +652,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(),
             "run": {"shards": "theta shards x%d" % world, "bytes_written_per_gpu_per_step": 8.0 * my_pts},
-            "e2e": {"value": sum_e2e_pts * e2e_steps / e2e_s, "unit": "points/s",
+            "e2e": {"pageable_result": e2e_pageable, "value": sum_e2e_pts * e2e_steps / e2e_s, "unit": "points/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "sample": "sshg_yield with host buffers on the first %d thetas of each rank's shard "
                               "(%.3g points/step/GPU), pinned result buffer, %d steps" % (n_e2e, e2e_pts, e2e_steps),
