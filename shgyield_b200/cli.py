@@ -44,7 +44,8 @@ def main(argv=None) -> int:
         try:
             res = shgyield_grid(device=True, shard=(rank, world), gather="peer", **cfg)
             if rank == 0:
-                cube = res["cube"].cpu().numpy()
+                from .grid import to_host
+                cube = to_host(res["cube"])
                 res = dict(res, cube=cube, **{pol: cube[:, :, k] for k, pol in enumerate(("pp", "ps", "sp", "ss"))})
             dist.barrier()
         finally:

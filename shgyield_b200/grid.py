@@ -301,6 +301,22 @@ class PeerCube:
             pass
 
 
+def to_host(tensor) -> np.ndarray:
+    """A contiguous float64 CUDA tensor as a fresh NumPy array, copied by the library's threaded staged copy
+    (sshg_download: page-locked staging buffers, several host threads take the first-touch page faults) -- about seven
+    times faster into new memory than tensor.cpu().numpy() for a multi-GB cube."""
+    import torch
+    if not (tensor.is_cuda and tensor.dtype == torch.float64 and tensor.is_contiguous()):
+        raise ValueError("to_host needs a contiguous float64 CUDA tensor")
+    out = np.empty(tuple(tensor.shape))
+    if out.size == 0:
+        return out
+    torch.cuda.current_stream(tensor.device).synchronize()
+    ctx = _lib.context(tensor.device.index)
+    _lib.check(ctx.lib.sshg_download(ctx.handle, out.ctypes.data, tensor.data_ptr(), out.nbytes), ctx.lib)
+    return out
+
+
 def broaden_energy_device(cube, sigma):
     """K1 along the energy (last, contiguous) axis of a device cube; returns a new tensor."""
     import torch

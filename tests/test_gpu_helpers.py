@@ -197,3 +197,21 @@ def test_points_broadened_large_broadcast_takes_the_unstaged_path():
     # compare with the full two-axis filter of the first 200 rows (radius 4 along axis 0)
     full = orc.gaussian_filter1d(orc.gaussian_filter1d(want[2].reshape(shape)[:300], 1.0, axis=0), 1.0, axis=1)[:200]
     assert np.max(np.abs(got[2].reshape(shape)[:200] - full)) <= 1e-10 * np.max(np.abs(full))
+
+
+def test_to_host_and_download_match_torch():
+    """grid.to_host / sshg_download: threaded staged copies (above 32 MB) and the direct copy (below, and into
+    page-locked memory) deliver the same bytes as torch's own copy, at sizes around the 64 MB staging chunks."""
+    import torch
+    from shgyield_b200 import _lib, grid
+    ctx = _lib.context(0)
+    for n in (1, 1000, (32 << 20) // 8 - 1, (32 << 20) // 8 + 3, (64 << 20) // 8, (64 << 20) // 8 + 1, 3 * (64 << 20) // 8 + 12345):
+        t = torch.rand(n, dtype=torch.float64, device="cuda")
+        assert np.array_equal(grid.to_host(t), t.cpu().numpy()), n
+    t = torch.rand((5, 3, 1000, 999), dtype=torch.float64, device="cuda")
+    assert np.array_equal(grid.to_host(t), t.cpu().numpy())
+    pin = _lib.pinned_empty((t.numel(),))
+    _lib.check(ctx.lib.sshg_download(ctx.handle, pin.ctypes.data, t.data_ptr(), pin.nbytes), ctx.lib)
+    assert np.array_equal(pin, t.cpu().numpy().ravel())
+    _lib.pinned_free(pin)
+    assert grid.to_host(torch.empty((0, 4), dtype=torch.float64, device="cuda")).shape == (0, 4)
