@@ -373,6 +373,26 @@ def run_configs(ctx, dev, consts, peak, fp64_peak):
             else:
                 r["bound"], r["frac"] = "fp64", (r["alg_fp64_tflops"] / fp64_peak) if fp64_peak else None
             entry["sigma_out_%g" % sigma] = r
+        if tag == "config3":
+            # the same map through the DROP-IN call, written the reference's way -- shg.shgyield(energy[E], theta[T, 1],
+            # phi[P, 1, 1]), host arrays in, four fresh NumPy arrays out, sigma_out over every axis like the reference --
+            # wall clock, best of 3 after one warm-up call (sshg_yield_broadcast + threaded staged copies)
+            kw = dict(eps_m1=m1, eps_m2=m2, eps_m3=m3, chi2=chi2, thick=float(np.ravel(axes["thick"])[0]),
+                      gamma=axes["gamma"])
+            for sigma in (0.0, 5.0):
+                call = lambda: shg.shgyield(energy=axes["energy"], theta=axes["theta"][:, None],
+                                            phi=axes["phi"][:, None, None], sigma_out=sigma, **kw)
+                call()
+                best = None
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    r = call()
+                    dt = time.perf_counter() - t0
+                    best = dt if best is None else min(best, dt)
+                    del r
+                entry["through_shgyield_sigma_out_%g" % sigma] = {
+                    "s_per_call": best, "points_per_s": pts / best, "result_gbs": 8e-9 * pts / best,
+                    "how": "host arrays in, four fresh NumPy arrays [P, T, E] out"}
         res[tag] = entry
         del out
     torch.cuda.empty_cache()
