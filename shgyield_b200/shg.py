@@ -657,14 +657,37 @@ def _amplitudes(energy, eps1w, eps2w, chi2, theta, phi, thick, mref):
     flat = lambda a, dt: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=dt), shape)).ravel()
     out = np.empty((4, n), dtype=np.complex128)
     if n:
-        a = dict(energy=flat(energy, np.float64), theta=flat(theta, np.float64), phi=flat(phi, np.float64),
-                 thick=flat(thick, np.float64), eidx=np.arange(n, dtype=np.int64),
-                 eps1w=np.stack([flat(eps1w[k], np.complex128) for k in ("M1", "M2", "M3")]),
-                 eps2w=np.stack([flat(eps2w[k], np.complex128) for k in ("M1", "M2", "M3")]),
-                 chi2=np.stack([flat(chi2[k], np.complex128) for k in CHI2_KEYS]))
+        # The spectra (energy, 6 eps, 18 chi2) usually vary along ONE axis of the broadcast -- the energy axis -- while the
+        # angles vary along the others: keep them as [nE] arrays plus an index per point instead of 25 arrays of n entries.
+        ndim = len(shape)
+        spec = [energy] + [eps1w[k] for k in ("M1", "M2", "M3")] + [eps2w[k] for k in ("M1", "M2", "M3")] + \
+               [chi2[k] for k in CHI2_KEYS]
+        spec_axes = sorted({ax for o in spec for ax in _axes_of(np.shape(o), ndim)})
+        if len(spec_axes) <= 1:
+            nE = shape[spec_axes[0]] if spec_axes else 1
+            line = (nE,) if spec_axes else ()
+
+            def along(o, dt):                       # the operand as a 1-D array along the spectral axis
+                o = np.asarray(o, dtype=dt)
+                return np.ascontiguousarray(np.broadcast_to(o.reshape(-1) if o.size > 1 else o.reshape(()), line)).reshape(nE)
+            idx_shape = [1] * ndim
+            if spec_axes:
+                idx_shape[spec_axes[0]] = nE
+            eidx = flat(np.arange(nE, dtype=np.int64).reshape(idx_shape), np.int64)
+            a = dict(energy=along(energy, np.float64), eidx=eidx,
+                     eps1w=np.stack([along(eps1w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                     eps2w=np.stack([along(eps2w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                     chi2=np.stack([along(chi2[k], np.complex128) for k in CHI2_KEYS]))
+        else:                                       # spectra spread over several axes: one entry per point
+            nE = n
+            a = dict(energy=flat(energy, np.float64), eidx=np.arange(n, dtype=np.int64),
+                     eps1w=np.stack([flat(eps1w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                     eps2w=np.stack([flat(eps2w[k], np.complex128) for k in ("M1", "M2", "M3")]),
+                     chi2=np.stack([flat(chi2[k], np.complex128) for k in CHI2_KEYS]))
+        a.update(theta=flat(theta, np.float64), phi=flat(phi, np.float64), thick=flat(thick, np.float64))
         phys = _physics(None, mref)
         phys.flags = _lib.FLAG_RADIANS
-        p = _lib.Points(n=n, nE=n, energy_eV=a["energy"].ctypes.data, eidx=a["eidx"].ctypes.data,
+        p = _lib.Points(n=n, nE=nE, energy_eV=a["energy"].ctypes.data, eidx=a["eidx"].ctypes.data,
                         theta_deg=a["theta"].ctypes.data, phi_deg=a["phi"].ctypes.data,
                         thick_nm=a["thick"].ctypes.data, eps1w=a["eps1w"].ctypes.data, eps2w=a["eps2w"].ctypes.data,
                         chi2=a["chi2"].ctypes.data, phys=phys)

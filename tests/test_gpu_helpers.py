@@ -57,6 +57,25 @@ def test_rad_amplitudes_match_oracle(shg):
             want = getattr(orc, name)(energy, e1, e2, ch, theta, phi, 10.0, mref, orc.SCIPY_1_18_CONSTANTS)
             assert got.shape == (3, 50)
             np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)), err_msg=name)
+    # spectra along the FIRST axis (compacted to [nE] + an index per point), and spectra spread over two axes (one entry
+    # per point): the same numbers as the oracle's native broadcasting
+    col = lambda d: {k: np.asarray(v)[:, None] for k, v in d.items()}
+    th_row = np.radians(np.array([10.0, 65.0, 89.0]))
+    got = shg.rad_pp(energy[:, None], col(e1), col(e2), col(ch), th_row, phi, 10.0, True)
+    want = orc.rad_pp(energy[:, None], col(e1), col(e2), col(ch), th_row, phi, 10.0, True, orc.SCIPY_1_18_CONSTANTS)
+    assert got.shape == (50, 3)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)))
+    ch2 = dict(ch, xxx=ch["xxx"] * np.array([[1.0], [2.0], [3.0]]))          # chi_xxx varies with the angle axis too
+    got = shg.rad_sp(energy, e1, e2, ch2, theta, phi, 10.0, True)
+    want = orc.rad_sp(energy, e1, e2, ch2, theta, phi, 10.0, True, orc.SCIPY_1_18_CONSTANTS)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)))
+    got = shg.rad_ss(1.7, {k: v[7] for k, v in e1.items()}, {k: v[7] for k, v in e2.items()}, {k: v[7] for k, v in ch.items()},
+                     theta, np.radians(np.arange(0, 360, 45.0)), 10.0, True)   # scalar spectra, angles broadcast
+    want = orc.rad_ss(1.7, {k: v[7] for k, v in e1.items()}, {k: v[7] for k, v in e2.items()},
+                      {k: v[7] for k, v in ch.items()}, theta, np.radians(np.arange(0, 360, 45.0)), 10.0, True,
+                      orc.SCIPY_1_18_CONSTANTS)
+    assert got.shape == (3, 8)
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.max(np.abs(want)))
 
 
 def test_context_options_and_stream_handling():
