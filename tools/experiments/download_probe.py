@@ -13,6 +13,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from shgyield_b200 import _lib  # noqa: E402
 
+if len(sys.argv) > 1:
+    _lib.LIB_PATH = os.path.abspath(sys.argv[1])
 ctx = _lib.context(0)
 n = (2 << 30) // 8
 dev = torch.rand(n, dtype=torch.float64, device="cuda")
@@ -42,4 +44,5 @@ res["reused_pageable_s"] = [round(dl(a), 4) for _ in range(3)]
 p = _lib.pinned_empty((n,))
 res["pinned_s"] = [round(dl(p), 4) for _ in range(3)]
 res["gbs_fresh"] = round(2.147 / min(ts), 1)
+res["lib"] = os.path.basename(_lib.LIB_PATH)
 print(json.dumps(res))
