@@ -142,6 +142,8 @@ SSHG_API int64_t sshg_ctx_launches(sshg_ctx* ctx);        /* kernels launched by
  *   "nseg"          1 .. 16   phi segments per column
  *   "k1_generic"    0 | 1     generic instead of fixed-radius FIR kernels     (default 0)
  *   "k1_bulk"       0 | 1     FIR tiles moved by bulk copies (cp.async.bulk)  (default 1 where alignment allows)
+ *   "pair_copy"     0 | 1     host-output sweeps into page-locked memory copy the sS rows of a (phi, phi + 180)
+ *                             pair once and duplicate them on the host (same bits)   (default 1)
  *   "graphs"        0 | 1     CUDA-graph replay of small point-list calls      (default 1)
  *   "quads"         0 | 1     four rows (phi, 180 - phi, phi + 180, 360 - phi) from one evaluation on grids that
  *                             contain them             (default: fused kernel on short launches and radii > 32)

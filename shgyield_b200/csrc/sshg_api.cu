@@ -163,6 +163,33 @@ int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
     return SSHG_OK;
 }
 
+void sshg_parallel_dup(char* base, size_t pitch, size_t src_off, size_t dst_off, size_t bytes, int64_t ncols) {
+    const size_t total = bytes * (size_t)ncols;
+    if (total == 0) return;
+    int T = copy_threads();
+    if (T > 8) T = 8;                                   // the PCIe copy of the next slab runs meanwhile
+    if (total < ((size_t)4 << 20)) T = 1;
+    const size_t share = ((total + T - 1) / T + 4095) & ~(size_t)4095;
+    auto work = [&](int t) {
+        size_t lo = (size_t)t * share, hi = lo + share < total ? lo + share : total;
+        while (lo < hi) {                               // virtual byte range [lo, hi) of the concatenated blocks
+            const size_t c = lo / bytes, off = lo - c * bytes;
+            const size_t n = (bytes - off < hi - lo) ? bytes - off : hi - lo;
+            memcpy(base + c * pitch + dst_off + off, base + c * pitch + src_off + off, n);
+            lo += n;
+        }
+    };
+    if (T == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(T - 1);
+    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+}
+
 extern "C" {
 
 int sshg_abi_version(void) { return SSHG_ABI_VERSION; }
@@ -206,7 +233,7 @@ int sshg_ctx_create(int device, sshg_ctx** out) {
     }
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
-    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+    ctx->opt = sshg_options{-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
     for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
@@ -280,6 +307,7 @@ const OptionKey kOptions[] = {
     {"graphs", &sshg_options::graphs, 0, 1, -1, -1},
     {"quads", &sshg_options::quads, 0, 1, -1, -1},
     {"k1_bulk", &sshg_options::k1_bulk, 0, 1, -1, -1},
+    {"pair_copy", &sshg_options::pair_copy, 0, 1, -1, -1},
 };
 const OptionKey* find_option(const char* key) {
     for (const OptionKey& o : kOptions)

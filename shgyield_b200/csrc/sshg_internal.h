@@ -42,6 +42,7 @@ struct sshg_options {
     int graphs;         // 0: small calls are launched kernel by kernel instead of replaying a CUDA graph
     int quads;          // 0: no four-row items (phi, 180 - phi, phi + 180, 360 - phi) in the azimuthal sweeps
     int k1_bulk;        // 0: the fixed-radius FIR kernels stage their tiles with per-thread loads / stores (no bulk copies)
+    int pair_copy;      // 0: host-output sweeps copy every row over PCIe (no host-side duplication of the equal sS rows)
 };
 
 // A recorded small call: copy in -> yield_points_kernel -> FIR passes -> copy out, keyed on everything the recorded
@@ -133,6 +134,9 @@ void sshg_gaussian_taps(double sigma, long long r, double* w);
 // are written by several host threads, so that the page faults of first touch and the copy out of the staging buffer run in
 // parallel (the driver's own pageable path is one thread: 3.8 GB/s into fresh memory on the test boxes, this 25-35).
 int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+
+// `ncols` blocks of `bytes` bytes, block c from base + c pitch + src_off to base + c pitch + dst_off, by several host threads.
+void sshg_parallel_dup(char* base, size_t pitch, size_t src_off, size_t dst_off, size_t bytes, int64_t ncols);
 
 // Copies a host array to a scratch slot (or passes a device pointer through).
 int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on_device,

@@ -1001,19 +1001,57 @@ static int yield_impl(sshg_ctx* ctx, const sshg_problem* p, double sigma_out, do
     } else {
         buf[1] = buf[0];
     }
+    // The copy is the bound of a host-output sweep (PCIe), so rows that are known to be equal cross it once: on a grid
+    // with (phi, phi + 180 deg) pairs the sS rows of a pair are the SAME BITS -- sS has odd harmonics only, the kernels
+    // evaluate the pair once and store the value twice (sweep4 / sweep4_quads; K3: harm_item / harm_quad with SS; the
+    // strict re-evaluation and K1 are functions of the row's un-broadened values, which are equal) -- so rows H .. 2 H - 1
+    // of sS stay on the device and host threads duplicate rows 0 .. H - 1 while the next slab is on the wire: one eighth
+    // less PCIe traffic.  The pairing test is the device's (phi_items_build), repeated here on the host array.
+    int64_t Hdup = 0;
+    if (!in_dev && !sparse && opt.pair_copy != 0 && p->nP >= 2) {
+        const int64_t H = p->nP / 2;
+        bool paired = true;
+        for (int64_t j = 0; j < H && paired; ++j) paired = p->phi_deg[j + H] == p->phi_deg[j] + 180.0;
+        if (paired) Hdup = H;
+    }
+    const size_t rowb = (size_t)p->nE * 8;                               // bytes per row
+    const size_t head_b = (size_t)(3 * p->nP + Hdup) * rowb;             // pp, ps, sp and sS rows 0 .. H - 1
+    const size_t tail_off = (size_t)(3 * p->nP + 2 * Hdup) * rowb, tail_b = (size_t)per_col * 8 - tail_off;
     int k = 0;
     bool used[2] = {false, false};
+    int64_t prev_c0 = -1, prev_nc = 0;
+    int prev_k = 0;
+    auto finish_prev = [&]() -> int {          // slab prev has arrived: duplicate its equal rows (the next copy is in flight)
+        if (prev_c0 < 0 || !Hdup) return SSHG_OK;
+        SSHG_CUDA(cudaEventSynchronize(ctx->ev_copied[prev_k]));
+        sshg_parallel_dup((char*)(out + prev_c0 * per_col), (size_t)per_col * 8, (size_t)(3 * p->nP) * rowb,
+                          (size_t)(3 * p->nP + Hdup) * rowb, (size_t)Hdup * rowb, prev_nc);
+        return SSHG_OK;
+    };
     for (int64_t c0 = 0; c0 < cols; c0 += cols_per_slab, k ^= 1) {
         const int64_t nc = (cols - c0 < cols_per_slab) ? cols - c0 : cols_per_slab;
         if (used[k]) SSHG_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied[k], 0));   // buffer drained
         if (int rc = produce(c0, nc, (double*)buf[k])) return rc;
         SSHG_CUDA(cudaEventRecord(ctx->ev_done[k], ctx->stream));
         SSHG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_done[k], 0));
-        SSHG_CUDA(cudaMemcpyAsync(out + c0 * per_col, buf[k], (size_t)nc * per_col * 8, cudaMemcpyDeviceToHost,
-                                  ctx->copy_stream));
+        if (!Hdup) {
+            SSHG_CUDA(cudaMemcpyAsync(out + c0 * per_col, buf[k], (size_t)nc * per_col * 8, cudaMemcpyDeviceToHost,
+                                      ctx->copy_stream));
+        } else {
+            SSHG_CUDA(cudaMemcpy2DAsync(out + c0 * per_col, (size_t)per_col * 8, buf[k], (size_t)per_col * 8, head_b, (size_t)nc,
+                                        cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (tail_b)
+                SSHG_CUDA(cudaMemcpy2DAsync((char*)(out + c0 * per_col) + tail_off, (size_t)per_col * 8, (const char*)buf[k] + tail_off,
+                                            (size_t)per_col * 8, tail_b, (size_t)nc, cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
         SSHG_CUDA(cudaEventRecord(ctx->ev_copied[k], ctx->copy_stream));
         used[k] = true;
+        if (int rc = finish_prev()) return rc;
+        prev_c0 = c0;
+        prev_nc = nc;
+        prev_k = k;
     }
+    if (int rc = finish_prev()) return rc;
     SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
     return SSHG_OK;

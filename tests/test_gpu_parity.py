@@ -319,6 +319,54 @@ def test_grid_device_and_host_paths_agree(grid, consts):
     _lib.pinned_free(host)
 
 
+@pytest.mark.parametrize("sigma_out", [0.0, 5.0])
+@pytest.mark.parametrize("nE,phi,thetas", [
+    (300, np.linspace(0, 360, 721), 6),            # pairs + one un-paired row; several columns per slab
+    (1024, np.arange(0, 360, 1.0), 3),             # pairs only
+    (201, np.linspace(0, 360, 41), 4),             # odd nE, pairs + one un-paired row
+    (128, np.linspace(0, 350, 17), 5),             # no pairing: nothing to duplicate
+    (20000, np.arange(0, 360, 0.5), 3),            # 461 MB per column: one column per slab, three slabs
+])
+def test_host_output_copies_equal_rows_once(grid, consts, nE, phi, thetas, sigma_out):
+    """Host-output sweeps into page-locked memory leave the second sS row of every (phi, phi + 180 deg) pair on the device
+    and duplicate the first on the host (one eighth less PCIe traffic).  The rows are the same bits, so the result is
+    bitwise what the plain copy (option pair_copy = 0), a pageable destination and the device path deliver -- with the
+    pair form, the quad form and the fused / two-pass broadening."""
+    import torch
+    from shgyield_b200 import _lib
+    cfg = _small_cfg(nE, np.linspace(3, 80, thetas), phi, [10.0], seed=11)
+    shape = (thetas, 1, 4, phi.size, nE)
+    ref = None
+    variants = (dict(pair_copy=0), dict()) if nE > 1024 else (dict(pair_copy=0), dict(), dict(quads=1), dict(k3=0) if sigma_out else dict())
+    for opts in variants:
+        host = _lib.pinned_empty(shape)
+        host[...] = -1.0
+        with util.lib_options(**opts):
+            grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma_out, out=host)
+        if ref is None:
+            ref = host.copy()
+            H = phi.size // 2
+            if np.array_equal(phi[H:2 * H], phi[:H] + 180.0):
+                assert np.array_equal(ref[:, :, 3, :H], ref[:, :, 3, H:2 * H])       # the premise
+        elif opts.get("quads") or opts.get("k3") == 0:
+            # other item forms / the two-pass path round differently in the last bits; equal rows stay equal
+            np.testing.assert_allclose(host, ref, rtol=1e-9, atol=1e-12 * np.max(ref))
+            H = phi.size // 2
+            if np.array_equal(phi[H:2 * H], phi[:H] + 180.0):
+                assert np.array_equal(host[:, :, 3, :H], host[:, :, 3, H:2 * H])
+        else:
+            assert np.array_equal(host, ref), opts
+        _lib.pinned_free(host)
+    pageable = grid.yield_grid_host(**cfg, consts=consts, sigma_out=sigma_out)
+    assert np.array_equal(pageable, ref)
+    if nE <= 1024:
+        dev = torch.device("cuda", 0)
+        d = {k: torch.from_numpy(np.ascontiguousarray(v)).to(dev) for k, v in cfg.items()}
+        cube = grid.yield_grid_device(d["energy"], d["theta"], d["phi"], d["thick"], d["eps1w"], d["eps2w"], d["chi2"],
+                                      consts=consts, sigma_out=sigma_out)
+        assert np.array_equal(cube.cpu().numpy(), ref)
+
+
 # ---- the drop-in API against the reference's outputs -------------------------------------------------
 @pytest.mark.parametrize("name,mat,kw", cases.API_CASES, ids=[c[0] for c in cases.API_CASES])
 def test_api_cases_match_reference(shg, spectra, name, mat, kw):
