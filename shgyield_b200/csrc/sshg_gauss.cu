@@ -5,15 +5,19 @@
 // int(4 sigma + 0.5), boundary 'reflect' (d c b a | a b c d | d c b a, repeated when the radius
 // exceeds the signal), sigma <= 1e-15 -> copy.
 //
-// Contiguous signals (the spectra rows and the energy axis of a yield cube) use
-// `gauss_stream_kernel`: a CTA stages a tile + halo in shared memory, each thread then produces
-// R = 9 consecutive outputs from a register window -- per staged sample one conflict-free LDS,
-// one broadcast LDS for the tap entering the window and 9 DFMAs, so the loop is bound by the FP64
-// pipe, not by shared memory.  Results return through shared memory for coalesced stores.
-// Strided signals (blurring a non-contiguous axis of an N-D array, which the reference does when a
-// broadcast call has sigma_out > 0) use `gauss_tiled_kernel` (SciPy's accumulation order: centre
-// tap, then pairs from the farthest inwards); radii whose halo exceeds shared memory use
-// `gauss_direct_kernel`.
+// Contiguous signals (the spectra rows and the energy axis of a yield cube): a CTA stages a tile + halo in shared
+// memory, each thread then produces a run of consecutive outputs from a register window -- per staged sample one
+// conflict-free LDS feeds up to 13 DFMAs.
+//   gauss_fixed_bulk_kernel<RAD>   every radius up to 64: taps in the constant bank, straight-line window, tile + halo
+//                                  and results moved by the bulk-copy engine (cp.async.bulk, one thread issues);
+//                                  FP64-pipe bound from sigma = 5, HBM bound below
+//   gauss_fixed_kernel<RAD>        the same with per-thread staging (rows that are not 16-byte aligned / of odd length)
+//   gauss_stream_kernel            any radius: taps as a rotating register window fed from shared memory
+// Non-contiguous axes of an N-D array (the reference's broad() filters EVERY axis of a broadcast result):
+//   gauss_column_kernel            [positions along the axis + halo] x [32 neighbouring signals] per CTA, the same
+//                                  register-window FIR down the columns
+//   gauss_tiled_kernel / gauss_direct_kernel   narrow trailing axes, very short axes, huge radii (SciPy's accumulation
+//                                  order: centre tap, then pairs from the farthest inwards)
 //
 // HBM traffic: 8 B read + 8 B written per sample (halo re-reads hit L2).
 #include "sshg_internal.h"
