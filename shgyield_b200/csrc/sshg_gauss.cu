@@ -378,9 +378,12 @@ __global__ void __launch_bounds__(GT) gauss_tiled_kernel(const double* __restric
 // (conflict-free: the lanes of a warp read neighbouring words).  The strided kernel above stages 1024 + 2 r samples per
 // CTA with `inner`-strided loads (one 32-byte sector per sample) and fills its CTAs badly on short axes (90 thetas).
 constexpr int CW = 32;              // signals per CTA (one per lane)
-constexpr int CG = 8;               // output groups per CTA (one per warp): CG * SR outputs along the axis
+constexpr int CWARPS = 8;           // warps per CTA
+constexpr int CG = CWARPS;          // output groups per CTA (one per warp): CG * SR = 72 outputs along the axis.  (Two
+                                    // groups per warp halve the share of the halo rows but cost registers and resident
+                                    // CTAs and measured 30 % slower.)
 
-__global__ void __launch_bounds__(CW * CG) gauss_column_kernel(const double* __restrict__ in, double* __restrict__ out,
+__global__ void __launch_bounds__(CW * CWARPS) gauss_column_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                                const double* __restrict__ taps, long long n, long long inner,
                                                                int r, int tiles_a, int tiles_c) {
     extern __shared__ double sm[];
@@ -390,34 +393,35 @@ __global__ void __launch_bounds__(CW * CG) gauss_column_kernel(const double* __r
     double* xs = sm;                               // [span][CW]
     double* wext = sm + (size_t)span_max * CW;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long blk = blockIdx.x;
-    const long long tc = blk % tiles_c, ta = (blk / tiles_c) % tiles_a, o = blk / tiles_c / tiles_a;
-    const long long a0 = ta * TA, col = tc * CW + lane;
+    const unsigned blk = blockIdx.x;               // 32-bit index arithmetic: a 64-bit division costs ~100 instructions
+    const unsigned tc = blk % (unsigned)tiles_c, rest = blk / (unsigned)tiles_c;
+    const unsigned ta = rest % (unsigned)tiles_a, o = rest / (unsigned)tiles_a;
+    const long long a0 = (long long)ta * TA, col = (long long)tc * CW + lane;
     // output groups of this tile that exist (a short axis, or the last tile of a long one): the others stage and compute nothing
     const int groups = (int)((((n - a0 < TA) ? n - a0 : TA) + SR - 1) / SR);
     const int used = groups * SR + 2 * r;          // staged positions that feed an output of this tile
     const int span = used + SR;                    // incl. zero padding (the window of the last output group over-reads)
     const bool colok = col < inner;
-    const double* src = in + o * n * inner;
-    double* dst = out + o * n * inner;
-    for (int j = warp; j < span; j += CG) {
+    const double* src = in + (long long)o * n * inner;
+    double* dst = out + (long long)o * n * inner;
+    for (int j = warp; j < span; j += CWARPS) {
         const long long a = a0 - r + j;
         double v = 0.0;                            // positions beyond n - 1 + r feed no valid output
-        if (j < used && colok && a < n + r) v = src[reflect(a, n) * inner + col];
+        if (j < used && colok && a < n + r) v = src[((a >= 0 && a < n) ? a : reflect(a, n)) * inner + col];
         xs[j * CW + lane] = v;
     }
-    for (int k = threadIdx.x; k < ntap; k += CW * CG) {
+    for (int k = threadIdx.x; k < ntap; k += CW * CWARPS) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
         wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
     __syncthreads();
+    if (warp >= groups) return;
     double acc[SR], wr[SR];
 #pragma unroll
     for (int q = 0; q < SR; ++q) {
         acc[q] = 0.0;
         wr[q] = wext[q];
     }
-    if (warp >= groups) return;
     sshg::fir_window<CW>(xs + (warp * SR) * CW + lane, wext, r, acc, wr);
     if (colok) {
 #pragma unroll
@@ -541,7 +545,7 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         const long long tiles_a = (n + CG * SR - 1) / (CG * SR), tiles_c = (inner_rows + CW - 1) / CW;
         if (outer * tiles_a * tiles_c < (1LL << 31)) {
             SSHG_CUDA(cudaFuncSetAttribute(gauss_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
-            gauss_column_kernel<<<(unsigned)(outer * tiles_a * tiles_c), CW * CG, smem_col, ctx->stream>>>(
+            gauss_column_kernel<<<(unsigned)(outer * tiles_a * tiles_c), CW * CWARPS, smem_col, ctx->stream>>>(
                 din, dout, (const double*)dw, n, inner_rows, (int)r, (int)tiles_a, (int)tiles_c);
             SSHG_CUDA(cudaGetLastError());
             ctx->launches++;
