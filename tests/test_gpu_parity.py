@@ -367,6 +367,26 @@ def test_host_output_copies_equal_rows_once(grid, consts, nE, phi, thetas, sigma
         assert np.array_equal(cube.cpu().numpy(), ref)
 
 
+def test_host_output_equal_rows_on_a_symmetric_material(grid, shg, spectra, consts):
+    """The same on Si(111) (exact azimuthal zeros in sS, strict rows in the broadened sweep): the clamped and the
+    re-evaluated rows of a (phi, phi + 180 deg) pair are the same bits too, so the single copy changes nothing."""
+    import torch
+    from shgyield_b200 import _lib
+    m1, m2, m3, chi2 = cases.si111_material(spectra)
+    energy, theta, phi = np.linspace(0.5, 4.5, 600), np.arange(0, 90, 6.0), np.arange(0, 360, 1.0)
+    eps1w, eps2w, chi_rot, thick = shg._prepare(energy, m1, m2, m3, chi2, 10.0, 0, 0.0, 0.0, "3-layer")
+    args = (energy, theta, phi, np.atleast_1d(thick).astype(float), eps1w, eps2w, chi_rot)
+    dev = torch.device("cuda", 0)
+    dargs = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in args]
+    for sigma_out in (0.0, 5.0):
+        cube = grid.yield_grid_device(*dargs, consts=consts, sigma_out=sigma_out).cpu().numpy()
+        host = _lib.pinned_empty(cube.shape)
+        grid.yield_grid_host(*args, consts=consts, sigma_out=sigma_out, out=host)
+        assert np.array_equal(host, cube), sigma_out
+        assert np.array_equal(cube[:, :, 3, :180], cube[:, :, 3, 180:])
+        _lib.pinned_free(host)
+
+
 # ---- the drop-in API against the reference's outputs -------------------------------------------------
 @pytest.mark.parametrize("name,mat,kw", cases.API_CASES, ids=[c[0] for c in cases.API_CASES])
 def test_api_cases_match_reference(shg, spectra, name, mat, kw):
