@@ -122,7 +122,9 @@ int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
     std::atomic<bool> abort_flag(false);
     std::vector<std::thread> pool;
     pool.reserve(T);
-    for (int t = 0; t < T; ++t) {
+    bool spawned = true;
+    for (int t = 0; t < T && spawned; ++t) {
+      try {
         pool.emplace_back([&, t]() {
             for (size_t i = 0; i < n_chunks; ++i) {
                 while (ready.load(std::memory_order_acquire) <= (long long)i) {
@@ -137,6 +139,16 @@ int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
                 done[i % 2].fetch_add(1, std::memory_order_release);
             }
         });
+      } catch (...) {                                   // no more threads (resource limits): nothing crosses the C ABI
+        spawned = false;
+      }
+    }
+    if (!spawned) {                                     // the workers that did start leave; the driver's own path copies
+        abort_flag.store(true);
+        for (auto& th : pool) th.join();
+        SSHG_CUDA(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        SSHG_CUDA(cudaStreamSynchronize(ctx->stream));
+        return SSHG_OK;
     }
     cudaError_t err = cudaSuccess;
     auto issue = [&](size_t i) {
@@ -185,8 +197,17 @@ void sshg_parallel_dup(char* base, size_t pitch, size_t src_off, size_t dst_off,
     }
     std::vector<std::thread> pool;
     pool.reserve(T - 1);
-    for (int t = 1; t < T; ++t) pool.emplace_back(work, t);
+    int started = 1;                                    // shares [0, started) have a thread (this one takes share 0)
+    for (int t = 1; t < T; ++t) {
+        try {
+            pool.emplace_back(work, t);
+            started = t + 1;
+        } catch (...) {                                 // no more threads: this thread does the remaining shares
+            break;
+        }
+    }
     work(0);
+    for (int t = started; t < T; ++t) work(t);
     for (auto& th : pool) th.join();
 }
 
