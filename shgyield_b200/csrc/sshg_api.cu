@@ -66,9 +66,7 @@ int sshg_stage_in(sshg_ctx* ctx, int slot, const void* src, size_t bytes, int on
     }
     void* d;
     if (int rc = sshg_scratch(ctx, slot, bytes, &d)) return rc;
-    // pageable source: the runtime stages the copy before returning, so the caller's buffer is
-    // free to change as soon as the API call returns.
-    SSHG_CUDA(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (int rc = sshg_copy_in(ctx, d, src, bytes)) return rc;
     *dev = d;
     return SSHG_OK;
 }
@@ -172,6 +170,71 @@ int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t byt
     if (err != cudaSuccess) abort_flag.store(true);
     for (auto& th : pool) th.join();
     if (err != cudaSuccess) return sshg_cuda_fail(err, "staged device-to-host copy", __FILE__, __LINE__);
+    return SSHG_OK;
+}
+
+// Host -> device copy of a large pageable array (sshg_stage_in): host threads fill the page-locked staging buffers, the
+// copy engine drains them -- the mirror image of sshg_copy_out.  Queued work on ctx->stream that reads `dst_dev` must be
+// issued after this returns (the last chunk is synchronised).
+int sshg_copy_in(sshg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes) {
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, src_host) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    (void)cudaGetLastError();
+    bool staged = !pinned && bytes >= STAGED_MIN;
+    if (staged && !ctx->stage[0]) {
+        for (int k = 0; k < 2 && staged; ++k) {
+            if (cudaMallocHost(&ctx->stage[k], STAGE_BYTES) != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (k == 1) cudaFreeHost(ctx->stage[0]);
+                ctx->stage[0] = ctx->stage[1] = nullptr;
+                staged = false;
+            }
+        }
+        if (staged) ctx->stage_bytes = STAGE_BYTES;
+    }
+    if (!staged) {
+        // pageable source: the runtime stages the copy before returning, so the caller's buffer is free to change as soon
+        // as the API call returns
+        SSHG_CUDA(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        return SSHG_OK;
+    }
+    // the device buffer may still be read by work queued on the compute stream: the copies wait for it; this call returns
+    // when the last copy has landed
+    SSHG_CUDA(cudaEventRecord(ctx->ev_switch, ctx->stream));
+    SSHG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_switch, 0));
+    const size_t n_chunks = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    int T = copy_threads();
+    for (size_t i = 0; i < n_chunks; ++i) {
+        const size_t len = i + 1 < n_chunks ? STAGE_BYTES : bytes - i * STAGE_BYTES;
+        if (i >= 2) SSHG_CUDA(cudaEventSynchronize(ctx->ev_copied[i % 2]));       // the engine has drained this buffer
+        // fill stage[i % 2] with T threads (blocking), then hand it to the copy engine; the other buffer is on the wire
+        {
+            const size_t per = ((len + T - 1) / T + 4095) & ~(size_t)4095;
+            char* dstb = (char*)ctx->stage[i % 2];
+            const char* srcb = (const char*)src_host + i * STAGE_BYTES;
+            auto work = [&](int t) {
+                const size_t lo = (size_t)t * per, hi = lo + per < len ? lo + per : len;
+                if (lo < hi) memcpy(dstb + lo, srcb + lo, hi - lo);
+            };
+            std::vector<std::thread> pool;
+            pool.reserve(T - 1);
+            int started = 1;
+            for (int t = 1; t < T; ++t) {
+                try {
+                    pool.emplace_back(work, t);
+                    started = t + 1;
+                } catch (...) {
+                    break;
+                }
+            }
+            work(0);
+            for (int t = started; t < T; ++t) work(t);
+            for (auto& th : pool) th.join();
+        }
+        SSHG_CUDA(cudaMemcpyAsync((char*)dst_dev + i * STAGE_BYTES, ctx->stage[i % 2], len, cudaMemcpyHostToDevice, ctx->copy_stream));
+        SSHG_CUDA(cudaEventRecord(ctx->ev_copied[i % 2], ctx->copy_stream));
+    }
+    SSHG_CUDA(cudaStreamSynchronize(ctx->copy_stream));                           // staging buffers free, data on the device
     return SSHG_OK;
 }
 

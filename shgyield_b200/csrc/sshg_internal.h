@@ -135,6 +135,10 @@ void sshg_gaussian_taps(double sigma, long long r, double* w);
 // parallel (the driver's own pageable path is one thread: 3.8 GB/s into fresh memory on the test boxes, this 25-35).
 int sshg_copy_out(sshg_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 
+// Host -> device copy ordered with ctx->stream; large pageable sources go through the page-locked staging buffers, filled
+// by several host threads.  The source may be changed as soon as the call returns.
+int sshg_copy_in(sshg_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes);
+
 // `ncols` blocks of `bytes` bytes, block c from base + c pitch + src_off to base + c pitch + dst_off, by several host threads.
 void sshg_parallel_dup(char* base, size_t pitch, size_t src_off, size_t dst_off, size_t bytes, int64_t ncols);
 
