@@ -383,10 +383,16 @@ constexpr int CG = CWARPS;          // output groups per CTA (one per warp): CG 
                                     // groups per warp halve the share of the halo rows but cost registers and resident
                                     // CTAs and measured 30 % slower.)
 
+// BULK: the rows of a tile (256 contiguous bytes each, `inner` doubles apart) are fetched by the bulk-copy engine, one
+// cp.async.bulk per row issued by one thread each, all in flight at once, completion on an mbarrier -- instead of a
+// load / store pair per element through the registers of a warp that handles its rows four at a time.  Needs 16-byte
+// aligned rows (even `inner`, aligned base); tiles at the ragged end of the signals take the per-thread loads.
+template <bool BULK>
 __global__ void __launch_bounds__(CW * CWARPS) gauss_column_kernel(const double* __restrict__ in, double* __restrict__ out,
                                                                const double* __restrict__ taps, long long n, long long inner,
                                                                int r, int tiles_a, int tiles_c) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(128) double sm[];
+    __shared__ __align__(8) unsigned long long bar;
     constexpr int TA = CG * SR;                    // outputs along the axis per CTA
     const int span_max = TA + 2 * r + SR;          // row count the shared-memory layout is planned for
     const int ntap = 2 * r + 1 + 3 * SR;
@@ -404,17 +410,55 @@ __global__ void __launch_bounds__(CW * CWARPS) gauss_column_kernel(const double*
     const bool colok = col < inner;
     const double* src = in + (long long)o * n * inner;
     double* dst = out + (long long)o * n * inner;
-    for (int j = warp; j < span; j += CWARPS) {
-        const long long a = a0 - r + j;
-        double v = 0.0;                            // positions beyond n - 1 + r feed no valid output
-        if (j < used && colok && a < n + r) v = src[((a >= 0 && a < n) ? a : reflect(a, n)) * inner + col];
-        xs[j * CW + lane] = v;
+    const bool full_tile = (long long)tc * CW + CW <= inner;       // CTA-uniform
+    if (BULK && full_tile) {
+        // rows that exist: j < used and a0 - r + j < n + r
+        const long long lim = n + r - (a0 - r);
+        const int rows_in = (int)(lim < used ? lim : used);
+        const unsigned bar_a = smem_addr(&bar);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"((unsigned)rows_in * CW * 8u) : "memory");
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < span; j += CW * CWARPS) {
+            if (j < rows_in) {
+                const long long a = a0 - r + j;
+                const long long ra = (a >= 0 && a < n) ? a : reflect(a, n);
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 smem_addr(xs + j * CW)),
+                             "l"(src + ra * inner + (long long)tc * CW), "r"((unsigned)(CW * 8)), "r"(bar_a)
+                             : "memory");
+            } else {                               // positions beyond n - 1 + r feed no valid output
+#pragma unroll 4
+                for (int c = 0; c < CW; ++c) xs[j * CW + c] = 0.0;
+            }
+        }
+    } else {
+        for (int j = warp; j < span; j += CWARPS) {
+            const long long a = a0 - r + j;
+            double v = 0.0;                        // positions beyond n - 1 + r feed no valid output
+            if (j < used && colok && a < n + r) v = src[((a >= 0 && a < n) ? a : reflect(a, n)) * inner + col];
+            xs[j * CW + lane] = v;
+        }
     }
     for (int k = threadIdx.x; k < ntap; k += CW * CWARPS) {
         const int j = k - (SR - 1);                // index into the full symmetric kernel
         wext[k] = (j >= 0 && j <= 2 * r) ? taps[j <= r ? r - j : j - r] : 0.0;
     }
     __syncthreads();
+    if (BULK && full_tile) {
+        const unsigned bar_a = smem_addr(&bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(done)
+                : "r"(bar_a)
+                : "memory");
+        }
+    }
     if (warp >= groups) return;
     double acc[SR], wr[SR];
 #pragma unroll
@@ -544,9 +588,16 @@ int sshg_gauss_device_ex(sshg_ctx* ctx, const double* din, double* dout, int64_t
         const long long inner_rows = inner_c;
         const long long tiles_a = (n + CG * SR - 1) / (CG * SR), tiles_c = (inner_rows + CW - 1) / CW;
         if (outer * tiles_a * tiles_c < (1LL << 31)) {
-            SSHG_CUDA(cudaFuncSetAttribute(gauss_column_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
-            gauss_column_kernel<<<(unsigned)(outer * tiles_a * tiles_c), CW * CWARPS, smem_col, ctx->stream>>>(
-                din, dout, (const double*)dw, n, inner_rows, (int)r, (int)tiles_a, (int)tiles_c);
+            const bool bulk = ctx->opt.k1_bulk != 0 && inner_rows % 2 == 0 && (uintptr_t)din % 16 == 0;
+            if (bulk) {
+                SSHG_CUDA(cudaFuncSetAttribute(gauss_column_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+                gauss_column_kernel<true><<<(unsigned)(outer * tiles_a * tiles_c), CW * CWARPS, smem_col, ctx->stream>>>(
+                    din, dout, (const double*)dw, n, inner_rows, (int)r, (int)tiles_a, (int)tiles_c);
+            } else {
+                SSHG_CUDA(cudaFuncSetAttribute(gauss_column_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_CAP));
+                gauss_column_kernel<false><<<(unsigned)(outer * tiles_a * tiles_c), CW * CWARPS, smem_col, ctx->stream>>>(
+                    din, dout, (const double*)dw, n, inner_rows, (int)r, (int)tiles_a, (int)tiles_c);
+            }
             SSHG_CUDA(cudaGetLastError());
             ctx->launches++;
             return SSHG_OK;
