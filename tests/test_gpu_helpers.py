@@ -234,3 +234,35 @@ def test_to_host_and_download_match_torch():
     assert np.array_equal(pin, t.cpu().numpy().ravel())
     _lib.pinned_free(pin)
     assert grid.to_host(torch.empty((0, 4), dtype=torch.float64, device="cuda")).shape == (0, 4)
+
+
+def test_yield_broadcast_rejects_bad_layouts():
+    """sshg_yield_broadcast validates shape and layout before anything is launched: SSHG_EINVAL with a message."""
+    import ctypes as C
+    from shgyield_b200 import _lib, grid, shg
+    from shgyield_b200.synthetic import synthetic_spectra
+    ctx = _lib.context(0)
+    energy, eps1w, eps2w, chi = synthetic_spectra(40, seed=1)
+    theta, phi, thick = np.array([10.0, 20.0, 30.0]), np.arange(0, 360, 45.0), np.array([5.0])
+    keep = []
+    p = grid._problem(energy, theta, phi, thick, eps1w, eps2w, chi, shg._physics(None), None, None, keep)
+    total = 8 * 3 * 40
+    outs = [np.empty(total) for _ in range(4)]
+    ptrs = (C.c_void_p * 4)(*[o.ctypes.data for o in outs])
+
+    def call(strides, shape, sigma=0.0):
+        st = (C.c_int64 * 4)(*strides)
+        shp = (C.c_int64 * len(shape))(*shape)
+        return ctx.lib.sshg_yield_broadcast(ctx.handle, C.byref(p), st, float(sigma), len(shape), shp, ptrs)
+    good = (40, 0, total, 3 * 40)                                        # [phi][theta][E]
+    assert call(good, (8, 3, 40)) == _lib.SSHG_OK
+    ref = [o.copy() for o in outs]
+    cube = grid.yield_grid_host(energy, theta, phi, thick, eps1w, eps2w, chi)        # [T, 1, 4, P, E]
+    for k in range(4):
+        assert np.array_equal(ref[k].reshape(8, 3, 40), np.transpose(cube[:, 0, k], (1, 0, 2)))
+    assert call(good, (8, 3, 41)) == _lib.SSHG_EINVAL                     # shape does not match the grid
+    assert call((40, 0, total - 1, 120), (8, 3, 40)) == _lib.SSHG_EINVAL   # polarisation stride
+    assert call((40, 0, total, 121), (8, 3, 40)) == _lib.SSHG_EINVAL       # phi rows would run past the array
+    assert call((-40, 0, total, 120), (8, 3, 40)) == _lib.SSHG_EINVAL
+    assert call(good, (8, 3, 40), sigma=-1.0) == _lib.SSHG_EINVAL
+    assert b"sigma_out" in ctx.lib.sshg_last_error()
